@@ -1,0 +1,129 @@
+/* phe_b200.h -- C ABI of libphe_b200.so: the B200-native replacement for the arithmetic the reference's
+ * pybind11 glue calls in ipcl:: (intel/pailliercryptolib, not vendored in /root/reference).
+ *
+ * Every entry point cites the reference interface it replaces (file:line under /root/reference).
+ * Conventions:
+ *   - all big numbers are little-endian arrays of uint32_t words at a fixed stride (the layout
+ *     BN2bytes/pyByte2BN produce, src/ipcl_python/bindings/ipcl_bindings.cpp:100-138, zero padded);
+ *   - for a key of n_words = bits/32 words: plaintext stride = n_words, ciphertext stride = 2*n_words;
+ *   - results are canonical residues in [0, modulus);
+ *   - every function returns 0 on success, non-zero on error; phe_last_error() gives the message of the
+ *     last error on the calling thread (the pybind11 shim maps it to RuntimeError, as ipcl's ERROR_CHECK does);
+ *   - *_dev variants take CUDA device pointers and a cudaStream_t (as void*), enqueue only, and never
+ *     synchronise; the plain variants take host pointers and include H2D/D2H.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef PHE_B200_H_
+#define PHE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct phe_pubkey phe_pubkey;   /* replaces ipcl::PublicKey  (ipcl_bindings_classes.cpp:14-91)  */
+typedef struct phe_privkey phe_privkey; /* replaces ipcl::PrivateKey (ipcl_bindings_classes.cpp:93-163) */
+
+const char* phe_last_error(void);
+const char* phe_version(void);
+
+/* ipcl::initializeContext / terminateContext / isQATRunning (ipcl_bindings.hpp:27-35): here the "context"
+ * is the CUDA device.  phe_device_count() == 0 means no usable GPU. */
+int phe_device_count(void);
+int phe_set_device(int device);
+int phe_get_device(void);
+
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches evidence). */
+unsigned long long phe_kernel_launches(void);
+
+/* ---- keys ---------------------------------------------------------------------------------------------- */
+
+/* ipcl::PublicKey(n, bits, enableDJN) and PublicKey::create(n, bits, hs, randbits)
+ * (ipcl_bindings_classes.cpp:16-27; ipcl_bindings.cpp:76-98 setIpclPubKey).
+ *   n: n_words words.  bits: key length (n_words*32 >= bits).
+ *   djn != 0: DJN scheme.  hs == NULL: draw x and compute hs = (-x^2 mod n)^n mod n^2 (enableDJN);
+ *             hs != NULL: 2*n_words words, randbits as given (create()).  randbits <= 0 means bits/2.
+ * Builds n^2, the Montgomery constants and (DJN) the fixed-base comb table on the current device. */
+int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const uint32_t* hs, int randbits,
+                      phe_pubkey** out);
+void phe_pubkey_destroy(phe_pubkey* pk);
+int phe_pubkey_bits(const phe_pubkey* pk);
+int phe_pubkey_n_words(const phe_pubkey* pk);
+int phe_pubkey_is_djn(const phe_pubkey* pk);
+int phe_pubkey_randbits(const phe_pubkey* pk);
+int phe_pubkey_get_n(const phe_pubkey* pk, uint32_t* n_out);            /* n_words   (PublicKey::getN)   */
+int phe_pubkey_get_nsquare(const phe_pubkey* pk, uint32_t* nsq_out);    /* 2*n_words (PublicKey::getNSQ) */
+int phe_pubkey_get_hs(const phe_pubkey* pk, uint32_t* hs_out);          /* 2*n_words (PublicKey::getHS)  */
+
+/* ipcl::PrivateKey(pk, p, q) (ipcl_bindings_classes.cpp:96-101).  Checks p*q == n, orders p < q, derives
+ * p^2, q^2, hp, hq, p^-1 mod q and their Montgomery forms. */
+int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, const uint32_t* q, int q_words,
+                       phe_privkey** out);
+void phe_privkey_destroy(phe_privkey* sk);
+int phe_privkey_get_p(const phe_privkey* sk, uint32_t* p_out);  /* n_words/2 words (PrivateKey::getP) */
+int phe_privkey_get_q(const phe_privkey* sk, uint32_t* q_out);  /* n_words/2 words (PrivateKey::getQ) */
+
+/* ipcl::generateKeypair(n_length, enable_DJN) (ipcl_bindings.cpp:12-15): host prime search.
+ * p, q = 3 (mod 4), top two bits set, gcd(p-1, q-1) = 2.  Outputs: n (bits/32 words), p, q (bits/64 words). */
+int phe_keygen(int bits, uint32_t* n_out, uint32_t* p_out, uint32_t* q_out);
+
+/* ---- the hot path, host buffers -------------------------------------------------------------------------- */
+
+/* ipcl::PublicKey::encrypt(PlainText, make_secure) (ipcl_bindings_classes.cpp:53-60).
+ *   m: count x n_words.  ct_out: count x 2*n_words.
+ *   make_secure == 0: ct = 1 + m n.
+ *   make_secure != 0: ct = (1 + m n) * obf; r == NULL draws r from the OS CSPRNG, otherwise r is
+ *   count x r_words (DJN: r < 2^randbits, r_words*32 >= randbits; classic: r in [1, n-1], r_words = n_words)
+ *   -- the deterministic hook used by the parity tests. */
+int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uint32_t* r, int r_words,
+                int make_secure, uint32_t* ct_out);
+
+/* ipcl::PublicKey::applyObfuscator(vector<BigNumber>&) (ipcl_bindings_classes.cpp:71-83): ct *= obf(r). */
+int phe_obfuscate(const phe_pubkey* pk, uint32_t* ct_inout, size_t count, const uint32_t* r, int r_words);
+
+/* ipcl::PrivateKey::decrypt(CipherText) -> decryptCRT (ipcl_bindings_classes.cpp:127-133).
+ *   ct: count x 2*n_words.  m_out: count x n_words. */
+int phe_decrypt(const phe_privkey* sk, const uint32_t* ct, size_t count, uint32_t* m_out);
+
+/* ipcl::CipherText::operator+(CipherText) -> raw_add (ipcl_bindings_classes.cpp:318-321):
+ *   out[i] = a[i] * b[i] mod n^2; nb is na or 1 (broadcast). */
+int phe_add(const phe_pubkey* pk, const uint32_t* a, size_t na, const uint32_t* b, size_t nb, uint32_t* out);
+
+/* ipcl::CipherText::operator*(PlainText) -> raw_mul -> ipcl::modExp (ipcl_bindings_classes.cpp:324-325):
+ *   out[i] = ct[i] ^ e[i] mod n^2; e: ne x e_words (e_words <= n_words), ne is n or 1 (broadcast). */
+int phe_mul(const phe_pubkey* pk, const uint32_t* ct, size_t n, const uint32_t* e, int e_words, size_t ne,
+            uint32_t* out);
+
+/* ipcl::modExp(base, exp, mod) element-wise with one shared odd modulus:
+ *   out[i] = base[i] ^ exp[i] mod modulus; all operands `words` words; supports moduli up to 6144 bits. */
+int phe_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulus, int words, size_t count,
+               uint32_t* out);
+
+/* ---- the hot path, device buffers (zero-copy chaining, multi-GPU gather) ----------------------------------- */
+
+int phe_encrypt_dev(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
+                    uint32_t* d_ct_out, void* stream);
+int phe_decrypt_dev(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m_out, void* stream);
+int phe_add_dev(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint32_t* d_b, size_t nb,
+                uint32_t* d_out, void* stream);
+/* exp_bits: upper bound on the bit length of every exponent (uniform loop count); 0 means e_words*32. */
+int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
+                int exp_bits, uint32_t* d_out, void* stream);
+
+/* ---- host-only helpers exposed for the CPU test-suite (no GPU needed) --------------------------------------- */
+
+/* Montgomery context block exactly as uploaded to the device for modulus `mod` (mod_words words) in the
+ * lane-group shape (L, TPI): 5 entries x KP words: N, R^2 mod N, R mod N, 1, extra (extra = x_words words, already
+ * reduced).  Returns KP (>0) or <0 on error.  out may be NULL to query KP.  n0inv_out = -N^-1 mod 2^28. */
+int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, uint32_t* out, uint32_t* n0inv_out);
+/* base^exp mod modulus on the host bignum (key-setup arithmetic), words words each. */
+int phe_host_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulus, int words, uint32_t* out);
+/* Shape selection: writes L, TPI for a modulus of `mod_bits` bits; returns 0 or error. */
+int phe_host_shape_for_bits(int mod_bits, int* L_out, int* TPI_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHE_B200_H_ */

@@ -1,0 +1,89 @@
+"""Builds libphe_b200.so (CUDA kernels + C ABI) in-tree for sm_100a with nvcc, and the pybind11 shim.
+
+python -m pailliercryptolib_python_b200.build [--force]
+"""
+import concurrent.futures
+import os
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIBDIR, "libphe_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--cudart", "static",
+]
+CU_SOURCES = ["phe_api.cu", "shape_37_1.cu", "shape_37_2.cu", "shape_37_4.cu", "shape_28_2.cu", "shape_28_4.cu", "shape_28_8.cu"]
+HEADERS = ["mont28.cuh", "paillier_items.cuh", "phe_kernels.cuh", "phe_launch.cuh", "phe_shapes.hpp", "hostbn.hpp",
+           os.path.join("..", "..", "include", "phe_b200.h")]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def build_lib(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    jobs = []
+    objs = []
+    for src in CU_SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _newer(o, [s] + hdrs):
+            jobs.append([NVCC] + NVCC_FLAGS + ["-c", s, "-o", o])
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for out in ex.map(_run, jobs):
+                if verbose and out.strip():
+                    print(out)
+    if force or jobs or _newer(LIB, objs):
+        _run([NVCC, "-shared", "--cudart", "static", "-o", LIB] + objs)
+    return LIB
+
+
+def build_bindings(force=False):
+    """pybind11 shim ipcl_bindings (thin: forwards to the C ABI)."""
+    src = os.path.join(CSRC, "ipcl_bindings.cpp")
+    if not os.path.exists(src):
+        return None
+    import pybind11
+
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    out = os.path.join(HERE, "bindings", "ipcl_bindings" + ext)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if force or _newer(out, [src, os.path.join(HERE, "..", "include", "phe_b200.h")]):
+        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
+               "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+               "-I", os.path.join(HERE, "..", "include"), src, "-o", out,
+               "-L", LIBDIR, "-lphe_b200", "-Wl,-rpath,$ORIGIN/../lib"]
+        _run(cmd)
+    return out
+
+
+def build_all(force=False, verbose=False):
+    lib = build_lib(force, verbose)
+    build_bindings(force)
+    return lib
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose=True))

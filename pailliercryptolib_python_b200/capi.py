@@ -1,0 +1,238 @@
+"""ctypes view of the C ABI (include/phe_b200.h).  Used by the tests, bench.py and the numpy fast path.
+
+The library has no CPU fallback: compute calls raise RuntimeError when no CUDA device is present.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libphe_b200.so")
+
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_lib = None
+
+# every symbol include/phe_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "phe_last_error", "phe_version", "phe_device_count", "phe_set_device", "phe_get_device", "phe_kernel_launches",
+    "phe_pubkey_create", "phe_pubkey_destroy", "phe_pubkey_bits", "phe_pubkey_n_words", "phe_pubkey_is_djn",
+    "phe_pubkey_randbits", "phe_pubkey_get_n", "phe_pubkey_get_nsquare", "phe_pubkey_get_hs",
+    "phe_privkey_create", "phe_privkey_destroy", "phe_privkey_get_p", "phe_privkey_get_q", "phe_keygen",
+    "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
+    "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
+    "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libphe_b200.so is not built (run `python -m pailliercryptolib_python_b200.build`); "
+                "there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        L.phe_last_error.restype = ctypes.c_char_p
+        L.phe_version.restype = ctypes.c_char_p
+        L.phe_kernel_launches.restype = ctypes.c_ulonglong
+        for name in ("phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
+                     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev", "phe_pubkey_create",
+                     "phe_privkey_create", "phe_keygen"):
+            getattr(L, name).restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s: %s" % (what, lib().phe_last_error().decode()))
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):  # raw device pointer
+        return ctypes.cast(ctypes.c_void_p(a), _u32p)
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"], "need a C-contiguous uint32 array"
+    return a.ctypes.data_as(_u32p)
+
+
+def int_to_words(v, nwords):
+    return np.frombuffer(int(v).to_bytes(4 * nwords, "little"), dtype="<u4").copy()
+
+
+def words_to_int(w):
+    return int.from_bytes(np.ascontiguousarray(w, dtype="<u4").tobytes(), "little")
+
+
+def ints_to_array(vals, nwords):
+    buf = b"".join(int(v).to_bytes(4 * nwords, "little") for v in vals)
+    return np.frombuffer(buf, dtype="<u4").reshape(len(vals), nwords).copy()
+
+
+def array_to_ints(arr):
+    arr = np.ascontiguousarray(arr, dtype="<u4")
+    n = arr.shape[1] * 4
+    raw = arr.tobytes()
+    return [int.from_bytes(raw[i * n:(i + 1) * n], "little") for i in range(arr.shape[0])]
+
+
+def device_count():
+    return lib().phe_device_count()
+
+
+def kernel_launches():
+    return int(lib().phe_kernel_launches())
+
+
+class PubKey:
+    """phe_pubkey handle.  n: Python int; hs: optional Python int (DJN generator)."""
+
+    def __init__(self, n, bits, djn=True, hs=None, randbits=0):
+        self.n_words = (bits + 31) // 32
+        self.bits = bits
+        self.n = int(n)
+        h = ctypes.c_void_p()
+        hs_arr = int_to_words(hs, 2 * self.n_words) if hs is not None else None
+        _check(lib().phe_pubkey_create(_p(int_to_words(n, self.n_words)), self.n_words, bits, int(bool(djn)),
+                                       _p(hs_arr), int(randbits), ctypes.byref(h)), "phe_pubkey_create")
+        self.h = h
+        self.djn = bool(djn)
+        self.randbits = lib().phe_pubkey_randbits(self.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().phe_pubkey_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def hs(self):
+        out = np.zeros(2 * self.n_words, dtype=np.uint32)
+        _check(lib().phe_pubkey_get_hs(self.h, _p(out)), "phe_pubkey_get_hs")
+        return words_to_int(out)
+
+    @property
+    def nsquare(self):
+        out = np.zeros(2 * self.n_words, dtype=np.uint32)
+        _check(lib().phe_pubkey_get_nsquare(self.h, _p(out)), "phe_pubkey_get_nsquare")
+        return words_to_int(out)
+
+    # ---- host-buffer ops on packed arrays -------------------------------------------------------------
+    def encrypt(self, m, r=None, make_secure=True):
+        m = np.ascontiguousarray(m, dtype=np.uint32).reshape(-1, self.n_words)
+        out = np.empty((m.shape[0], 2 * self.n_words), dtype=np.uint32)
+        rw = 0
+        if r is not None:
+            r = np.ascontiguousarray(r, dtype=np.uint32)
+            r = r.reshape(m.shape[0], -1)
+            rw = r.shape[1]
+        _check(lib().phe_encrypt(self.h, _p(m), ctypes.c_size_t(m.shape[0]), _p(r), rw, int(bool(make_secure)),
+                                 _p(out)), "phe_encrypt")
+        return out
+
+    def obfuscate(self, ct, r=None):
+        ct = np.ascontiguousarray(ct, dtype=np.uint32).reshape(-1, 2 * self.n_words).copy()
+        rw = 0
+        if r is not None:
+            r = np.ascontiguousarray(r, dtype=np.uint32).reshape(ct.shape[0], -1)
+            rw = r.shape[1]
+        _check(lib().phe_obfuscate(self.h, _p(ct), ctypes.c_size_t(ct.shape[0]), _p(r), rw), "phe_obfuscate")
+        return ct
+
+    def add(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, 2 * self.n_words)
+        b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, 2 * self.n_words)
+        out = np.empty_like(a)
+        _check(lib().phe_add(self.h, _p(a), ctypes.c_size_t(a.shape[0]), _p(b), ctypes.c_size_t(b.shape[0]), _p(out)),
+               "phe_add")
+        return out
+
+    def mul(self, ct, e):
+        ct = np.ascontiguousarray(ct, dtype=np.uint32).reshape(-1, 2 * self.n_words)
+        e = np.ascontiguousarray(e, dtype=np.uint32)
+        if e.ndim == 1:
+            e = e.reshape(1, -1)
+        out = np.empty_like(ct)
+        _check(lib().phe_mul(self.h, _p(ct), ctypes.c_size_t(ct.shape[0]), _p(e), e.shape[1],
+                             ctypes.c_size_t(e.shape[0]), _p(out)), "phe_mul")
+        return out
+
+    # ---- device-pointer ops (ints are raw CUDA pointers, e.g. torch.Tensor.data_ptr()) ------------------
+    def encrypt_dev(self, d_m, count, d_r, r_words, d_out, stream=0):
+        _check(lib().phe_encrypt_dev(self.h, _p(d_m), ctypes.c_size_t(count), _p(d_r) if d_r else None, r_words,
+                                     _p(d_out), ctypes.c_void_p(stream)), "phe_encrypt_dev")
+
+    def add_dev(self, d_a, na, d_b, nb, d_out, stream=0):
+        _check(lib().phe_add_dev(self.h, _p(d_a), ctypes.c_size_t(na), _p(d_b), ctypes.c_size_t(nb), _p(d_out),
+                                 ctypes.c_void_p(stream)), "phe_add_dev")
+
+    def mul_dev(self, d_ct, n, d_e, e_words, ne, exp_bits, d_out, stream=0):
+        _check(lib().phe_mul_dev(self.h, _p(d_ct), ctypes.c_size_t(n), _p(d_e), e_words, ctypes.c_size_t(ne),
+                                 exp_bits, _p(d_out), ctypes.c_void_p(stream)), "phe_mul_dev")
+
+
+class PrivKey:
+    def __init__(self, pk, p, q):
+        self.pk = pk
+        hw = pk.n_words // 2
+        h = ctypes.c_void_p()
+        _check(lib().phe_privkey_create(pk.h, _p(int_to_words(p, hw)), hw, _p(int_to_words(q, hw)), hw,
+                                        ctypes.byref(h)), "phe_privkey_create")
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().phe_privkey_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def decrypt(self, ct):
+        ct = np.ascontiguousarray(ct, dtype=np.uint32).reshape(-1, 2 * self.pk.n_words)
+        out = np.empty((ct.shape[0], self.pk.n_words), dtype=np.uint32)
+        _check(lib().phe_decrypt(self.h, _p(ct), ctypes.c_size_t(ct.shape[0]), _p(out)), "phe_decrypt")
+        return out
+
+    def decrypt_dev(self, d_ct, count, d_out, stream=0):
+        _check(lib().phe_decrypt_dev(self.h, _p(d_ct), ctypes.c_size_t(count), _p(d_out), ctypes.c_void_p(stream)),
+               "phe_decrypt_dev")
+
+
+def modexp(base, exp, modulus, words):
+    """Generic element-wise modexp (ipcl::modExp): lists of ints -> list of ints."""
+    b = ints_to_array(base, words)
+    e = ints_to_array(exp, words)
+    out = np.empty_like(b)
+    _check(lib().phe_modexp(_p(b), _p(e), _p(int_to_words(modulus, words)), words, ctypes.c_size_t(len(base)),
+                            _p(out)), "phe_modexp")
+    return array_to_ints(out)
+
+
+def keygen(bits):
+    n = np.zeros(bits // 32, dtype=np.uint32)
+    p = np.zeros(bits // 64, dtype=np.uint32)
+    q = np.zeros(bits // 64, dtype=np.uint32)
+    _check(lib().phe_keygen(bits, _p(n), _p(p), _p(q)), "phe_keygen")
+    return words_to_int(n), words_to_int(p), words_to_int(q)
+
+
+def host_mont_block(modulus, mod_words, L, TPI):
+    kp = lib().phe_host_mont_block(_p(int_to_words(modulus, mod_words)), mod_words, L, TPI, None, None)
+    if kp <= 0:
+        raise RuntimeError(lib().phe_last_error().decode())
+    out = np.zeros(5 * kp, dtype=np.uint32)
+    n0 = ctypes.c_uint32()
+    lib().phe_host_mont_block(_p(int_to_words(modulus, mod_words)), mod_words, L, TPI, _p(out), ctypes.byref(n0))
+    return out.reshape(5, kp), n0.value
+
+
+def host_modexp(base, exp, modulus, words):
+    out = np.zeros(words, dtype=np.uint32)
+    _check(lib().phe_host_modexp(_p(int_to_words(base, words)), _p(int_to_words(exp, words)),
+                                 _p(int_to_words(modulus, words)), words, _p(out)), "phe_host_modexp")
+    return words_to_int(out)

@@ -42,7 +42,9 @@ PHE_HD void store_words(uint32_t* out, int nwords, const uint32_t (&x)[L], uint3
   Env::sync();
   limbs_to_smem<L, TPI, Env>(stage, x);
   Env::sync();
-  for (int v = Env::lane(); v < nwords; v += TPI) out[v] = word_from_smem_limbs<L, TPI>(stage, v);
+  if (out) {   // null: this group is a padding duplicate of the last item (block-uniform loops), skip the store
+    for (int v = Env::lane(); v < nwords; v += TPI) out[v] = word_from_smem_limbs<L, TPI>(stage, v);
+  }
   Env::sync();
 }
 
@@ -352,7 +354,12 @@ PHE_HD void item_dec_tail(const uint32_t* up_w, const uint32_t* uq_w, int u_word
   }
   // here: mod = q, x = m_q
   const uint32_t neg = sub_exact<L, TPI, Env>(x, mp);                // m_q - m_p
-  if (neg) add_exact<L, TPI, Env>(x, mod);                           // + q (wraps back into range)
+  {                                                                  // + q if negative (branch-free: shuffles inside)
+    uint32_t addend[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) addend[j] = neg ? mod[j] : 0u;
+    add_exact<L, TPI, Env>(x, addend);                               // wraps back into range
+  }
   montmul<L, TPI, Env>(x, x, cst + DT_PINVM * KP, mod, n0invs[1]);
   canonicalize<L, TPI, Env>(x, mod);                                 // h in [0, q)
   load_entry<L, TPI, Env>(mod, cst + DT_N * KP);

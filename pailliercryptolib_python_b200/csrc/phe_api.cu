@@ -1,0 +1,756 @@
+// phe_api.cu -- C ABI (include/phe_b200.h) over the sm_100a kernels.  Host side = per-key setup with hostbn,
+// buffer management, launches.  There is no CPU fallback for the compute entry points.
+#include <sys/random.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/phe_b200.h"
+#include "hostbn.hpp"
+#include "phe_kernels.cuh"
+#include "phe_shapes.hpp"
+
+using hbn::BN;
+
+namespace phe {
+extern const ShapeOps g_ops_37_1, g_ops_37_2, g_ops_37_4, g_ops_28_2, g_ops_28_4, g_ops_28_8;
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_counter() { return g_launches.load(); }
+const ShapeOps* shape_ops(int L, int TPI) {
+  const ShapeOps* all[] = {&g_ops_37_1, &g_ops_37_2, &g_ops_37_4, &g_ops_28_2, &g_ops_28_4, &g_ops_28_8};
+  for (auto* o : all) if (o->L == L && o->TPI == TPI) return o;
+  return nullptr;
+}
+}  // namespace phe
+
+using namespace phe;
+
+namespace {
+
+thread_local std::string t_err;
+int fail(const std::string& m) { t_err = m; return 1; }
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+#define PHE_TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
+
+// smallest shape whose capacity covers mod_bits + 8 (R >= 2^8 N keeps every Montgomery product < 2N)
+const ShapeOps* shape_for_bits(int mod_bits) {
+  static const int order[][2] = {{37, 1}, {28, 2}, {37, 2}, {28, 4}, {37, 4}, {28, 8}};
+  for (auto& s : order) {
+    const ShapeOps* o = shape_ops(s[0], s[1]);
+    if (o && o->capacity_bits >= mod_bits + 8) return o;
+  }
+  return nullptr;
+}
+
+// value -> padded limb entry [TPI][LP]
+void to_entry(const BN& v, const ShapeOps* o, uint32_t* out) {
+  const int LP = o->KP / o->TPI;
+  std::memset(out, 0, (size_t)o->KP * 4);
+  if (v.bits() > (size_t)o->capacity_bits) throw std::runtime_error("to_entry: value exceeds shape capacity");
+  for (int g = 0; g < o->L * o->TPI; ++g) {
+    const size_t bit = (size_t)g * LW;
+    const size_t wi = bit >> 5, sh = bit & 31;
+    uint64_t two = 0;
+    if (wi < v.w.size()) two = v.w[wi];
+    if (wi + 1 < v.w.size()) two |= (uint64_t)v.w[wi + 1] << 32;
+    out[(g / o->L) * LP + (g % o->L)] = (uint32_t)(two >> sh) & LMASK;
+  }
+}
+
+// Montgomery block (ME_COUNT entries) for modulus N with context-specific extra value
+std::vector<uint32_t> mont_block(const BN& N, const BN& extra, const ShapeOps* o, uint32_t* n0inv) {
+  if (!N.is_odd()) throw std::runtime_error("modulus must be odd");
+  std::vector<uint32_t> blk((size_t)ME_COUNT * o->KP);
+  const BN R = hbn::shl(BN(1), o->capacity_bits);
+  const BN Rm = hbn::mod(R, N);
+  to_entry(N, o, &blk[(size_t)ME_N * o->KP]);
+  to_entry(hbn::mulmod(Rm, Rm, N), o, &blk[(size_t)ME_R2 * o->KP]);
+  to_entry(Rm, o, &blk[(size_t)ME_ONEM * o->KP]);
+  to_entry(BN(1), o, &blk[(size_t)ME_ONE * o->KP]);
+  to_entry(extra, o, &blk[(size_t)ME_X0 * o->KP]);
+  *n0inv = hbn::neg_inv28(N.low());
+  return blk;
+}
+
+struct DevBuf {
+  uint32_t* p = nullptr;
+  size_t words = 0;
+  int ensure(size_t w) {
+    if (w <= words) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; words = 0;
+    // grow geometrically to avoid re-allocating on slowly increasing batch sizes
+    size_t want = w + w / 8;
+    cudaError_t e = cudaMalloc(&p, want * 4);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, w * 4); want = w; }
+    if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    words = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; words = 0; }
+};
+
+int upload(DevBuf& b, const std::vector<uint32_t>& v) {
+  PHE_TRY(b.ensure(v.size()));
+  CUDA_TRY(cudaMemcpy(b.p, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int random_words(uint32_t* out, size_t words) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(out);
+  size_t left = words * 4;
+  while (left) {
+    const ssize_t got = getrandom(p, left > (1u << 24) ? (1u << 24) : left, 0);
+    if (got <= 0) return fail("getrandom failed");
+    p += got; left -= (size_t)got;
+  }
+  return 0;
+}
+
+BN random_bits(size_t bits) {
+  std::vector<uint32_t> w((bits + 31) / 32);
+  if (random_words(w.data(), w.size())) throw std::runtime_error("getrandom failed");
+  if (bits & 31) w.back() &= (1u << (bits & 31)) - 1u;
+  return BN::from_words(w.data(), w.size());
+}
+
+int max_bits_host(const uint32_t* e, int e_words, size_t n) {
+  int best = 1;
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t* row = e + i * (size_t)e_words;
+    for (int j = e_words - 1; j >= 0; --j)
+      if (row[j]) { const int b = 32 * j + 32 - __builtin_clz(row[j]); if (b > best) best = b; break; }
+  }
+  return best;
+}
+
+int window_for_bits(int ebits) { return ebits <= 8 ? 1 : (ebits <= 160 ? 3 : 5); }
+
+}  // namespace
+
+struct phe_pubkey {
+  int bits = 0, n_words = 0, djn = 0, randbits = 0, device = 0;
+  BN n, nsq, hs;
+  const ShapeOps* ops = nullptr;  // shape of the n^2 context
+  MontCtxArgs ctx{};
+  DevBuf d_ctx, d_comb;
+  int nwin = 0;
+  mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_tbl;  // op workspaces
+  mutable std::mutex mu;
+};
+
+struct phe_privkey {
+  const phe_pubkey* pk = nullptr;
+  BN p, q;
+  const ShapeOps* ops = nullptr;  // shape of the x^2 contexts (also used for p, q, n in the tail)
+  DevBuf d_ctx[2], d_exp[2], d_tail;
+  MontCtxArgs ctx[2]{};
+  int ebits[2] = {0, 0};
+  int hw = 0;  // words of x^2 (= n_words)
+  uint32_t n0invs[3] = {0, 0, 0};
+  mutable DevBuf ws_in, ws_out, ws_mont[2], ws_u[2], ws_tbl;
+  mutable std::mutex mu;
+};
+
+namespace {
+
+// shared exponent / generic powm launch on the n^2 context of a public key
+int launch_powm(const ShapeOps* o, const MontCtxArgs& ctx, const uint32_t* d_base, int base_words, const uint32_t* d_e,
+                int e_words, size_t e_stride, int ebits, uint32_t* d_out, int out_words, int count, DevBuf& tbl,
+                cudaStream_t s) {
+  const int win = window_for_bits(ebits);
+  PHE_TRY(tbl.ensure(o->powm_tbl_words(win, 1, count)));
+  PowmArgs p{};
+  p.base_w = d_base; p.base_words = base_words;
+  p.base_mont[0] = p.base_mont[1] = nullptr;
+  p.e_w[0] = d_e; p.e_w[1] = nullptr;
+  p.e_words = e_words; p.e_stride = e_stride;
+  p.ebits[0] = ebits; p.ebits[1] = 0;
+  p.out_w[0] = d_out; p.out_w[1] = nullptr;
+  p.out_words = out_words; p.count = count;
+  p.ctx[0] = ctx; p.ctx[1] = ctx;
+  p.tbl = tbl.p;
+  CUDA_TRY(o->powm(win, p, 1, s));
+  return 0;
+}
+
+constexpr size_t CHUNK = 1u << 20;  // items per launch (bounds scratch and int indexing)
+
+// obf[i] for r[i] into d_obf (canonical ciphertext words).  d_r: device, r_words per item.
+int obfuscators_dev(const phe_pubkey* pk, const uint32_t* d_r, int r_words, size_t count, uint32_t* d_obf,
+                    cudaStream_t s) {
+  const int cw = 2 * pk->n_words;
+  if (pk->djn) {
+    // comb kernel with m = 0 gives (1 + 0) * obf
+    PHE_TRY(pk->ws_d.ensure((size_t)pk->n_words));
+    CUDA_TRY(cudaMemsetAsync(pk->ws_d.p, 0, (size_t)pk->n_words * 4, s));
+    for (size_t off = 0; off < count; off += CHUNK) {
+      const int c = (int)std::min(CHUNK, count - off);
+      EncCombArgs a{};
+      a.m_w = pk->ws_d.p; a.m_words = 0;   // zero words: m = 0 for every item
+      a.r_w = d_r + off * r_words; a.r_words = r_words; a.nwin = pk->nwin;
+      a.out_w = d_obf + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = pk->d_comb.p;
+      CUDA_TRY(pk->ops->encrypt_comb(a, s));
+    }
+    return 0;
+  }
+  // classic: r^n mod n^2, shared exponent n
+  PHE_TRY(pk->ws_d.ensure((size_t)pk->n_words));
+  std::vector<uint32_t> nw(pk->n_words);
+  pk->n.to_words(nw.data(), nw.size());
+  CUDA_TRY(cudaMemcpyAsync(pk->ws_d.p, nw.data(), nw.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // nw is a stack-lifetime staging buffer
+  for (size_t off = 0; off < count; off += CHUNK) {
+    const int c = (int)std::min(CHUNK, count - off);
+    PHE_TRY(launch_powm(pk->ops, pk->ctx, d_r + off * r_words, r_words, pk->ws_d.p, pk->n_words, 0,
+                        (int)pk->n.bits(), d_obf + off * cw, cw, c, pk->ws_tbl, s));
+  }
+  return 0;
+}
+
+int make_r_host(const phe_pubkey* pk, size_t count, std::vector<uint32_t>& r, int* r_words) {
+  if (pk->djn) {
+    *r_words = (pk->randbits + 31) / 32;
+    r.resize(count * (size_t)*r_words);
+    PHE_TRY(random_words(r.data(), r.size()));
+    if (pk->randbits & 31) {
+      const uint32_t mask = (1u << (pk->randbits & 31)) - 1u;
+      for (size_t i = 0; i < count; ++i) r[i * *r_words + *r_words - 1] &= mask;
+    }
+    return 0;
+  }
+  // classic: r = random(bits) mod (n - 1) + 1   (ipcl getNormalObfuscator)
+  *r_words = pk->n_words;
+  r.assign(count * (size_t)pk->n_words, 0);
+  const BN nm1 = hbn::sub(pk->n, BN(1));
+  for (size_t i = 0; i < count; ++i) {
+    const BN v = hbn::add(hbn::mod(random_bits(pk->bits), nm1), BN(1));
+    v.to_words(&r[i * pk->n_words], pk->n_words);
+  }
+  return 0;
+}
+
+int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
+                     uint32_t* d_ct, cudaStream_t s) {
+  const int cw = 2 * pk->n_words;
+  if (count == 0) return 0;
+  if (!d_r || pk->djn) {
+    for (size_t off = 0; off < count; off += CHUNK) {
+      const int c = (int)std::min(CHUNK, count - off);
+      EncCombArgs a{};
+      a.m_w = d_m + off * pk->n_words; a.m_words = pk->n_words;
+      a.r_w = d_r ? d_r + off * r_words : nullptr; a.r_words = r_words; a.nwin = pk->nwin;
+      a.out_w = d_ct + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = pk->d_comb.p;
+      if (d_r && (size_t)r_words * 32 < (size_t)pk->nwin * 8) return fail("phe_encrypt: r_words too small for randbits");
+      CUDA_TRY(pk->ops->encrypt_comb(a, s));
+    }
+    return 0;
+  }
+  // classic scheme: obf = r^n, then ct = (1 + m n) * obf
+  PHE_TRY(pk->ws_c.ensure(std::min(count, CHUNK) * cw));
+  for (size_t off = 0; off < count; off += CHUNK) {
+    const int c = (int)std::min(CHUNK, count - off);
+    PHE_TRY(obfuscators_dev(pk, d_r + off * r_words, r_words, c, pk->ws_c.p, s));
+    EncFinishArgs f{};
+    f.m_w = d_m + off * pk->n_words; f.m_words = pk->n_words; f.obf_w = pk->ws_c.p;
+    f.out_w = d_ct + off * cw; f.out_words = cw; f.count = c; f.ctx = pk->ctx;
+    CUDA_TRY(pk->ops->encrypt_finish(f, s));
+  }
+  return 0;
+}
+
+int add_dev_impl(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint32_t* d_b, size_t nb, uint32_t* d_out,
+                 cudaStream_t s) {
+  if (nb != na && nb != 1) return fail("phe_add: size mismatch (b must have na or 1 elements)");
+  const int cw = 2 * pk->n_words;
+  for (size_t off = 0; off < na; off += CHUNK) {
+    const int c = (int)std::min(CHUNK, na - off);
+    const bool bc = (nb == 1 && na != 1);
+    CUDA_TRY(pk->ops->modmul(d_a + off * cw, bc ? d_b : d_b + off * cw, bc ? 0 : (size_t)cw, d_out + off * cw, cw, c,
+                             pk->ctx, s));
+  }
+  return 0;
+}
+
+int mul_dev_impl(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
+                 int exp_bits, uint32_t* d_out, cudaStream_t s) {
+  if (ne != n && ne != 1) return fail("phe_mul: size mismatch (exponents must have n or 1 elements)");
+  if (e_words < 1) return fail("phe_mul: e_words must be >= 1");
+  const int cw = 2 * pk->n_words;
+  int ebits = exp_bits > 0 ? exp_bits : e_words * 32;
+  if (ebits > e_words * 32) ebits = e_words * 32;
+  const bool bc = (ne == 1 && n != 1);
+  for (size_t off = 0; off < n; off += CHUNK) {
+    const int c = (int)std::min(CHUNK, n - off);
+    PHE_TRY(launch_powm(pk->ops, pk->ctx, d_ct + off * cw, cw, bc ? d_e : d_e + off * e_words, e_words,
+                        bc ? 0 : (size_t)e_words, ebits, d_out + off * cw, cw, c, pk->ws_tbl, s));
+  }
+  return 0;
+}
+
+int decrypt_dev_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m, cudaStream_t s) {
+  const ShapeOps* o = sk->ops;
+  const int hw = sk->hw, cw = 2 * hw;
+  const size_t chunk = std::min(count, CHUNK);
+  for (int y = 0; y < 2; ++y) {
+    PHE_TRY(sk->ws_mont[y].ensure(chunk * o->KP));
+    PHE_TRY(sk->ws_u[y].ensure(chunk * hw));
+  }
+  PHE_TRY(sk->ws_tbl.ensure(o->powm_tbl_words(5, 2, (int)chunk)));
+  for (size_t off = 0; off < count; off += CHUNK) {
+    const int c = (int)std::min(CHUNK, count - off);
+    DecPrepArgs dp{};
+    dp.c_w = d_ct + off * cw; dp.hw = hw; dp.count = c;
+    for (int y = 0; y < 2; ++y) { dp.out[y] = sk->ws_mont[y].p; dp.ctx[y] = sk->ctx[y]; }
+    CUDA_TRY(o->dec_prep(dp, s));
+    PowmArgs p{};
+    p.base_w = nullptr; p.base_words = 0; p.e_words = hw; p.e_stride = 0; p.out_words = hw; p.count = c;
+    for (int y = 0; y < 2; ++y) {
+      p.base_mont[y] = sk->ws_mont[y].p; p.e_w[y] = sk->d_exp[y].p; p.ebits[y] = sk->ebits[y];
+      p.out_w[y] = sk->ws_u[y].p; p.ctx[y] = sk->ctx[y];
+    }
+    p.tbl = sk->ws_tbl.p;
+    CUDA_TRY(o->powm(5, p, 2, s));
+    DecTailArgs t{};
+    t.up_w = sk->ws_u[0].p; t.uq_w = sk->ws_u[1].p; t.u_words = hw; t.m_w = d_m + off * hw; t.m_words = hw;
+    t.count = c; t.cst = sk->d_tail.p;
+    for (int i = 0; i < 3; ++i) t.n0invs[i] = sk->n0invs[i];
+    CUDA_TRY(o->dec_tail(t, s));
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* phe_last_error(void) { return t_err.c_str(); }
+const char* phe_version(void) { return "phe_b200 0.1 (sm_100a, radix-2^28 IMAD.WIDE Montgomery)"; }
+
+int phe_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int phe_set_device(int device) { CUDA_TRY(cudaSetDevice(device)); return 0; }
+int phe_get_device(void) { int d = -1; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; } return d; }
+unsigned long long phe_kernel_launches(void) { return launch_counter(); }
+
+int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const uint32_t* hs, int randbits,
+                      phe_pubkey** out) {
+  try {
+    if (!n || !out || n_words <= 0) return fail("phe_pubkey_create: bad arguments");
+    if (phe_device_count() <= 0) return fail("phe_pubkey_create: no CUDA device (there is no CPU fallback)");
+    BN N = BN::from_words(n, n_words);
+    if (!N.is_odd() || N.bits() < 16) return fail("phe_pubkey_create: n must be odd and non-trivial");
+    if ((int)N.bits() > bits) bits = (int)N.bits();
+    if (n_words * 32 < bits) return fail("phe_pubkey_create: n_words too small");
+    std::unique_ptr<phe_pubkey> pk(new phe_pubkey);
+    pk->bits = bits; pk->n_words = n_words; pk->djn = djn ? 1 : 0; pk->n = N; pk->nsq = hbn::mul(N, N);
+    CUDA_TRY(cudaGetDevice(&pk->device));
+    pk->ops = shape_for_bits(2 * n_words * 32);
+    if (!pk->ops) return fail("phe_pubkey_create: key too large (n^2 up to 6144 bits supported)");
+    const BN R = hbn::shl(BN(1), pk->ops->capacity_bits);
+    std::vector<uint32_t> blk = mont_block(pk->nsq, hbn::mulmod(N, hbn::mod(R, pk->nsq), pk->nsq), pk->ops, &pk->ctx.n0inv);
+    PHE_TRY(upload(pk->d_ctx, blk));
+    pk->ctx.entries = pk->d_ctx.p;
+    if (djn) {
+      pk->randbits = randbits > 0 ? randbits : bits / 2;
+      if (hs) {
+        pk->hs = BN::from_words(hs, 2 * (size_t)n_words);
+        if (!(pk->hs < pk->nsq)) return fail("phe_pubkey_create: hs >= n^2");
+      } else {
+        // ipcl PublicKey::enableDJN: x random with gcd(x, n) = 1, hs = (-x^2 mod n)^n mod n^2
+        BN x, g;
+        do { x = random_bits((size_t)bits + 128); g = hbn::gcd(x, N); } while (!(g == BN(1)));
+        const BN xm = hbn::mod(x, N);
+        const BN h = hbn::sub(N, hbn::mulmod(xm, xm, N));
+        // the modexp runs on the device (generic powm on the n^2 context)
+        const int cw = 2 * n_words;
+        std::vector<uint32_t> hb(cw), nw(n_words), res(cw);
+        h.to_words(hb.data(), cw); N.to_words(nw.data(), n_words);
+        DevBuf db, de, dout;
+        PHE_TRY(upload(db, hb)); PHE_TRY(upload(de, nw)); PHE_TRY(dout.ensure(cw));
+        int rc = launch_powm(pk->ops, pk->ctx, db.p, cw, de.p, n_words, 0, (int)N.bits(), dout.p, cw, 1, pk->ws_tbl, 0);
+        if (!rc && cudaMemcpy(res.data(), dout.p, (size_t)cw * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("hs readback failed");
+        db.release(); de.release(); dout.release();
+        if (rc) return rc;
+        pk->hs = BN::from_words(res.data(), cw);
+      }
+      // fixed-base comb table
+      pk->nwin = (pk->randbits + 7) / 8;
+      PHE_TRY(pk->d_comb.ensure((size_t)pk->nwin * 256 * pk->ops->KP));
+      std::vector<uint32_t> hsw(2 * (size_t)n_words);
+      pk->hs.to_words(hsw.data(), hsw.size());
+      DevBuf dhs;
+      PHE_TRY(upload(dhs, hsw));
+      CombArgs ca{};
+      ca.hs_w = dhs.p; ca.hs_words = 2 * n_words; ca.nwin = pk->nwin; ca.comb = pk->d_comb.p; ca.ctx = pk->ctx;
+      cudaError_t e = pk->ops->comb_build(ca, 0);
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
+      dhs.release();
+      if (e != cudaSuccess) return fail(std::string("comb table build: ") + cudaGetErrorString(e));
+    }
+    *out = pk.release();
+    return 0;
+  } catch (const std::exception& e) { return fail(std::string("phe_pubkey_create: ") + e.what()); }
+}
+
+void phe_pubkey_destroy(phe_pubkey* pk) {
+  if (!pk) return;
+  for (DevBuf* b : {&pk->d_ctx, &pk->d_comb, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
+  delete pk;
+}
+int phe_pubkey_bits(const phe_pubkey* pk) { return pk ? pk->bits : -1; }
+int phe_pubkey_n_words(const phe_pubkey* pk) { return pk ? pk->n_words : -1; }
+int phe_pubkey_is_djn(const phe_pubkey* pk) { return pk ? pk->djn : -1; }
+int phe_pubkey_randbits(const phe_pubkey* pk) { return pk ? pk->randbits : -1; }
+int phe_pubkey_get_n(const phe_pubkey* pk, uint32_t* o) { if (!pk || !o) return fail("null"); pk->n.to_words(o, pk->n_words); return 0; }
+int phe_pubkey_get_nsquare(const phe_pubkey* pk, uint32_t* o) { if (!pk || !o) return fail("null"); pk->nsq.to_words(o, 2 * (size_t)pk->n_words); return 0; }
+int phe_pubkey_get_hs(const phe_pubkey* pk, uint32_t* o) { if (!pk || !o) return fail("null"); pk->hs.to_words(o, 2 * (size_t)pk->n_words); return 0; }
+
+int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, const uint32_t* q, int q_words,
+                       phe_privkey** out) {
+  try {
+    if (!pk || !p || !q || !out) return fail("phe_privkey_create: bad arguments");
+    BN P = BN::from_words(p, p_words), Q = BN::from_words(q, q_words);
+    if (!(hbn::mul(P, Q) == pk->n)) return fail("phe_privkey_create: p * q != n");
+    if (Q < P) std::swap(P, Q);
+    std::unique_ptr<phe_privkey> sk(new phe_privkey);
+    sk->pk = pk; sk->p = P; sk->q = Q; sk->hw = pk->n_words;
+    sk->ops = shape_for_bits(pk->n_words * 32);
+    if (!sk->ops) return fail("phe_privkey_create: unsupported key size");
+    const ShapeOps* o = sk->ops;
+    const BN R = hbn::shl(BN(1), o->capacity_bits);
+    const BN g = hbn::add(pk->n, BN(1));
+    BN hx[2];
+    const BN X[2] = {P, Q};
+    for (int y = 0; y < 2; ++y) {
+      const BN X2 = hbn::mul(X[y], X[y]);
+      const BN Rm = hbn::mod(R, X2);
+      // extra = 2^(32 hw) * R^2 mod x^2  (high half of the ciphertext in the pre-reduction)
+      const BN k2 = hbn::mulmod(hbn::mod(hbn::shl(BN(1), 32 * (size_t)sk->hw), X2), hbn::mulmod(Rm, Rm, X2), X2);
+      std::vector<uint32_t> blk = mont_block(X2, k2, o, &sk->ctx[y].n0inv);
+      PHE_TRY(upload(sk->d_ctx[y], blk));
+      sk->ctx[y].entries = sk->d_ctx[y].p;
+      const BN e = hbn::sub(X[y], BN(1));
+      std::vector<uint32_t> ew(sk->hw);
+      e.to_words(ew.data(), ew.size());
+      PHE_TRY(upload(sk->d_exp[y], ew));
+      sk->ebits[y] = (int)e.bits();
+      // hx = (L_x(g^(x-1) mod x^2))^-1 mod x
+      const BN u = hbn::modexp(hbn::mod(g, X2), e, X2);
+      const BN Lx = hbn::div(hbn::sub(u, BN(1)), X[y]);
+      hx[y] = hbn::modinv_prime(hbn::mod(Lx, X[y]), X[y]);
+    }
+    const BN pinv = hbn::modinv_prime(hbn::mod(P, Q), Q);
+    std::vector<uint32_t> tail((size_t)DT_COUNT * o->KP);
+    auto put = [&](int idx, const BN& v) { to_entry(v, o, &tail[(size_t)idx * o->KP]); };
+    put(DT_P, P); put(DT_Q, Q); put(DT_N, pk->n);
+    put(DT_HPM, hbn::mulmod(hx[0], hbn::mod(R, P), P));
+    put(DT_HQM, hbn::mulmod(hx[1], hbn::mod(R, Q), Q));
+    put(DT_PINVM, hbn::mulmod(pinv, hbn::mod(R, Q), Q));
+    put(DT_PMN, hbn::mulmod(P, hbn::mod(R, pk->n), pk->n));
+    put(DT_ONE, BN(1));
+    PHE_TRY(upload(sk->d_tail, tail));
+    sk->n0invs[0] = hbn::neg_inv28(P.low());
+    sk->n0invs[1] = hbn::neg_inv28(Q.low());
+    sk->n0invs[2] = hbn::neg_inv28(pk->n.low());
+    *out = sk.release();
+    return 0;
+  } catch (const std::exception& e) { return fail(std::string("phe_privkey_create: ") + e.what()); }
+}
+
+void phe_privkey_destroy(phe_privkey* sk) {
+  if (!sk) return;
+  for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_tail, &sk->ws_in, &sk->ws_out,
+                    &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl}) b->release();
+  delete sk;
+}
+int phe_privkey_get_p(const phe_privkey* sk, uint32_t* o) { if (!sk || !o) return fail("null"); sk->p.to_words(o, sk->hw / 2); return 0; }
+int phe_privkey_get_q(const phe_privkey* sk, uint32_t* o) { if (!sk || !o) return fail("null"); sk->q.to_words(o, sk->hw / 2); return 0; }
+
+// ---- key generation (host) ---------------------------------------------------------------------------
+static bool probably_prime(const BN& c) {
+  static std::vector<uint32_t> small;
+  if (small.empty()) {
+    std::vector<bool> sieve(8192, true);
+    for (uint32_t i = 2; i < 8192; ++i) if (sieve[i]) { small.push_back(i); for (uint32_t j = i * i; j < 8192; j += i) sieve[j] = false; }
+  }
+  for (uint32_t sp : small) {
+    uint64_t rem = 0;
+    for (size_t i = c.w.size(); i-- > 0;) rem = ((rem << 32) | c.w[i]) % sp;
+    if (rem == 0) return c == BN(sp);
+  }
+  const BN cm1 = hbn::sub(c, BN(1));
+  size_t s = 0;
+  while (!cm1.bit(s)) ++s;
+  const BN d = hbn::shr(cm1, s);
+  for (int round = 0; round < 12; ++round) {
+    BN a = hbn::add(hbn::mod(random_bits(c.bits() + 64), hbn::sub(c, BN(3))), BN(2));  // [2, c-2]
+    BN x = hbn::modexp(a, d, c);
+    if (x == BN(1) || x == cm1) continue;
+    bool witness = true;
+    for (size_t i = 1; i < s; ++i) {
+      x = hbn::mulmod(x, x, c);
+      if (x == cm1) { witness = false; break; }
+    }
+    if (witness) return false;
+  }
+  return true;
+}
+
+static BN random_prime_3mod4(int bits) {
+  for (;;) {
+    BN c = random_bits(bits);
+    std::vector<uint32_t> w((bits + 31) / 32, 0);
+    c.to_words(w.data(), w.size());
+    w[0] |= 3u;
+    const int top = bits - 1, top2 = bits - 2;
+    w[top >> 5] |= 1u << (top & 31);
+    w[top2 >> 5] |= 1u << (top2 & 31);
+    c = BN::from_words(w.data(), w.size());
+    if (probably_prime(c)) return c;
+  }
+}
+
+int phe_keygen(int bits, uint32_t* n_out, uint32_t* p_out, uint32_t* q_out) {
+  try {
+    if (bits < 64 || bits > 3072 || (bits % 64) != 0) return fail("phe_keygen: bits must be a multiple of 64 in [64, 3072]");
+    if (!n_out || !p_out || !q_out) return fail("phe_keygen: null output");
+    for (;;) {
+      const BN p = random_prime_3mod4(bits / 2), q = random_prime_3mod4(bits / 2);
+      if (p == q) continue;
+      if (!(hbn::gcd(hbn::sub(p, BN(1)), hbn::sub(q, BN(1))) == BN(2))) continue;
+      const BN n = hbn::mul(p, q);
+      if ((int)n.bits() != bits) continue;
+      n.to_words(n_out, bits / 32);
+      p.to_words(p_out, bits / 64);
+      q.to_words(q_out, bits / 64);
+      return 0;
+    }
+  } catch (const std::exception& e) { return fail(std::string("phe_keygen: ") + e.what()); }
+}
+
+// ---- device-buffer entry points --------------------------------------------------------------------------
+int phe_encrypt_dev(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
+                    uint32_t* d_ct_out, void* stream) {
+  if (!pk || !d_m || !d_ct_out) return fail("phe_encrypt_dev: null argument");
+  std::lock_guard<std::mutex> lk(pk->mu);
+  return encrypt_dev_impl(pk, d_m, count, d_r, r_words, d_ct_out, (cudaStream_t)stream);
+}
+int phe_decrypt_dev(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m_out, void* stream) {
+  if (!sk || !d_ct || !d_m_out) return fail("phe_decrypt_dev: null argument");
+  if (count == 0) return 0;
+  std::lock_guard<std::mutex> lk(sk->mu);
+  return decrypt_dev_impl(sk, d_ct, count, d_m_out, (cudaStream_t)stream);
+}
+int phe_add_dev(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint32_t* d_b, size_t nb, uint32_t* d_out,
+                void* stream) {
+  if (!pk || !d_a || !d_b || !d_out) return fail("phe_add_dev: null argument");
+  if (na == 0) return 0;
+  std::lock_guard<std::mutex> lk(pk->mu);
+  return add_dev_impl(pk, d_a, na, d_b, nb, d_out, (cudaStream_t)stream);
+}
+int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
+                int exp_bits, uint32_t* d_out, void* stream) {
+  if (!pk || !d_ct || !d_e || !d_out) return fail("phe_mul_dev: null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(pk->mu);
+  return mul_dev_impl(pk, d_ct, n, d_e, e_words, ne, exp_bits, d_out, (cudaStream_t)stream);
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------------------------
+int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uint32_t* r, int r_words,
+                int make_secure, uint32_t* ct_out) {
+  try {
+    if (!pk || !m || !ct_out) return fail("phe_encrypt: null argument");
+    if (count == 0) return 0;
+    std::lock_guard<std::mutex> lk(pk->mu);
+    CUDA_TRY(cudaSetDevice(pk->device));
+    const int cw = 2 * pk->n_words;
+    std::vector<uint32_t> rgen;
+    if (make_secure && !r) { PHE_TRY(make_r_host(pk, count, rgen, &r_words)); r = rgen.data(); }
+    if (!make_secure) r = nullptr;
+    PHE_TRY(pk->ws_a.ensure(count * pk->n_words));
+    PHE_TRY(pk->ws_b.ensure(count * cw));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, m, count * pk->n_words * 4, cudaMemcpyHostToDevice, 0));
+    const uint32_t* d_r = nullptr;
+    DevBuf rbuf;
+    if (r) {
+      PHE_TRY(rbuf.ensure(count * (size_t)r_words));
+      cudaError_t e = cudaMemcpyAsync(rbuf.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice, 0);
+      if (e != cudaSuccess) { rbuf.release(); return fail(std::string("H2D r: ") + cudaGetErrorString(e)); }
+      d_r = rbuf.p;
+    }
+    int rc = encrypt_dev_impl(pk, pk->ws_a.p, count, d_r, r_words, pk->ws_b.p, 0);
+    if (!rc) {
+      cudaError_t e = cudaMemcpy(ct_out, pk->ws_b.p, count * cw * 4, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = fail(std::string("phe_encrypt D2H: ") + cudaGetErrorString(e));
+    }
+    rbuf.release();
+    return rc;
+  } catch (const std::exception& e) { return fail(std::string("phe_encrypt: ") + e.what()); }
+}
+
+int phe_obfuscate(const phe_pubkey* pk, uint32_t* ct, size_t count, const uint32_t* r, int r_words) {
+  try {
+    if (!pk || !ct) return fail("phe_obfuscate: null argument");
+    if (count == 0) return 0;
+    std::lock_guard<std::mutex> lk(pk->mu);
+    CUDA_TRY(cudaSetDevice(pk->device));
+    const int cw = 2 * pk->n_words;
+    std::vector<uint32_t> rgen;
+    if (!r) { PHE_TRY(make_r_host(pk, count, rgen, &r_words)); r = rgen.data(); }
+    DevBuf rbuf, obuf;
+    PHE_TRY(rbuf.ensure(count * (size_t)r_words));
+    PHE_TRY(obuf.ensure(count * cw));
+    PHE_TRY(pk->ws_b.ensure(count * cw));
+    int rc = 0;
+    if (cudaMemcpy(rbuf.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(pk->ws_b.p, ct, count * cw * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("phe_obfuscate: H2D failed");
+    if (!rc) rc = obfuscators_dev(pk, rbuf.p, r_words, count, obuf.p, 0);
+    if (!rc) rc = add_dev_impl(pk, pk->ws_b.p, count, obuf.p, count, pk->ws_b.p, 0);
+    if (!rc && cudaMemcpy(ct, pk->ws_b.p, count * cw * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("phe_obfuscate: D2H failed");
+    rbuf.release(); obuf.release();
+    return rc;
+  } catch (const std::exception& e) { return fail(std::string("phe_obfuscate: ") + e.what()); }
+}
+
+int phe_decrypt(const phe_privkey* sk, const uint32_t* ct, size_t count, uint32_t* m_out) {
+  try {
+    if (!sk || !ct || !m_out) return fail("phe_decrypt: null argument");
+    if (count == 0) return 0;
+    std::lock_guard<std::mutex> lk(sk->mu);
+    CUDA_TRY(cudaSetDevice(sk->pk->device));
+    const int hw = sk->hw, cw = 2 * hw;
+    PHE_TRY(sk->ws_in.ensure(count * cw));
+    PHE_TRY(sk->ws_out.ensure(count * hw));
+    CUDA_TRY(cudaMemcpyAsync(sk->ws_in.p, ct, count * cw * 4, cudaMemcpyHostToDevice, 0));
+    PHE_TRY(decrypt_dev_impl(sk, sk->ws_in.p, count, sk->ws_out.p, 0));
+    CUDA_TRY(cudaMemcpy(m_out, sk->ws_out.p, count * hw * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  } catch (const std::exception& e) { return fail(std::string("phe_decrypt: ") + e.what()); }
+}
+
+int phe_add(const phe_pubkey* pk, const uint32_t* a, size_t na, const uint32_t* b, size_t nb, uint32_t* out) {
+  try {
+    if (!pk || !a || !b || !out) return fail("phe_add: null argument");
+    if (nb != na && nb != 1) return fail("phe_add: size mismatch (b must have na or 1 elements)");
+    if (na == 0) return 0;
+    std::lock_guard<std::mutex> lk(pk->mu);
+    CUDA_TRY(cudaSetDevice(pk->device));
+    const int cw = 2 * pk->n_words;
+    PHE_TRY(pk->ws_a.ensure(na * cw));
+    PHE_TRY(pk->ws_b.ensure(nb * cw));
+    PHE_TRY(pk->ws_c.ensure(na * cw));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, a, na * cw * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, b, nb * cw * 4, cudaMemcpyHostToDevice, 0));
+    PHE_TRY(add_dev_impl(pk, pk->ws_a.p, na, pk->ws_b.p, nb, pk->ws_c.p, 0));
+    CUDA_TRY(cudaMemcpy(out, pk->ws_c.p, na * cw * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  } catch (const std::exception& e) { return fail(std::string("phe_add: ") + e.what()); }
+}
+
+int phe_mul(const phe_pubkey* pk, const uint32_t* ct, size_t n, const uint32_t* e, int e_words, size_t ne,
+            uint32_t* out) {
+  try {
+    if (!pk || !ct || !e || !out) return fail("phe_mul: null argument");
+    if (ne != n && ne != 1) return fail("phe_mul: size mismatch (exponents must have n or 1 elements)");
+    if (e_words < 1 || e_words > pk->n_words) return fail("phe_mul: e_words out of range");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(pk->mu);
+    CUDA_TRY(cudaSetDevice(pk->device));
+    const int cw = 2 * pk->n_words;
+    const int ebits = max_bits_host(e, e_words, ne);
+    PHE_TRY(pk->ws_a.ensure(n * cw));
+    PHE_TRY(pk->ws_b.ensure(ne * (size_t)e_words));
+    PHE_TRY(pk->ws_c.ensure(n * cw));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, ct, n * cw * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, e, ne * (size_t)e_words * 4, cudaMemcpyHostToDevice, 0));
+    PHE_TRY(mul_dev_impl(pk, pk->ws_a.p, n, pk->ws_b.p, e_words, ne, ebits, pk->ws_c.p, 0));
+    CUDA_TRY(cudaMemcpy(out, pk->ws_c.p, n * cw * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  } catch (const std::exception& e) { return fail(std::string("phe_mul: ") + e.what()); }
+}
+
+int phe_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulus, int words, size_t count,
+               uint32_t* out) {
+  try {
+    if (!base || !exp || !modulus || !out || words <= 0) return fail("phe_modexp: bad arguments");
+    if (count == 0) return 0;
+    if (phe_device_count() <= 0) return fail("phe_modexp: no CUDA device (there is no CPU fallback)");
+    const BN N = BN::from_words(modulus, words);
+    if (!N.is_odd()) return fail("phe_modexp: modulus must be odd");
+    const ShapeOps* o = shape_for_bits((int)N.bits());
+    if (!o) return fail("phe_modexp: modulus too large (up to 6264 bits)");
+    MontCtxArgs ctx{};
+    std::vector<uint32_t> blk = mont_block(N, BN(), o, &ctx.n0inv);
+    // bases must be < modulus for the Montgomery bound; reduce on the host only if needed
+    std::vector<uint32_t> bred;
+    for (size_t i = 0; i < count; ++i) {
+      BN b = BN::from_words(base + i * words, words);
+      if (!(b < N)) {
+        if (bred.empty()) bred.assign(base, base + count * (size_t)words);
+        hbn::mod(b, N).to_words(&bred[i * words], words);
+      }
+    }
+    const uint32_t* bsrc = bred.empty() ? base : bred.data();
+    DevBuf dctx, db, de, dout, tbl;
+    int rc = upload(dctx, blk);
+    ctx.entries = dctx.p;
+    if (!rc) rc = db.ensure(count * words);
+    if (!rc) rc = de.ensure(count * words);
+    if (!rc) rc = dout.ensure(count * words);
+    if (!rc && (cudaMemcpy(db.p, bsrc, count * words * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(de.p, exp, count * words * 4, cudaMemcpyHostToDevice) != cudaSuccess)) rc = fail("phe_modexp: H2D failed");
+    const int ebits = max_bits_host(exp, words, count);
+    for (size_t off = 0; !rc && off < count; off += CHUNK) {
+      const int c = (int)std::min(CHUNK, count - off);
+      rc = launch_powm(o, ctx, db.p + off * words, words, de.p + off * words, words, words, ebits, dout.p + off * words,
+                       words, c, tbl, 0);
+    }
+    if (!rc && cudaMemcpy(out, dout.p, count * words * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("phe_modexp: D2H failed");
+    for (DevBuf* b : {&dctx, &db, &de, &dout, &tbl}) b->release();
+    return rc;
+  } catch (const std::exception& e) { return fail(std::string("phe_modexp: ") + e.what()); }
+}
+
+// ---- host-only helpers ---------------------------------------------------------------------------------------
+int phe_host_shape_for_bits(int mod_bits, int* L_out, int* TPI_out) {
+  const ShapeOps* o = shape_for_bits(mod_bits);
+  if (!o) return fail("no shape for this size");
+  if (L_out) *L_out = o->L;
+  if (TPI_out) *TPI_out = o->TPI;
+  return 0;
+}
+
+int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, uint32_t* out, uint32_t* n0inv_out) {
+  try {
+    const ShapeOps* o = shape_ops(L, TPI);
+    if (!o) { fail("unknown shape"); return -1; }
+    if (!out) return o->KP;
+    uint32_t n0 = 0;
+    std::vector<uint32_t> blk = mont_block(BN::from_words(mod, mod_words), BN(), o, &n0);
+    std::memcpy(out, blk.data(), blk.size() * 4);
+    if (n0inv_out) *n0inv_out = n0;
+    return o->KP;
+  } catch (const std::exception& e) { fail(e.what()); return -1; }
+}
+
+int phe_host_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulus, int words, uint32_t* out) {
+  try {
+    hbn::modexp(BN::from_words(base, words), BN::from_words(exp, words), BN::from_words(modulus, words)).to_words(out, words);
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+}  // extern "C"

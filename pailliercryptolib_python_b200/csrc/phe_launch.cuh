@@ -1,0 +1,118 @@
+// phe_launch.cuh -- templated launchers; included by each shape_*.cu with PHE_SHAPE_L / PHE_SHAPE_TPI defined.
+#pragma once
+#include <algorithm>
+
+#include "phe_kernels.cuh"
+#include "phe_shapes.hpp"
+
+namespace phe {
+
+inline int sm_count() {
+  static int cached[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) dev = 0;
+  if (!cached[dev]) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+  return cached[dev];
+}
+
+// grid.x for a persistent-style launch: a whole number of resident waves, never more CTAs than work
+template <class K> int grid_for(K kernel, size_t smem, int count, int gpb, int ny) {
+  int occ = 0;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NT, smem);
+  if (occ < 1) occ = 1;
+  const int resident = std::max(1, sm_count() * occ / ny);
+  const int need = (count + gpb - 1) / gpb;
+  return std::max(1, std::min(resident, need));
+}
+
+template <int L, int TPI> struct Launch {
+  using KS = KShape<L, TPI>;
+
+  static cudaError_t modmul(const uint32_t* a, const uint32_t* b, size_t b_stride, uint32_t* out, int nwords,
+                            int count, const MontCtxArgs& ctx, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int grid = grid_for(k_modmul<L, TPI>, smem, count, KS::GPB, 1);
+    k_modmul<L, TPI><<<grid, NT, smem, s>>>(a, b, b_stride, out, nwords, count, ctx);
+    count_launch();
+    return cudaGetLastError();
+  }
+
+  template <int WIN> static cudaError_t powm_w(const PowmArgs& p, int ny, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int grid = grid_for(k_powm<L, TPI, WIN>, smem, p.count, KS::GPB, ny);
+    k_powm<L, TPI, WIN><<<dim3(grid, ny), NT, smem, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+  }
+  static cudaError_t powm(int win, const PowmArgs& p, int ny, cudaStream_t s) {
+    switch (win) {
+      case 1: return powm_w<1>(p, ny, s);
+      case 3: return powm_w<3>(p, ny, s);
+      case 5: return powm_w<5>(p, ny, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  template <int WIN> static size_t tbl_words_w(int ny, int count) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int grid = grid_for(k_powm<L, TPI, WIN>, smem, count, KS::GPB, ny);
+    return (size_t)grid * ny * KS::GPB * ((size_t)KS::KP << WIN);
+  }
+  static size_t powm_tbl_words(int win, int ny, int count) {
+    switch (win) {
+      case 1: return tbl_words_w<1>(ny, count);
+      case 3: return tbl_words_w<3>(ny, count);
+      case 5: return tbl_words_w<5>(ny, count);
+      default: return 0;
+    }
+  }
+
+  static cudaError_t dec_prep(const DecPrepArgs& p, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int grid = grid_for(k_dec_prep<L, TPI>, smem, p.count, KS::GPB, 2);
+    k_dec_prep<L, TPI><<<dim3(grid, 2), NT, smem, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+  }
+  static cudaError_t dec_tail(const DecTailArgs& p, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(DT_COUNT);
+    const int grid = grid_for(k_dec_tail<L, TPI>, smem, p.count, KS::GPB, 1);
+    k_dec_tail<L, TPI><<<grid, NT, smem, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+  }
+  static cudaError_t encrypt_comb(const EncCombArgs& p, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int grid = grid_for(k_encrypt_comb<L, TPI>, smem, p.count, KS::GPB, 1);
+    k_encrypt_comb<L, TPI><<<grid, NT, smem, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+  }
+  static cudaError_t encrypt_finish(const EncFinishArgs& p, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int grid = grid_for(k_encrypt_finish<L, TPI>, smem, p.count, KS::GPB, 1);
+    k_encrypt_finish<L, TPI><<<grid, NT, smem, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+  }
+  static cudaError_t comb_build(const CombArgs& p, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    cudaFuncSetAttribute(k_comb_bases<L, TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_comb_bases<L, TPI><<<1, NT, smem, s>>>(p);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int grid = grid_for(k_comb_fill<L, TPI>, smem, p.nwin, KS::GPB, 1);
+    k_comb_fill<L, TPI><<<grid, NT, smem, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+  }
+
+  static constexpr ShapeOps ops() {
+    return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &dec_prep, &dec_tail,
+                    &encrypt_comb, &encrypt_finish, &comb_build};
+  }
+};
+
+}  // namespace phe

@@ -1,0 +1,38 @@
+// phe_shapes.hpp -- type-erased launch table, one instance per (L, TPI) lane-group shape.
+// Each shape is compiled in its own translation unit (shape_*.cu) so the build parallelises.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace phe {
+
+struct MontCtxArgs;
+struct PowmArgs;
+struct DecPrepArgs;
+struct DecTailArgs;
+struct EncCombArgs;
+struct EncFinishArgs;
+struct CombArgs;
+
+struct ShapeOps {
+  int L, TPI, KP, GPB;
+  int capacity_bits;  // 28 * L * TPI
+  // every launcher returns the launch error (cudaGetLastError) and counts one kernel launch
+  cudaError_t (*modmul)(const uint32_t* a, const uint32_t* b, size_t b_stride, uint32_t* out, int nwords, int count,
+                        const MontCtxArgs& ctx, cudaStream_t s);
+  cudaError_t (*powm)(int win, const PowmArgs& p, int ny, cudaStream_t s);
+  size_t (*powm_tbl_words)(int win, int ny, int count);   // scratch size for a powm launch
+  cudaError_t (*dec_prep)(const DecPrepArgs& p, cudaStream_t s);
+  cudaError_t (*dec_tail)(const DecTailArgs& p, cudaStream_t s);
+  cudaError_t (*encrypt_comb)(const EncCombArgs& p, cudaStream_t s);
+  cudaError_t (*encrypt_finish)(const EncFinishArgs& p, cudaStream_t s);
+  cudaError_t (*comb_build)(const CombArgs& p, cudaStream_t s);
+};
+
+const ShapeOps* shape_ops(int L, int TPI);   // nullptr if not built
+unsigned long long launch_counter();          // kernels launched by this library so far
+void count_launch();
+
+}  // namespace phe

@@ -1,0 +1,182 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libphe_b200.so), against the Python-int oracle
+on the same seeded inputs.  Bit-exact (integer work).  Run with `pytest -m gpu` on a B200."""
+import random
+
+import numpy as np
+import pytest
+
+import paillier_oracle as O
+from pailliercryptolib_python_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20240611
+
+
+@pytest.fixture(scope="module")
+def key2048():
+    pk_o, sk_o = O.bench_keypair()
+    pk = capi.PubKey(pk_o.n, 2048, djn=True, hs=pk_o.hs)
+    sk = capi.PrivKey(pk, sk_o.p, sk_o.q)
+    return pk_o, sk_o, pk, sk
+
+
+def _rand_cts(pk_o, rng, count):
+    # valid ciphertexts without paying oracle modexps: (1 + m n) * s^n is overkill; any unit mod n^2 decrypts to something.
+    return [rng.randrange(1, pk_o.nsquare) for _ in range(count)]
+
+
+def test_requires_gpu():
+    assert capi.device_count() >= 1
+
+
+def test_encrypt_djn_pinned_r(key2048):
+    pk_o, sk_o, pk, sk = key2048
+    rng = random.Random(SEED)
+    ms = [0, 1, pk_o.n - 1, pk_o.n // 3 - 1] + [rng.randrange(pk_o.n) for _ in range(20)] + [rng.getrandbits(53) for _ in range(40)]
+    rs = [0, 1, (1 << 1024) - 1] + [rng.getrandbits(1024) for _ in range(len(ms) - 3)]
+    got = capi.array_to_ints(pk.encrypt(capi.ints_to_array(ms, 64), capi.ints_to_array(rs, 32)))
+    assert got == O.encrypt_batch(pk_o, ms, rs)
+    # make_secure = False
+    got = capi.array_to_ints(pk.encrypt(capi.ints_to_array(ms, 64), None, make_secure=False))
+    assert got == O.encrypt_batch(pk_o, ms, None)
+
+
+def test_decrypt_crt(key2048):
+    pk_o, sk_o, pk, sk = key2048
+    rng = random.Random(SEED + 1)
+    ms = [0, 1, pk_o.n - 1] + [rng.randrange(pk_o.n) for _ in range(29)]
+    cs = O.encrypt_batch(pk_o, ms, [rng.getrandbits(1024) for _ in ms])
+    cs += _rand_cts(pk_o, rng, 32)
+    got = capi.array_to_ints(sk.decrypt(capi.ints_to_array(cs, 128)))
+    assert got[:len(ms)] == ms
+    assert got == O.decrypt_batch(sk_o, cs)
+
+
+def test_add_and_broadcast(key2048):
+    pk_o, sk_o, pk, sk = key2048
+    rng = random.Random(SEED + 2)
+    a = [0, 1, pk_o.nsquare - 1] + _rand_cts(pk_o, rng, 200)
+    b = [5, 1, pk_o.nsquare - 1] + _rand_cts(pk_o, rng, 200)
+    got = capi.array_to_ints(pk.add(capi.ints_to_array(a, 128), capi.ints_to_array(b, 128)))
+    assert got == O.add_batch(pk_o, a, b)
+    got = capi.array_to_ints(pk.add(capi.ints_to_array(a, 128), capi.ints_to_array(b[3:4], 128)))
+    assert got == O.add_batch(pk_o, a, b[3:4])
+    with pytest.raises(RuntimeError):
+        pk.add(capi.ints_to_array(a, 128), capi.ints_to_array(b[:7], 128))
+
+
+@pytest.mark.parametrize("ebits", [1, 7, 53, 160, 700, 2048])
+def test_mul_variable_exponent(key2048, ebits):
+    pk_o, sk_o, pk, sk = key2048
+    rng = random.Random(SEED + ebits)
+    n = 40 if ebits <= 160 else 12
+    a = [0, 1] + _rand_cts(pk_o, rng, n)
+    e = [3, 0] + [rng.getrandbits(ebits) for _ in range(n)]
+    e[2] |= 1 << (ebits - 1)
+    ew = (ebits + 31) // 32
+    got = capi.array_to_ints(pk.mul(capi.ints_to_array(a, 128), capi.ints_to_array(e, ew)))
+    assert got == O.mul_batch(pk_o, a, e)
+    got = capi.array_to_ints(pk.mul(capi.ints_to_array(a, 128), capi.ints_to_array(e[2:3], ew)))
+    assert got == O.mul_batch(pk_o, a, e[2:3])
+
+
+def test_roundtrip_homomorphism_large(key2048):
+    """Size-independent property at a batch far beyond what the oracle checks directly:
+    D(E(a) * E(b) ) = a + b and D(E(a)^k) = k a (mod n), internal CSPRNG r."""
+    pk_o, sk_o, pk, sk = key2048
+    rng = np.random.Generator(np.random.PCG64(SEED))
+    N = 20000
+    a = rng.integers(0, 2**62, size=N, dtype=np.uint64)
+    b = rng.integers(0, 2**62, size=N, dtype=np.uint64)
+    k = rng.integers(1, 2**20, size=N, dtype=np.uint64)
+
+    def pack(v):
+        out = np.zeros((N, 64), dtype=np.uint32)
+        out[:, 0] = (v & 0xFFFFFFFF).astype(np.uint32)
+        out[:, 1] = (v >> 32).astype(np.uint32)
+        return out
+
+    ca, cb = pk.encrypt(pack(a)), pk.encrypt(pack(b))
+    assert not np.array_equal(ca, pk.encrypt(pack(a)))  # randomised
+    s = sk.decrypt(pk.add(ca, cb))
+    want = a.astype(object) + b.astype(object)
+    got = s[:, 0].astype(object) + (s[:, 1].astype(object) << 32) + (s[:, 2].astype(object) << 64)
+    assert (s[:, 3:] == 0).all() and (got == want).all()
+    ke = np.zeros((N, 1), dtype=np.uint32)
+    ke[:, 0] = k.astype(np.uint32)
+    p = sk.decrypt(pk.mul(ca, ke))
+    want = a.astype(object) * k.astype(object)
+    got = p[:, 0].astype(object) + (p[:, 1].astype(object) << 32) + (p[:, 2].astype(object) << 64)
+    assert (p[:, 3:] == 0).all() and (got == want).all()
+
+
+def test_obfuscate_matches_oracle(key2048):
+    pk_o, sk_o, pk, sk = key2048
+    rng = random.Random(SEED + 5)
+    cs = _rand_cts(pk_o, rng, 9)
+    rs = [rng.getrandbits(1024) for _ in cs]
+    got = capi.array_to_ints(pk.obfuscate(capi.ints_to_array(cs, 128), capi.ints_to_array(rs, 32)))
+    assert got == [c * O.obfuscator(pk_o, r) % pk_o.nsquare for c, r in zip(cs, rs)]
+
+
+def test_classic_scheme_1024():
+    pk_o, sk_o = O.seeded_keypair(1024, 5, djn=False)
+    pk = capi.PubKey(pk_o.n, 1024, djn=False)
+    sk = capi.PrivKey(pk, sk_o.q, sk_o.p)  # swapped on purpose: the key orders p < q itself
+    rng = random.Random(SEED + 6)
+    ms = [0, pk_o.n - 1] + [rng.randrange(pk_o.n) for _ in range(14)]
+    rs = [1, pk_o.n - 1] + [rng.randrange(1, pk_o.n) for _ in range(14)]
+    ct = pk.encrypt(capi.ints_to_array(ms, 32), capi.ints_to_array(rs, 32))
+    assert capi.array_to_ints(ct) == O.encrypt_batch(pk_o, ms, rs)
+    assert capi.array_to_ints(sk.decrypt(ct)) == ms
+    # internal r
+    assert capi.array_to_ints(sk.decrypt(pk.encrypt(capi.ints_to_array(ms, 32)))) == ms
+
+
+@pytest.mark.parametrize("bits", [1024, 3072])
+def test_djn_other_key_sizes(bits):
+    pk_o, sk_o = O.seeded_keypair(bits, 77)
+    pk = capi.PubKey(pk_o.n, bits, djn=True, hs=pk_o.hs)
+    sk = capi.PrivKey(pk, sk_o.p, sk_o.q)
+    rng = random.Random(SEED + bits)
+    ms = [0, 1, pk_o.n - 1] + [rng.randrange(pk_o.n) for _ in range(13)]
+    rs = [rng.getrandbits(bits // 2) for _ in ms]
+    ct = pk.encrypt(capi.ints_to_array(ms, bits // 32), capi.ints_to_array(rs, bits // 64))
+    assert capi.array_to_ints(ct) == O.encrypt_batch(pk_o, ms, rs)
+    assert capi.array_to_ints(sk.decrypt(ct)) == ms == O.decrypt_batch(sk_o, capi.array_to_ints(ct))
+    a, b = capi.array_to_ints(ct[:8]), capi.array_to_ints(ct[8:])
+    assert capi.array_to_ints(pk.add(ct[:8], ct[8:])) == O.add_batch(pk_o, a, b)
+    e = [rng.getrandbits(53) for _ in range(8)]
+    assert capi.array_to_ints(pk.mul(ct[:8], capi.ints_to_array(e, 2))) == O.mul_batch(pk_o, a, e)
+
+
+def test_generated_djn_key_roundtrip():
+    """ipclPublicKey(n, bits, True) without hs: the library draws x and builds hs on the device."""
+    n, p, q = capi.keygen(1024)
+    pk = capi.PubKey(n, 1024, djn=True)
+    hs = pk.hs
+    assert 1 < hs < n * n and pow(hs, 1, n * n) == hs
+    sk = capi.PrivKey(pk, p, q)
+    pk_o = O.PubKey(n, 1024, True, hs, 512)
+    rng = random.Random(SEED + 9)
+    ms = [rng.randrange(n) for _ in range(8)]
+    rs = [rng.getrandbits(512) for _ in ms]
+    ct = pk.encrypt(capi.ints_to_array(ms, 32), capi.ints_to_array(rs, 16))
+    assert capi.array_to_ints(ct) == O.encrypt_batch(pk_o, ms, rs)
+    assert capi.array_to_ints(sk.decrypt(ct)) == ms
+
+
+def test_generic_modexp():
+    rng = random.Random(SEED + 10)
+    for bits in (512, 1024, 2048, 4096):
+        mod = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+        base = [0, 1, mod - 1, mod + 5] + [rng.randrange(mod) for _ in range(6)]
+        exp = [5, 0, 2, 3] + [rng.getrandbits(bits) for _ in range(6)]
+        assert capi.modexp(base, exp, mod, bits // 32) == [pow(b, e, mod) for b, e in zip(base, exp)]
+
+
+def test_empty_batches(key2048):
+    pk_o, sk_o, pk, sk = key2048
+    assert pk.encrypt(np.zeros((0, 64), dtype=np.uint32)).shape == (0, 128)
+    assert sk.decrypt(np.zeros((0, 128), dtype=np.uint32)).shape == (0, 64)
