@@ -38,6 +38,17 @@ int phe_get_device(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches evidence). */
 unsigned long long phe_kernel_launches(void);
 
+/* Measurement hooks (bench.py): with timing enabled every kernel launch is bracketed by a cudaEvent pair on
+ * the stream it is launched on; phe_timing_read waits for the recorded events and returns the summed device
+ * time and launch count of one kernel kind since the last phe_timing_enable.  Kinds: 0 k_modmul, 1 k_powm,
+ * 2 k_dec_prep, 3 k_dec_tail, 4 k_encrypt_comb, 5 k_encrypt_finish, 6 k_comb_build. */
+int phe_timing_enable(int on);
+int phe_timing_read(int kind, double* ms_total, unsigned long long* launches);
+const char* phe_timing_kind_name(int kind);
+/* Integer-pipe roofline denominator measured on the current device: sustained IMAD.WIDE.U32 issue rate in
+ * multiply-accumulates per second (all SMs, independent chains), best of `reps` runs. */
+int phe_int_pipe_peak(int reps, double* mac_per_s);
+
 /* ---- keys ---------------------------------------------------------------------------------------------- */
 
 /* ipcl::PublicKey(n, bits, enableDJN) and PublicKey::create(n, bits, hs, randbits)

@@ -22,6 +22,7 @@ SYMBOLS = [
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
     "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits",
+    "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak",
 ]
 
 
@@ -86,6 +87,32 @@ def kernel_launches():
     return int(lib().phe_kernel_launches())
 
 
+KERNEL_KINDS = ["k_modmul", "k_powm", "k_dec_prep", "k_dec_tail", "k_encrypt_comb", "k_encrypt_finish", "k_comb_build"]
+
+
+def timing_enable(on=True):
+    """Bracket every kernel launch with a cudaEvent pair on its stream (bench.py's roofline timing)."""
+    _check(lib().phe_timing_enable(int(bool(on))), "phe_timing_enable")
+
+
+def timing_read():
+    """{kernel kind: (total device ms, launches)} since timing_enable()."""
+    out = {}
+    for k, name in enumerate(KERNEL_KINDS):
+        ms = ctypes.c_double()
+        n = ctypes.c_ulonglong()
+        _check(lib().phe_timing_read(k, ctypes.byref(ms), ctypes.byref(n)), "phe_timing_read")
+        out[name] = (ms.value, int(n.value))
+    return out
+
+
+def int_pipe_peak(reps=5):
+    """Measured IMAD.WIDE.U32 issue rate of the current device in MAC/s (the roofline denominator)."""
+    v = ctypes.c_double()
+    _check(lib().phe_int_pipe_peak(int(reps), ctypes.byref(v)), "phe_int_pipe_peak")
+    return v.value
+
+
 class PubKey:
     """phe_pubkey handle.  n: Python int; hs: optional Python int (DJN generator)."""
 
@@ -122,9 +149,11 @@ class PubKey:
         return words_to_int(out)
 
     # ---- host-buffer ops on packed arrays -------------------------------------------------------------
-    def encrypt(self, m, r=None, make_secure=True):
+    def encrypt(self, m, r=None, make_secure=True, out=None):
         m = np.ascontiguousarray(m, dtype=np.uint32).reshape(-1, self.n_words)
-        out = np.empty((m.shape[0], 2 * self.n_words), dtype=np.uint32)
+        if out is None:
+            out = np.empty((m.shape[0], 2 * self.n_words), dtype=np.uint32)
+        assert out.shape == (m.shape[0], 2 * self.n_words)
         rw = 0
         if r is not None:
             r = np.ascontiguousarray(r, dtype=np.uint32)
@@ -192,9 +221,11 @@ class PrivKey:
         except Exception:
             pass
 
-    def decrypt(self, ct):
+    def decrypt(self, ct, out=None):
         ct = np.ascontiguousarray(ct, dtype=np.uint32).reshape(-1, 2 * self.pk.n_words)
-        out = np.empty((ct.shape[0], self.pk.n_words), dtype=np.uint32)
+        if out is None:
+            out = np.empty((ct.shape[0], self.pk.n_words), dtype=np.uint32)
+        assert out.shape == (ct.shape[0], self.pk.n_words)
         _check(lib().phe_decrypt(self.h, _p(ct), ctypes.c_size_t(ct.shape[0]), _p(out)), "phe_decrypt")
         return out
 

@@ -23,6 +23,64 @@ extern const ShapeOps g_ops_37_1, g_ops_37_2, g_ops_37_4, g_ops_28_2, g_ops_28_4
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launch_counter() { return g_launches.load(); }
+// ---- per-kind launch timing (cudaEvent pairs on the launching stream) -------------------------------------
+namespace {
+struct TimingState {
+  std::mutex mu;
+  bool on = false;
+  struct Pair { int kind; cudaEvent_t e0, e1; };
+  std::vector<Pair> open_pairs;                 // recorded, not yet read
+  std::vector<cudaEvent_t> pending_begin[KK_COUNT];
+  double ms[KK_COUNT] = {0};
+  unsigned long long n[KK_COUNT] = {0};
+} g_tm;
+std::atomic<bool> g_tm_on{false};
+}  // namespace
+void timing_begin(int kind, cudaStream_t s) {
+  if (!g_tm_on.load(std::memory_order_relaxed)) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  std::lock_guard<std::mutex> lk(g_tm.mu);
+  g_tm.pending_begin[kind].push_back(e);
+}
+void timing_end(int kind, cudaStream_t s) {
+  if (!g_tm_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_tm.mu);
+  if (g_tm.pending_begin[kind].empty()) return;
+  cudaEvent_t e0 = g_tm.pending_begin[kind].back();
+  g_tm.pending_begin[kind].pop_back();
+  cudaEvent_t e1;
+  if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return; }
+  cudaEventRecord(e1, s);
+  g_tm.open_pairs.push_back({kind, e0, e1});
+}
+static void timing_drain() {   // caller holds no lock; waits for the recorded events
+  std::vector<TimingState::Pair> pairs;
+  { std::lock_guard<std::mutex> lk(g_tm.mu); pairs.swap(g_tm.open_pairs); }
+  for (auto& p : pairs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      std::lock_guard<std::mutex> lk(g_tm.mu);
+      g_tm.ms[p.kind] += ms; g_tm.n[p.kind] += 1;
+    }
+    cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+  }
+}
+static void timing_set(bool on) {
+  timing_drain();
+  std::lock_guard<std::mutex> lk(g_tm.mu);
+  for (int k = 0; k < KK_COUNT; ++k) { g_tm.ms[k] = 0; g_tm.n[k] = 0; }
+  g_tm_on.store(on);
+}
+static bool timing_read(int kind, double* ms, unsigned long long* n) {
+  if (kind < 0 || kind >= KK_COUNT) return false;
+  timing_drain();
+  std::lock_guard<std::mutex> lk(g_tm.mu);
+  if (ms) *ms = g_tm.ms[kind];
+  if (n) *n = g_tm.n[kind];
+  return true;
+}
 const ShapeOps* shape_ops(int L, int TPI) {
   const ShapeOps* all[] = {&g_ops_37_1, &g_ops_37_2, &g_ops_37_4, &g_ops_28_2, &g_ops_28_4, &g_ops_28_8};
   for (auto* o : all) if (o->L == L && o->TPI == TPI) return o;
@@ -343,6 +401,17 @@ int phe_device_count(void) {
 int phe_set_device(int device) { CUDA_TRY(cudaSetDevice(device)); return 0; }
 int phe_get_device(void) { int d = -1; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; } return d; }
 unsigned long long phe_kernel_launches(void) { return launch_counter(); }
+
+int phe_timing_enable(int on) { phe::timing_set(on != 0); return 0; }
+int phe_timing_read(int kind, double* ms_total, unsigned long long* launches) {
+  if (!phe::timing_read(kind, ms_total, launches)) return fail("phe_timing_read: unknown kernel kind");
+  return 0;
+}
+const char* phe_timing_kind_name(int kind) {
+  static const char* names[KK_COUNT] = {"k_modmul", "k_powm", "k_dec_prep", "k_dec_tail", "k_encrypt_comb",
+                                        "k_encrypt_finish", "k_comb_build"};
+  return (kind >= 0 && kind < KK_COUNT) ? names[kind] : nullptr;
+}
 
 int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const uint32_t* hs, int randbits,
                       phe_pubkey** out) {

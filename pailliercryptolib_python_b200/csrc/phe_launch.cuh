@@ -34,16 +34,18 @@ template <int L, int TPI> struct Launch {
                             int count, const MontCtxArgs& ctx, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     const int grid = grid_for(k_modmul<L, TPI>, smem, count, KS::GPB, 1);
+    { TimedLaunch tl_(KK_MODMUL, s);
     k_modmul<L, TPI><<<grid, NT, smem, s>>>(a, b, b_stride, out, nwords, count, ctx);
-    count_launch();
+    }
     return cudaGetLastError();
   }
 
   template <int WIN> static cudaError_t powm_w(const PowmArgs& p, int ny, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     const int grid = grid_for(k_powm<L, TPI, WIN>, smem, p.count, KS::GPB, ny);
+    { TimedLaunch tl_(KK_POWM, s);
     k_powm<L, TPI, WIN><<<dim3(grid, ny), NT, smem, s>>>(p);
-    count_launch();
+    }
     return cudaGetLastError();
   }
   static cudaError_t powm(int win, const PowmArgs& p, int ny, cudaStream_t s) {
@@ -71,41 +73,47 @@ template <int L, int TPI> struct Launch {
   static cudaError_t dec_prep(const DecPrepArgs& p, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     const int grid = grid_for(k_dec_prep<L, TPI>, smem, p.count, KS::GPB, 2);
+    { TimedLaunch tl_(KK_DEC_PREP, s);
     k_dec_prep<L, TPI><<<dim3(grid, 2), NT, smem, s>>>(p);
-    count_launch();
+    }
     return cudaGetLastError();
   }
   static cudaError_t dec_tail(const DecTailArgs& p, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(DT_COUNT);
     const int grid = grid_for(k_dec_tail<L, TPI>, smem, p.count, KS::GPB, 1);
+    { TimedLaunch tl_(KK_DEC_TAIL, s);
     k_dec_tail<L, TPI><<<grid, NT, smem, s>>>(p);
-    count_launch();
+    }
     return cudaGetLastError();
   }
   static cudaError_t encrypt_comb(const EncCombArgs& p, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     const int grid = grid_for(k_encrypt_comb<L, TPI>, smem, p.count, KS::GPB, 1);
+    { TimedLaunch tl_(KK_ENC_COMB, s);
     k_encrypt_comb<L, TPI><<<grid, NT, smem, s>>>(p);
-    count_launch();
+    }
     return cudaGetLastError();
   }
   static cudaError_t encrypt_finish(const EncFinishArgs& p, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     const int grid = grid_for(k_encrypt_finish<L, TPI>, smem, p.count, KS::GPB, 1);
+    { TimedLaunch tl_(KK_ENC_FINISH, s);
     k_encrypt_finish<L, TPI><<<grid, NT, smem, s>>>(p);
-    count_launch();
+    }
     return cudaGetLastError();
   }
   static cudaError_t comb_build(const CombArgs& p, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     cudaFuncSetAttribute(k_comb_bases<L, TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { TimedLaunch tl_(KK_COMB_BUILD, s);
     k_comb_bases<L, TPI><<<1, NT, smem, s>>>(p);
-    count_launch();
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int grid = grid_for(k_comb_fill<L, TPI>, smem, p.nwin, KS::GPB, 1);
+    { TimedLaunch tl_(KK_COMB_BUILD, s);
     k_comb_fill<L, TPI><<<grid, NT, smem, s>>>(p);
-    count_launch();
+    }
     return cudaGetLastError();
   }
 

@@ -35,4 +35,15 @@ const ShapeOps* shape_ops(int L, int TPI);   // nullptr if not built
 unsigned long long launch_counter();          // kernels launched by this library so far
 void count_launch();
 
+// Per-kernel-kind device timing (phe_timing_* in the C ABI): when enabled every launch is bracketed by a
+// cudaEvent pair on its own stream.  Off by default (no events recorded).
+enum KernelKind { KK_MODMUL = 0, KK_POWM, KK_DEC_PREP, KK_DEC_TAIL, KK_ENC_COMB, KK_ENC_FINISH, KK_COMB_BUILD, KK_COUNT };
+void timing_begin(int kind, cudaStream_t s);
+void timing_end(int kind, cudaStream_t s);
+struct TimedLaunch {   // RAII: brackets one kernel launch, counts it
+  int kind; cudaStream_t s;
+  TimedLaunch(int k, cudaStream_t st) : kind(k), s(st) { timing_begin(k, st); }
+  ~TimedLaunch() { timing_end(kind, s); count_launch(); }
+};
+
 }  // namespace phe
