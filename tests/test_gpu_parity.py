@@ -180,3 +180,65 @@ def test_empty_batches(key2048):
     pk_o, sk_o, pk, sk = key2048
     assert pk.encrypt(np.zeros((0, 64), dtype=np.uint32)).shape == (0, 128)
     assert sk.decrypt(np.zeros((0, 128), dtype=np.uint32)).shape == (0, 64)
+
+
+# ---- committed golden vectors (tests/golden/paillier_kat.json) through the C ABI ---------------------------------
+def _kat():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "paillier_kat.json")) as f:
+        return json.load(f)["keys"]
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_golden_vectors(idx):
+    k = _kat()[idx]
+    ints = lambda xs: [int(x, 16) for x in xs]  # noqa: E731
+    n, p, q, bits = int(k["n"], 16), int(k["p"], 16), int(k["q"], 16), k["bits"]
+    nw = bits // 32
+    pk = capi.PubKey(n, bits, djn=k["djn"], hs=int(k["hs"], 16) if k["djn"] else None)
+    sk = capi.PrivKey(pk, p, q)
+    rw = (k["randbits"] + 31) // 32 if k["djn"] else nw
+    m = capi.ints_to_array(ints(k["m"]), nw)
+    ct = pk.encrypt(m, capi.ints_to_array(ints(k["r"]), rw))
+    assert capi.array_to_ints(ct) == ints(k["ct"])
+    assert capi.array_to_ints(pk.encrypt(m, None, make_secure=False)) == ints(k["ct_raw"])
+    assert capi.array_to_ints(sk.decrypt(capi.ints_to_array(ints(k["dec_in"]), 2 * nw))) == ints(k["dec_out"])
+    b = capi.ints_to_array(ints(k["add_b"]), 2 * nw)
+    assert capi.array_to_ints(pk.add(ct, b)) == ints(k["add_out"])
+    assert capi.array_to_ints(pk.add(ct, b[:1])) == ints(k["add_bcast_out"])
+    e = capi.ints_to_array(ints(k["mul_e"]), nw)
+    assert capi.array_to_ints(pk.mul(ct, e)) == ints(k["mul_out"])
+    assert capi.array_to_ints(pk.mul(ct, e[3:4])) == ints(k["mul_bcast_out"])
+
+
+def test_batch_vs_c_oracle_ragged_sizes(key2048):
+    """Ragged batch sizes around the CTA / wave boundaries, every element checked against the C oracle."""
+    import os
+
+    import c_oracle
+    pk_o, sk_o, pk, sk = key2048
+    rng = np.random.Generator(np.random.PCG64(SEED + 11))
+    th = os.cpu_count() or 1
+    for count in (1, 2, 31, 33, 63, 65, 127, 129, 1000):
+        m = np.zeros((count, 64), dtype=np.uint32)
+        m[:, :3] = rng.integers(0, 2**32, size=(count, 3), dtype=np.uint64).astype(np.uint32)
+        r = rng.integers(0, 2**32, size=(count, 32), dtype=np.uint64).astype(np.uint32)
+        ct = pk.encrypt(m, r)
+        assert np.array_equal(ct, c_oracle.encrypt(pk_o.n, 64, pk_o.hs, m, r, threads=th))
+        assert np.array_equal(sk.decrypt(ct), m)
+        e = rng.integers(0, 2**32, size=(count, 2), dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(pk.mul(ct, e), c_oracle.mul(pk_o.n, 64, ct, e, threads=th))
+        assert np.array_equal(pk.add(ct, ct[::-1].copy()), c_oracle.add(pk_o.n, 64, ct, ct[::-1].copy(), threads=th))
+
+
+def test_timing_hooks_and_pipe_peak(key2048):
+    pk_o, sk_o, pk, sk = key2048
+    capi.timing_enable(True)
+    ct = pk.encrypt(np.zeros((64, 64), dtype=np.uint32), np.ones((64, 32), dtype=np.uint32))
+    sk.decrypt(ct)
+    t = capi.timing_read()
+    capi.timing_enable(False)
+    assert t["k_encrypt_comb"][1] == 1 and t["k_powm"][1] == 1 and t["k_powm"][0] > 0
+    peak = capi.int_pipe_peak(2)
+    assert 4e12 < peak < 12e12   # IMAD.WIDE.U32: one warp instruction per 4 cycles per SM sub-partition
