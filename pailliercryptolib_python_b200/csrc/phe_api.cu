@@ -197,27 +197,73 @@ struct phe_pubkey {
   int bits = 0, n_words = 0, djn = 0, randbits = 0, device = 0;
   BN n, nsq, hs;
   const ShapeOps* ops = nullptr;  // shape of the n^2 context
-  MontCtxArgs ctx{};
-  DevBuf d_ctx, d_comb;
+  mutable MontCtxArgs ctx{};
+  mutable DevBuf d_ctx, d_comb;
+  std::vector<uint32_t> h_ctx;    // Montgomery block, uploaded lazily
   int nwin = 0;
   mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_tbl;  // op workspaces
   mutable std::mutex mu;
+  mutable bool dev_ready = false;  // device state (Montgomery block, comb table) is built on first compute call
 };
 
 struct phe_privkey {
   const phe_pubkey* pk = nullptr;
   BN p, q;
   const ShapeOps* ops = nullptr;  // shape of the x^2 contexts (also used for p, q, n in the tail)
-  DevBuf d_ctx[2], d_exp[2], d_tail;
-  MontCtxArgs ctx[2]{};
+  mutable DevBuf d_ctx[2], d_exp[2], d_tail;
+  mutable MontCtxArgs ctx[2]{};
   int ebits[2] = {0, 0};
   int hw = 0;  // words of x^2 (= n_words)
   uint32_t n0invs[3] = {0, 0, 0};
   mutable DevBuf ws_in, ws_out, ws_mont[2], ws_u[2], ws_tbl;
   mutable std::mutex mu;
+  mutable bool dev_ready = false;
+  std::vector<uint32_t> h_ctx[2], h_exp[2], h_tail;   // host copies uploaded on first compute call
 };
 
 namespace {
+
+// Device state of a key is built on the first compute call (so key objects can be created, inspected and pickled on
+// a host without a GPU); every compute entry point goes through these and fails loudly when no device exists.
+int pk_ensure_device(const phe_pubkey* pk) {
+  if (pk->dev_ready) return 0;
+  if (phe_device_count() <= 0) return fail("no CUDA device (the compute path has no CPU fallback)");
+  CUDA_TRY(cudaGetDevice(const_cast<int*>(&pk->device)));
+  PHE_TRY(upload(pk->d_ctx, pk->h_ctx));
+  pk->ctx.entries = pk->d_ctx.p;
+  if (pk->djn) {
+    // fixed-base comb table T[j][d] = hs^(d 2^(8j)) R mod n^2
+    PHE_TRY(pk->d_comb.ensure((size_t)pk->nwin * 256 * pk->ops->KP));
+    std::vector<uint32_t> hsw(2 * (size_t)pk->n_words);
+    pk->hs.to_words(hsw.data(), hsw.size());
+    DevBuf dhs;
+    PHE_TRY(upload(dhs, hsw));
+    CombArgs ca{};
+    ca.hs_w = dhs.p; ca.hs_words = 2 * pk->n_words; ca.nwin = pk->nwin; ca.comb = pk->d_comb.p; ca.ctx = pk->ctx;
+    cudaError_t e = pk->ops->comb_build(ca, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    dhs.release();
+    if (e != cudaSuccess) return fail(std::string("comb table build: ") + cudaGetErrorString(e));
+  }
+  pk->dev_ready = true;
+  return 0;
+}
+
+int sk_ensure_device(const phe_privkey* sk) {
+  if (sk->dev_ready) return 0;
+  {
+    std::lock_guard<std::mutex> lk(sk->pk->mu);
+    PHE_TRY(pk_ensure_device(sk->pk));
+  }
+  for (int y = 0; y < 2; ++y) {
+    PHE_TRY(upload(sk->d_ctx[y], sk->h_ctx[y]));
+    sk->ctx[y].entries = sk->d_ctx[y].p;
+    PHE_TRY(upload(sk->d_exp[y], sk->h_exp[y]));
+  }
+  PHE_TRY(upload(sk->d_tail, sk->h_tail));
+  sk->dev_ready = true;
+  return 0;
+}
 
 // shared exponent / generic powm launch on the n^2 context of a public key
 int launch_powm(const ShapeOps* o, const MontCtxArgs& ctx, const uint32_t* d_base, int base_words, const uint32_t* d_e,
@@ -417,56 +463,30 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
                       phe_pubkey** out) {
   try {
     if (!n || !out || n_words <= 0) return fail("phe_pubkey_create: bad arguments");
-    if (phe_device_count() <= 0) return fail("phe_pubkey_create: no CUDA device (there is no CPU fallback)");
     BN N = BN::from_words(n, n_words);
     if (!N.is_odd() || N.bits() < 16) return fail("phe_pubkey_create: n must be odd and non-trivial");
     if ((int)N.bits() > bits) bits = (int)N.bits();
     if (n_words * 32 < bits) return fail("phe_pubkey_create: n_words too small");
     std::unique_ptr<phe_pubkey> pk(new phe_pubkey);
     pk->bits = bits; pk->n_words = n_words; pk->djn = djn ? 1 : 0; pk->n = N; pk->nsq = hbn::mul(N, N);
-    CUDA_TRY(cudaGetDevice(&pk->device));
     pk->ops = shape_for_bits(2 * n_words * 32);
     if (!pk->ops) return fail("phe_pubkey_create: key too large (n^2 up to 6144 bits supported)");
     const BN R = hbn::shl(BN(1), pk->ops->capacity_bits);
-    std::vector<uint32_t> blk = mont_block(pk->nsq, hbn::mulmod(N, hbn::mod(R, pk->nsq), pk->nsq), pk->ops, &pk->ctx.n0inv);
-    PHE_TRY(upload(pk->d_ctx, blk));
-    pk->ctx.entries = pk->d_ctx.p;
+    pk->h_ctx = mont_block(pk->nsq, hbn::mulmod(N, hbn::mod(R, pk->nsq), pk->nsq), pk->ops, &pk->ctx.n0inv);
     if (djn) {
       pk->randbits = randbits > 0 ? randbits : bits / 2;
       if (hs) {
         pk->hs = BN::from_words(hs, 2 * (size_t)n_words);
         if (!(pk->hs < pk->nsq)) return fail("phe_pubkey_create: hs >= n^2");
       } else {
-        // ipcl PublicKey::enableDJN: x random with gcd(x, n) = 1, hs = (-x^2 mod n)^n mod n^2
+        // ipcl PublicKey::enableDJN: x random with gcd(x, n) = 1, hs = (-x^2 mod n)^n mod n^2 (once per key, host)
         BN x, g;
         do { x = random_bits((size_t)bits + 128); g = hbn::gcd(x, N); } while (!(g == BN(1)));
         const BN xm = hbn::mod(x, N);
         const BN h = hbn::sub(N, hbn::mulmod(xm, xm, N));
-        // the modexp runs on the device (generic powm on the n^2 context)
-        const int cw = 2 * n_words;
-        std::vector<uint32_t> hb(cw), nw(n_words), res(cw);
-        h.to_words(hb.data(), cw); N.to_words(nw.data(), n_words);
-        DevBuf db, de, dout;
-        PHE_TRY(upload(db, hb)); PHE_TRY(upload(de, nw)); PHE_TRY(dout.ensure(cw));
-        int rc = launch_powm(pk->ops, pk->ctx, db.p, cw, de.p, n_words, 0, (int)N.bits(), dout.p, cw, 1, pk->ws_tbl, 0);
-        if (!rc && cudaMemcpy(res.data(), dout.p, (size_t)cw * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("hs readback failed");
-        db.release(); de.release(); dout.release();
-        if (rc) return rc;
-        pk->hs = BN::from_words(res.data(), cw);
+        pk->hs = hbn::modexp(h, N, pk->nsq);
       }
-      // fixed-base comb table
       pk->nwin = (pk->randbits + 7) / 8;
-      PHE_TRY(pk->d_comb.ensure((size_t)pk->nwin * 256 * pk->ops->KP));
-      std::vector<uint32_t> hsw(2 * (size_t)n_words);
-      pk->hs.to_words(hsw.data(), hsw.size());
-      DevBuf dhs;
-      PHE_TRY(upload(dhs, hsw));
-      CombArgs ca{};
-      ca.hs_w = dhs.p; ca.hs_words = 2 * n_words; ca.nwin = pk->nwin; ca.comb = pk->d_comb.p; ca.ctx = pk->ctx;
-      cudaError_t e = pk->ops->comb_build(ca, 0);
-      if (e == cudaSuccess) e = cudaDeviceSynchronize();
-      dhs.release();
-      if (e != cudaSuccess) return fail(std::string("comb table build: ") + cudaGetErrorString(e));
     }
     *out = pk.release();
     return 0;
@@ -507,13 +527,10 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
       const BN Rm = hbn::mod(R, X2);
       // extra = 2^(32 hw) * R^2 mod x^2  (high half of the ciphertext in the pre-reduction)
       const BN k2 = hbn::mulmod(hbn::mod(hbn::shl(BN(1), 32 * (size_t)sk->hw), X2), hbn::mulmod(Rm, Rm, X2), X2);
-      std::vector<uint32_t> blk = mont_block(X2, k2, o, &sk->ctx[y].n0inv);
-      PHE_TRY(upload(sk->d_ctx[y], blk));
-      sk->ctx[y].entries = sk->d_ctx[y].p;
+      sk->h_ctx[y] = mont_block(X2, k2, o, &sk->ctx[y].n0inv);
       const BN e = hbn::sub(X[y], BN(1));
-      std::vector<uint32_t> ew(sk->hw);
-      e.to_words(ew.data(), ew.size());
-      PHE_TRY(upload(sk->d_exp[y], ew));
+      sk->h_exp[y].assign(sk->hw, 0);
+      e.to_words(sk->h_exp[y].data(), sk->h_exp[y].size());
       sk->ebits[y] = (int)e.bits();
       // hx = (L_x(g^(x-1) mod x^2))^-1 mod x
       const BN u = hbn::modexp(hbn::mod(g, X2), e, X2);
@@ -529,7 +546,7 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
     put(DT_PINVM, hbn::mulmod(pinv, hbn::mod(R, Q), Q));
     put(DT_PMN, hbn::mulmod(P, hbn::mod(R, pk->n), pk->n));
     put(DT_ONE, BN(1));
-    PHE_TRY(upload(sk->d_tail, tail));
+    sk->h_tail = tail;
     sk->n0invs[0] = hbn::neg_inv28(P.low());
     sk->n0invs[1] = hbn::neg_inv28(Q.low());
     sk->n0invs[2] = hbn::neg_inv28(pk->n.low());
@@ -614,12 +631,14 @@ int phe_encrypt_dev(const phe_pubkey* pk, const uint32_t* d_m, size_t count, con
                     uint32_t* d_ct_out, void* stream) {
   if (!pk || !d_m || !d_ct_out) return fail("phe_encrypt_dev: null argument");
   std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
   return encrypt_dev_impl(pk, d_m, count, d_r, r_words, d_ct_out, (cudaStream_t)stream);
 }
 int phe_decrypt_dev(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m_out, void* stream) {
   if (!sk || !d_ct || !d_m_out) return fail("phe_decrypt_dev: null argument");
   if (count == 0) return 0;
   std::lock_guard<std::mutex> lk(sk->mu);
+    PHE_TRY(sk_ensure_device(sk));
   return decrypt_dev_impl(sk, d_ct, count, d_m_out, (cudaStream_t)stream);
 }
 int phe_add_dev(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint32_t* d_b, size_t nb, uint32_t* d_out,
@@ -627,6 +646,7 @@ int phe_add_dev(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint
   if (!pk || !d_a || !d_b || !d_out) return fail("phe_add_dev: null argument");
   if (na == 0) return 0;
   std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
   return add_dev_impl(pk, d_a, na, d_b, nb, d_out, (cudaStream_t)stream);
 }
 int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
@@ -634,6 +654,7 @@ int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint
   if (!pk || !d_ct || !d_e || !d_out) return fail("phe_mul_dev: null argument");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
   return mul_dev_impl(pk, d_ct, n, d_e, e_words, ne, exp_bits, d_out, (cudaStream_t)stream);
 }
 
@@ -644,6 +665,7 @@ int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uin
     if (!pk || !m || !ct_out) return fail("phe_encrypt: null argument");
     if (count == 0) return 0;
     std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
     CUDA_TRY(cudaSetDevice(pk->device));
     const int cw = 2 * pk->n_words;
     std::vector<uint32_t> rgen;
@@ -675,6 +697,7 @@ int phe_obfuscate(const phe_pubkey* pk, uint32_t* ct, size_t count, const uint32
     if (!pk || !ct) return fail("phe_obfuscate: null argument");
     if (count == 0) return 0;
     std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
     CUDA_TRY(cudaSetDevice(pk->device));
     const int cw = 2 * pk->n_words;
     std::vector<uint32_t> rgen;
@@ -699,6 +722,7 @@ int phe_decrypt(const phe_privkey* sk, const uint32_t* ct, size_t count, uint32_
     if (!sk || !ct || !m_out) return fail("phe_decrypt: null argument");
     if (count == 0) return 0;
     std::lock_guard<std::mutex> lk(sk->mu);
+    PHE_TRY(sk_ensure_device(sk));
     CUDA_TRY(cudaSetDevice(sk->pk->device));
     const int hw = sk->hw, cw = 2 * hw;
     PHE_TRY(sk->ws_in.ensure(count * cw));
@@ -716,6 +740,7 @@ int phe_add(const phe_pubkey* pk, const uint32_t* a, size_t na, const uint32_t* 
     if (nb != na && nb != 1) return fail("phe_add: size mismatch (b must have na or 1 elements)");
     if (na == 0) return 0;
     std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
     CUDA_TRY(cudaSetDevice(pk->device));
     const int cw = 2 * pk->n_words;
     PHE_TRY(pk->ws_a.ensure(na * cw));
@@ -737,6 +762,7 @@ int phe_mul(const phe_pubkey* pk, const uint32_t* ct, size_t n, const uint32_t* 
     if (e_words < 1 || e_words > pk->n_words) return fail("phe_mul: e_words out of range");
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
     CUDA_TRY(cudaSetDevice(pk->device));
     const int cw = 2 * pk->n_words;
     const int ebits = max_bits_host(e, e_words, ne);

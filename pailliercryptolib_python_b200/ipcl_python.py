@@ -1,0 +1,463 @@
+"""The ipcl_python API surface on top of the B200 engine: PaillierKeypair, PaillierPublicKey, PaillierPrivateKey,
+PaillierEncryptedNumber, BNUtils -- same names, arguments, return types and error behaviour as the reference
+(/root/reference/src/ipcl_python/ipcl_python.py), so existing callers switch by changing the import.
+
+What is different underneath (B200-first, not a translation):
+  * a PaillierEncryptedNumber keeps its ciphertexts as ONE packed [N, 2*n_words] uint32 matrix inside an ipclCipherText
+    and its exponents as an int64 vector; every operator is a handful of whole-batch calls into libphe_b200.so
+    (encrypt / decrypt / modmul / modexp kernels), never a Python loop over ipclBigNumber objects;
+  * the fixed-point codec is vectorised (fixedpoint.encode_array / decode_array);
+  * exponent alignment gathers the rows that need scaling, raises them to 2^delta in one batched HE-mul and scatters
+    them back with numpy indexing (reference: ipcl_python.py:528-741, per-element lists);
+  * negative plaintext factors still invert the ciphertext first (ipcl_python.py:272-276, 426-441, 470-479) so results
+    are bit-identical to the reference's; the inverse is Python's pow(x, -1, n^2) instead of gmpy2.invert;
+  * sum()/dot()/@ reduce with a log-depth tree of batched HE-adds; sum() works for any length (the reference's passes
+    a list where it needs a ciphertext container, ipcl_python.py:752-755).
+"""
+from typing import Optional, Tuple, Union
+
+import numpy as np
+
+from .bindings.ipcl_bindings import (
+    ipclBigNumber,
+    ipclCipherText,
+    ipclKeypair,
+    ipclPlainText,
+    ipclPrivateKey,
+    ipclPublicKey,
+)
+from .fixedpoint import FixedPointNumber, decode_array, encode_array
+
+_NUMBER = (int, float, np.integer, np.floating)
+
+
+def _ints_to_limbs(vals, words):
+    buf = b"".join(int(v).to_bytes(4 * words, "little") for v in vals)
+    return np.frombuffer(buf, dtype="<u4").reshape(len(vals), words).astype(np.uint32)
+
+
+def _limbs_to_ints(arr):
+    arr = np.ascontiguousarray(arr, dtype="<u4")
+    step = arr.shape[1] * 4
+    raw = arr.tobytes()
+    return [int.from_bytes(raw[i * step:(i + 1) * step], "little") for i in range(arr.shape[0])]
+
+
+class PaillierKeypair:
+    @staticmethod
+    def generate_keypair(n_length: int = 1024, enable_DJN: bool = True) -> Tuple["PaillierPublicKey", "PaillierPrivateKey"]:
+        """Generate a key pair (ipcl_python.py:20-40).  Unlike the reference (<= 2048 bits) keys up to 3072 bits work."""
+        pub, pri = ipclKeypair.generate_keypair(n_length, enable_DJN)
+        return PaillierPublicKey(pub), PaillierPrivateKey(pri)
+
+
+class PaillierPublicKey:
+    def __init__(self, key: Union[ipclPublicKey, "PaillierPublicKey", int], n_length: Optional[int] = None,
+                 enable_DJN: Optional[bool] = None):
+        if isinstance(key, ipclPublicKey):
+            self.pubkey = key
+            self.n = BNUtils.BN2int(key.n)
+        elif isinstance(key, PaillierPublicKey):
+            # the reference's `self = key` leaves the object unset; share the handle instead
+            self.pubkey, self.n = key.pubkey, key.n
+        elif isinstance(key, int) and n_length is not None and enable_DJN is not None:
+            self.n = key
+            self.pubkey = ipclPublicKey(BNUtils.int2BN(key), n_length, enable_DJN)
+        else:
+            raise ValueError("PaillierPublicKey: PubKey should be either key value (n),"
+                             "PaillierPublicKey or IPP-PaillierPublicKey object")
+        self._derive()
+
+    def _derive(self):
+        self.max_int = self.n // 3 - 1
+        self.nsquare = self.n * self.n
+        self.n_words = (max(self.pubkey.length, self.n.bit_length()) + 31) // 32
+
+    def __getstate__(self):
+        return self.pubkey
+
+    def __setstate__(self, state):
+        self.pubkey = state
+        self.n = BNUtils.BN2int(state.n)
+        self._derive()
+
+    def __repr__(self):
+        return repr(self.pubkey)
+
+    def __eq__(self, other):
+        return self.n == other.n
+
+    def __hash__(self):
+        return hash(self.pubkey)
+
+    def apply_obfuscator(self, x: Union[int, ipclBigNumber]):
+        if isinstance(x, int):
+            x = BNUtils.int2BN(x)
+        return self.pubkey.apply_obfuscator(x)
+
+    def raw_encrypt(self, plaintext) -> "PaillierEncryptedNumber":
+        return self.encrypt(plaintext, apply_obfuscator=False)
+
+    def encrypt(self, values: Union[np.ndarray, list, int, float], apply_obfuscator: bool = True) -> "PaillierEncryptedNumber":
+        """Encrypt a scalar or a 1-D list/array of ints/floats into ONE PaillierEncryptedNumber holding the batch
+        (ipcl_python.py:108-147)."""
+        if np.isscalar(values):
+            values = [values]
+        arr = values if isinstance(values, np.ndarray) else None
+        if arr is None or arr.dtype == object:
+            if not all(isinstance(v, _NUMBER) for v in values):
+                raise ValueError("PaillierPublicKey.encrypt: input value(s) should be integer or float")
+        elif arr.ndim != 1 or arr.dtype.kind not in "iuf":
+            raise ValueError("PaillierPublicKey.encrypt: input value(s) should be integer or float")
+        limbs, expos = encode_array(values, self.n, self.max_int, self.n_words)
+        ct = self.pubkey.encrypt(ipclPlainText.from_packed(limbs), apply_obfuscator)
+        return PaillierEncryptedNumber(self, ct, exponents=expos, length=len(expos))
+
+
+class PaillierPrivateKey:
+    def __init__(self, key: Union[ipclPrivateKey, ipclPublicKey, PaillierPublicKey], p: Optional[int] = None,
+                 q: Optional[int] = None):
+        if isinstance(key, ipclPrivateKey):
+            self.prikey = key
+            self.__n = BNUtils.BN2int(key.n)
+        elif isinstance(key, ipclPublicKey) and p is not None and q is not None:
+            self.prikey = ipclPrivateKey(key, BNUtils.int2BN(p), BNUtils.int2BN(q))
+            self.__n = BNUtils.BN2int(key.n)
+        elif isinstance(key, PaillierPublicKey) and p is not None and q is not None:
+            self.prikey = ipclPrivateKey(key.pubkey, BNUtils.int2BN(p), BNUtils.int2BN(q))
+            self.__n = key.n
+        else:
+            raise KeyError("PaillierPrivateKey: key should be either Private key or Public key (with p and q)")
+        self.__max_int = self.__n // 3 - 1
+
+    def __getstate__(self):
+        return (self.prikey, self.__n, self.__max_int)
+
+    def __setstate__(self, state):
+        (self.prikey, self.__n, self.__max_int) = state
+
+    def __eq__(self, other: "PaillierPrivateKey"):
+        return (self.prikey.p == other.prikey.p) and (self.prikey.q == other.prikey.q)
+
+    def __hash__(self):
+        return hash(self.prikey)
+
+    def __repr__(self):
+        return repr(self.prikey)
+
+    def _decrypt_packed(self, number: "PaillierEncryptedNumber", who: str) -> np.ndarray:
+        if number.public_key.n != self.__n:
+            raise ValueError("%s: Public key mismatch" % who)
+        return self.prikey.decrypt(number.ciphertext()).to_packed()
+
+    def raw_decrypt(self, ciphertext: "PaillierEncryptedNumber"):
+        vals = _limbs_to_ints(self._decrypt_packed(ciphertext, "PaillierPrivateKey.raw_decrypt"))
+        return vals if len(ciphertext) > 1 else vals[0]
+
+    def decrypt(self, encrypted_number: "PaillierEncryptedNumber"):
+        """Decrypt and decode: list of ints/floats, or a single value for a length-1 ciphertext (ipcl_python.py:219-245)."""
+        limbs = self._decrypt_packed(encrypted_number, "PailierPrivateKey.decrypt")
+        vals = decode_array(limbs, encrypted_number.exponent(), self.__n, self.__max_int)
+        return vals if len(encrypted_number) > 1 else vals[0]
+
+
+class PaillierEncryptedNumber:
+    def __init__(self, public_key: PaillierPublicKey, ciphertext: ipclCipherText, exponents, length: int):
+        if ciphertext.public_key != public_key.pubkey:
+            raise ValueError("PaillierEncryptedNumber: public key mismatch")
+        self.public_key = public_key
+        self.__ct = ciphertext
+        self.__expo = np.asarray(exponents, dtype=np.int64).reshape(-1)
+        self.__length = length
+
+    # ---- plumbing ---------------------------------------------------------------------------------------------
+    def _wrap(self, packed, exponents) -> "PaillierEncryptedNumber":
+        ct = packed if isinstance(packed, ipclCipherText) else ipclCipherText.from_packed(self.public_key.pubkey, packed)
+        return PaillierEncryptedNumber(self.public_key, ct, exponents, len(ct))
+
+    def packed(self) -> np.ndarray:
+        """[N, 2*n_words] uint32 little-endian limb matrix of the ciphertexts (a copy)."""
+        return self.__ct.to_packed()
+
+    def __repr__(self):
+        return repr(self.__ct)
+
+    def __getstate__(self) -> tuple:
+        return (self.public_key, len(self), self.exponent(), _limbs_to_ints(self.packed()))
+
+    def __setstate__(self, state: tuple):
+        self.public_key, self.__length, expo, ints = state
+        self.__expo = np.asarray(expo, dtype=np.int64).reshape(-1)
+        self.__ct = ipclCipherText.from_packed(self.public_key.pubkey, _ints_to_limbs(ints, 2 * self.public_key.n_words))
+
+    def __len__(self) -> int:
+        return self.__length
+
+    def length(self) -> int:
+        return self.__length
+
+    def ciphertext(self) -> ipclCipherText:
+        return self.__ct
+
+    def ciphertextBN(self, idx: Optional[int] = None):
+        if idx is None:
+            return self.__ct.getTexts()
+        if not 0 <= idx < self.__length:
+            raise IndexError("ciphertext: idx out of range")
+        return self.__ct[idx]
+
+    def exponent(self, idx: Optional[int] = None):
+        if idx is None:
+            return [int(e) for e in self.__expo]
+        if not 0 <= idx < self.__length:
+            raise IndexError("exponent: idx out of range")
+        return int(self.__expo[idx])
+
+    def apply_obfuscator(self):
+        self.__ct = self.public_key.pubkey.apply_obfuscator_packed(self.__ct)
+
+    def __getitem__(self, key: Union[int, slice]) -> "PaillierEncryptedNumber":
+        if isinstance(key, (int, np.integer)):
+            key = slice(int(key), int(key) + 1)
+        start = 0 if key.start is None else key.start
+        stop = len(self) if key.stop is None else key.stop
+        if key.step not in (None, 1):
+            raise RuntimeError("Step size not supported")
+        if not 0 <= stop <= len(self) or not 0 <= start < len(self):
+            raise IndexError("__getitem__: key out of range")
+        return self._wrap(self.__ct[start:stop], self.__expo[start:stop])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    # ---- homomorphic add ----------------------------------------------------------------------------------------
+    def __add__(self, other):
+        if self.__length == 1 and isinstance(other, PaillierEncryptedNumber) and len(other) > 1:
+            return other.__raw_add(self)
+        return self.__raw_add(other)
+
+    def __radd__(self, other):
+        return self + other
+
+    def __sub__(self, other):
+        if isinstance(other, list):
+            other = np.array(other)
+        return self.__raw_add(other * -1.0)
+
+    def __rsub__(self, other):
+        if isinstance(other, PaillierEncryptedNumber):
+            return other - self
+        return (self * (-1.0)).__raw_add(other)
+
+    def __raw_add(self, other) -> "PaillierEncryptedNumber":
+        if isinstance(other, (np.ndarray, list)):
+            if self.__length != len(other):
+                raise ValueError("PaillierEncryptedNumber.__raw_add: array(list) size mismatch with PaillierEncryptedNumber")
+            other = self.public_key.encrypt(other, apply_obfuscator=False)
+        elif np.isscalar(other) and isinstance(other, (int, float)):
+            other = self.public_key.encrypt(other, apply_obfuscator=False)
+        elif isinstance(other, PaillierEncryptedNumber):
+            if self.public_key != other.public_key:
+                raise ValueError("PaillierEncryptedNumber.__raw_add: PublicKey mismatch")
+            if self.__length != len(other) and len(other) > 1:
+                raise ValueError("PaillierEncryptedNumber.__raw_add: CipherText size mismatch with PaillierEncryptedNumber")
+        x_ct, y_ct, expo = self.__align_exponent(self.__ct, self.__expo, other.ciphertext(), other.__expo)
+        return self._wrap(x_ct + y_ct, expo)
+
+    def _scale_rows(self, packed: np.ndarray, rows: np.ndarray, deltas: np.ndarray) -> None:
+        """packed[rows] <- packed[rows] ^ (2^delta) mod n^2, one batched HE-mul (the reference multiplies by the
+        plaintext BASE^delta: ipcl_python.py:551-560, 602-606)."""
+        if rows.size == 0:
+            return
+        words = int(deltas.max()) // 32 + 1
+        factors = np.zeros((rows.size, words), dtype=np.uint32)
+        factors[np.arange(rows.size), deltas // 32] = np.uint32(1) << (deltas % 32).astype(np.uint32)
+        sub = ipclCipherText.from_packed(self.public_key.pubkey, np.ascontiguousarray(packed[rows]))
+        packed[rows] = (sub * ipclPlainText.from_packed(factors)).to_packed()
+
+    def increase_exponent_to(self, x_ct: ipclCipherText, x_expo, exponent: int) -> ipclCipherText:
+        """Raise every element whose exponent is below `exponent` (ipcl_python.py:528-568)."""
+        diff = int(exponent) - np.asarray(x_expo, dtype=np.int64)
+        rows = np.nonzero(diff > 0)[0]
+        if rows.size == 0:
+            return x_ct
+        packed = x_ct.to_packed()
+        self._scale_rows(packed, rows, diff[rows])
+        return ipclCipherText.from_packed(self.public_key.pubkey, packed)
+
+    def __align_exponent(self, x_ct, x_expo, y_ct, y_expo):
+        """Bring both operands to max(exponent) per element; y may be a single broadcast ciphertext
+        (ipcl_python.py:570-741)."""
+        x_expo = np.asarray(x_expo, dtype=np.int64)
+        y_expo = np.asarray(y_expo, dtype=np.int64)
+        count = len(x_ct)
+        y_bcast = np.broadcast_to(y_expo, (count,)) if len(y_ct) == 1 else y_expo
+        out_expo = np.maximum(x_expo, y_bcast)
+        x_rows = np.nonzero(x_expo < y_bcast)[0]
+        y_rows = np.nonzero(y_bcast < x_expo)[0]
+        if x_rows.size:
+            xp = x_ct.to_packed()
+            self._scale_rows(xp, x_rows, (y_bcast - x_expo)[x_rows])
+            x_ct = ipclCipherText.from_packed(self.public_key.pubkey, xp)
+        if y_rows.size:
+            yp = y_ct.to_packed()
+            if len(y_ct) == 1 and count > 1:
+                yp = np.repeat(yp, count, axis=0)
+            self._scale_rows(yp, y_rows, (x_expo - y_bcast)[y_rows])
+            y_ct = ipclCipherText.from_packed(self.public_key.pubkey, yp)
+        return x_ct, y_ct, out_expo
+
+    # ---- homomorphic multiply by plaintext ---------------------------------------------------------------------------
+    def __invert_rows(self, packed: np.ndarray, rows: np.ndarray) -> None:
+        nsq = self.public_key.nsquare
+        vals = _limbs_to_ints(packed[rows])
+        packed[rows] = _ints_to_limbs([pow(v, -1, nsq) for v in vals], packed.shape[1])
+
+    def _mul_encoded(self, packed: np.ndarray, pt_limbs: np.ndarray, ct_expo, pt_expo):
+        """ct[i] ^ pt[i] with the reference's negative-plaintext rule: if pt >= n - max_int use (ct^-1)^(n - pt) so the
+        exponent stays short (ipcl_python.py:426-441, 470-479).  pt_limbs: [N or 1, n_words]."""
+        pk = self.public_key
+        n_l = _ints_to_limbs([pk.n], pk.n_words)[0]
+        thr = _ints_to_limbs([pk.n - pk.max_int], pk.n_words)[0]
+        # lexicographic compare pt >= thr from the top word down
+        ge = np.ones(pt_limbs.shape[0], dtype=bool)
+        decided = np.zeros(pt_limbs.shape[0], dtype=bool)
+        for j in range(pk.n_words - 1, -1, -1):
+            col = pt_limbs[:, j]
+            gt, lt = (col > thr[j]) & ~decided, (col < thr[j]) & ~decided
+            ge[lt] = False
+            decided |= gt | lt
+            if decided.all():
+                break
+        neg = np.nonzero(ge)[0]
+        if neg.size:
+            pt_limbs = pt_limbs.copy()
+            borrow = np.zeros(neg.size, dtype=np.int64)
+            for j in range(pk.n_words):
+                v = np.int64(int(n_l[j])) - pt_limbs[neg, j].astype(np.int64) - borrow
+                borrow = (v < 0).astype(np.int64)
+                pt_limbs[neg, j] = (v & 0xFFFFFFFF).astype(np.uint32)
+            if pt_limbs.shape[0] == 1 and packed.shape[0] > 1:
+                self.__invert_rows(packed, np.arange(packed.shape[0]))
+            else:
+                self.__invert_rows(packed, neg)
+        used = pk.n_words
+        while used > 1 and not pt_limbs[:, used - 1].any():
+            used -= 1
+        ct = ipclCipherText.from_packed(pk.pubkey, packed)
+        res = ct * ipclPlainText.from_packed(np.ascontiguousarray(pt_limbs[:, :used]))
+        return res, np.asarray(ct_expo, dtype=np.int64) + np.asarray(pt_expo, dtype=np.int64)
+
+    def __mul__(self, other) -> "PaillierEncryptedNumber":
+        pk = self.public_key
+        if np.isscalar(other):
+            pt_limbs, pt_expo = encode_array([other], pk.n, pk.max_int, pk.n_words)
+        else:
+            if len(other) != self.__length:
+                raise ValueError("PaillierEncryptedNumber.__mul__: Multiply size mismatch")
+            pt_limbs, pt_expo = encode_array(other, pk.n, pk.max_int, pk.n_words)
+        res, expo = self._mul_encoded(self.packed(), pt_limbs, self.__expo, pt_expo)
+        return self._wrap(res, expo)
+
+    def __rmul__(self, other):
+        return self * other
+
+    def __truediv__(self, other):
+        if isinstance(other, list):
+            other = np.array(other)
+        return self * (1.0 / other)
+
+    # ---- reductions ---------------------------------------------------------------------------------------------------
+    def _tree_sum(self, packed: np.ndarray, groups: int, width: int) -> np.ndarray:
+        """packed: [groups * width, cw] (row-major groups).  Returns [groups, cw]: the HE-sum of every group, by a
+        log-depth tree of batched HE-adds (ipcl_python.py:810-827 does the same with rotate-and-add)."""
+        pk = self.public_key
+        cw = packed.shape[1]
+        cur = packed.reshape(groups, width, cw)
+        while cur.shape[1] > 1:
+            w = cur.shape[1]
+            half = w // 2
+            a = ipclCipherText.from_packed(pk.pubkey, np.ascontiguousarray(cur[:, :half].reshape(-1, cw)))
+            b = ipclCipherText.from_packed(pk.pubkey, np.ascontiguousarray(cur[:, half:2 * half].reshape(-1, cw)))
+            s = (a + b).to_packed().reshape(groups, half, cw)
+            cur = np.concatenate([s, cur[:, 2 * half:]], axis=1) if w % 2 else s
+        return cur.reshape(groups, cw)
+
+    def sum(self) -> "PaillierEncryptedNumber":
+        top = int(self.__expo.max())
+        aligned = self.increase_exponent_to(self.__ct, self.__expo, top).to_packed()
+        return self._wrap(self._tree_sum(aligned, 1, len(self)), [top])
+
+    def mean(self) -> "PaillierEncryptedNumber":
+        return self.sum() / len(self)
+
+    def dot(self, other) -> "PaillierEncryptedNumber":
+        if len(other) != len(self):
+            raise ValueError("PaillierEncryptedNumber.dot: input size mismatch with ciphertext")
+        return (self * other).sum()
+
+    def __matmul(self, other: np.ndarray, m: int, n: int, k: int, rhs: bool) -> "PaillierEncryptedNumber":
+        """(m x n) @ (n x k): one batched HE-mul over all m*k*n products, per-output exponent alignment, tree sum.
+        Index maps as ipcl_python.py:777-808."""
+        pk = self.public_key
+        ii, jj, ll = np.meshgrid(np.arange(m), np.arange(k), np.arange(n), indexing="ij")
+        if rhs:   # other (m x n) @ self (n x k)
+            idx_self = (ll * k + jj).reshape(-1)
+            pts = other[ii, ll].reshape(-1) if other.ndim == 2 else other[ll].reshape(-1)
+        else:     # self (m x n) @ other (n x k)
+            idx_self = (ii * n + ll).reshape(-1)
+            pts = other[ll, jj].reshape(-1) if other.ndim == 2 else other[ll].reshape(-1)
+        pt_limbs, pt_expo = encode_array(pts, pk.n, pk.max_int, pk.n_words)
+        prod, expo = self._mul_encoded(self.packed()[idx_self], pt_limbs, self.__expo[idx_self], pt_expo)
+        expo = expo.reshape(m * k, n)
+        top = expo.max(axis=1)
+        packed = prod.to_packed()
+        delta = (top[:, None] - expo).reshape(-1)
+        rows = np.nonzero(delta > 0)[0]
+        self._scale_rows(packed, rows, delta[rows])
+        return self._wrap(self._tree_sum(packed, m * k, n), top)
+
+    def __matmul__(self, other) -> "PaillierEncryptedNumber":
+        if len(self) % len(other) != 0:
+            raise ValueError("PaillierEncryptedNumber.__matmul__: matrix multiply size mismatch")
+        other = np.array(other)
+        if other.ndim not in (1, 2):
+            raise NotImplementedError("PaillierEncryptedNumber.__matmul__: input ndim %dnot supported" % other.ndim)
+        n = other.shape[0]
+        k = other.shape[1] if other.ndim == 2 else 1
+        return self.__matmul(other, len(self) // n, n, k, rhs=False)
+
+    def __rmatmul__(self, other) -> "PaillierEncryptedNumber":
+        other = np.array(other)
+        if other.ndim not in (1, 2):
+            raise NotImplementedError("PaillierEncryptedNumber.__rmatmul__: input ndim %d not supported" % other.ndim)
+        m = other.shape[0] if other.ndim == 2 else 1
+        n = other.shape[1] if other.ndim == 2 else other.shape[0]
+        if len(self) % n != 0:
+            raise ValueError("PaillierEncryptedNumber.__rmatmul__: matrix multiplysize mismatch")
+        return self.__matmul(other, m, n, len(self) // n, rhs=True)
+
+    def __imatmul__(self, other) -> "PaillierEncryptedNumber":
+        return self @ other
+
+
+class BNUtils:
+    """Python int <-> ipclBigNumber through little-endian bytes (ipcl_python.py:933-977)."""
+
+    @staticmethod
+    def int2Bytes(val: int) -> bytes:
+        return val.to_bytes((val.bit_length() + 7) // 8, byteorder="little")
+
+    @staticmethod
+    def bytes2Int(val: bytes) -> int:
+        return int.from_bytes(val, "little")
+
+    @staticmethod
+    def int2BN(val: int) -> ipclBigNumber:
+        if val in (0, 1, 2):
+            return (ipclBigNumber.Zero, ipclBigNumber.One, ipclBigNumber.Two)[val]
+        return ipclBigNumber(BNUtils.int2Bytes(val))
+
+    @staticmethod
+    def BN2int(val: ipclBigNumber) -> int:
+        return BNUtils.bytes2Int(val.to_bytes())

@@ -30,10 +30,17 @@ def test_library_exports_every_declared_symbol():
 def test_no_cpu_fallback():
     if capi.device_count() > 0:
         pytest.skip("a GPU is present")
-    with pytest.raises(RuntimeError, match="no CUDA device"):
-        capi.PubKey(0xC5A1 * 0xB3F7 | 1, 64, djn=False)
-    with pytest.raises(RuntimeError, match="no CUDA device"):
-        capi.modexp([3], [5], 1000003, 1)
+    # key objects are host-side state (constructible, picklable); every compute entry point refuses to run
+    n, p, q = capi.keygen(256)
+    pk = capi.PubKey(n, 256, djn=True)
+    sk = capi.PrivKey(pk, p, q)
+    m = np.ones((2, 8), dtype=np.uint32)
+    ct = np.ones((2, 16), dtype=np.uint32)
+    for call in (lambda: pk.encrypt(m), lambda: pk.encrypt(m, None, make_secure=False), lambda: pk.add(ct, ct),
+                 lambda: pk.mul(ct, m[:, :2]), lambda: pk.obfuscate(ct), lambda: sk.decrypt(ct),
+                 lambda: capi.modexp([3], [5], 1000003, 1)):
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            call()
 
 
 def test_host_modexp_and_mont_block():
