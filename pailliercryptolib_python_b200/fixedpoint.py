@@ -184,7 +184,19 @@ def encode_array(values, n, max_int, words):
     int16/32/64 arrays: exponent 0.  Anything else (object arrays, Python big ints, mixed lists) goes through the scalar
     codec element by element so the results are identical by construction.
     """
-    arr = np.asarray(values)
+    if isinstance(values, np.ndarray):
+        arr = values
+    else:
+        # a Python sequence: the element TYPES decide the exponents (int -> 0, float -> 53 - frexp), so only a
+        # homogeneous sequence may take a vector path; np.asarray would silently turn a mixed list into floats
+        values = list(values)
+        if values and all(type(v) is float or isinstance(v, np.floating) for v in values):
+            arr = np.asarray(values, dtype=np.float64)
+        elif values and all(type(v) is int and -(1 << 63) <= v < (1 << 63) for v in values):
+            arr = np.asarray(values, dtype=np.int64)
+        else:
+            arr = np.empty(len(values), dtype=object)
+            arr[:] = values
     if arr.ndim != 1:
         raise ValueError("encode_array: need a 1-D sequence")
     count = arr.shape[0]
@@ -206,7 +218,7 @@ def encode_array(values, n, max_int, words):
     else:
         limbs = np.zeros((count, words), dtype=np.uint32)
         expo = np.zeros(count, dtype=np.int64)
-        for i, v in enumerate(values):
+        for i, v in enumerate(arr):
             f = FixedPointNumber.encode(v, n, max_int)
             limbs[i] = _n_limbs(f.encoding, words)
             expo[i] = f.exponent

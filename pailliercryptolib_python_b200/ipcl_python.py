@@ -162,6 +162,10 @@ class PaillierPrivateKey:
 
 
 class PaillierEncryptedNumber:
+    # numpy must not broadcast over this object: `ndarray + ct`, `ndarray * ct`, `ndarray @ ct` defer to the reflected
+    # operators below (the reference only works with a *list* on the left, tests/ipcl_python_test.py:93-98)
+    __array_ufunc__ = None
+
     def __init__(self, public_key: PaillierPublicKey, ciphertext: ipclCipherText, exponents, length: int):
         if ciphertext.public_key != public_key.pubkey:
             raise ValueError("PaillierEncryptedNumber: public key mismatch")

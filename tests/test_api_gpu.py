@@ -97,7 +97,9 @@ def test_matmul_reference_flows(keys, seed):
     got = np.array(pri.decrypt(ct_a @ b)).reshape(m, k)
     assert np.allclose(got, a @ b)
     ct_b = pub.encrypt(b.flatten())
-    got = np.array(pri.decrypt(a @ ct_b)).reshape(m, k)
+    got = np.array(pri.decrypt(a.tolist() @ ct_b)).reshape(m, k)      # list on the left, as the reference test
+    assert np.allclose(got, a @ b)
+    got = np.array(pri.decrypt(a @ ct_b)).reshape(m, k)               # ndarray on the left defers to __rmatmul__
     assert np.allclose(got, a @ b)
     ct_a @= b
     assert np.allclose(np.array(pri.decrypt(ct_a)).reshape(m, k), a @ b)
