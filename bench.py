@@ -282,7 +282,7 @@ def run_gpu(args):
         per_launch_ms = powm_ms / powm_n
         achieved = W_DEC_2048 * (N * args.steps / powm_n) / (per_launch_ms * 1e-3)
         roofline = {
-            "bound": "int_pipe", "kernel": "k_powm<37,2,5> (decrypt: c^(p-1) mod p^2, c^(q-1) mod q^2)",
+            "bound": "int_pipe", "kernel": "k_powm<20,2,5> (decrypt: c^(p-1) mod p^2, c^(q-1) mod q^2)",
             "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s", "frac": achieved / peak,
             "traffic": None, "launch_ms": per_launch_ms, "launches": powm_n,
             "peak_source": "measured live: phe_int_pipe_peak (IMAD.WIDE.U32 issue rate, all SMs)",

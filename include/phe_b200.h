@@ -126,9 +126,10 @@ int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint
 /* ---- host-only helpers exposed for the CPU test-suite (no GPU needed) --------------------------------------- */
 
 /* Montgomery context block exactly as uploaded to the device for modulus `mod` (mod_words words) in the
- * lane-group shape (L, TPI): 5 entries x KP words: N, R^2 mod N, R mod N, 1, extra (extra = x_words words, already
- * reduced).  Returns KP (>0) or <0 on error.  out may be NULL to query KP.  n0inv_out = -N^-1 mod 2^28. */
-int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, uint32_t* out, uint32_t* n0inv_out);
+ * lane-group shape (L, TPI): 5 entries x KP doubles (each the exact integer value of one 52-bit limb, padded
+ * [TPI][LP] layout): N, R^2 mod N, R mod N, 1, extra (0 here), R = 2^(52 L TPI).  Returns KP (>0) or <0 on
+ * error.  out may be NULL to query KP.  n0inv_out = -N^-1 mod 2^52. */
+int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, double* out, uint64_t* n0inv_out);
 /* base^exp mod modulus on the host bignum (key-setup arithmetic), words words each. */
 int phe_host_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulus, int words, uint32_t* out);
 /* Shape selection: writes L, TPI for a modulus of `mod_bits` bits; returns 0 or error. */

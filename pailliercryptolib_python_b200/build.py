@@ -19,8 +19,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--cudart", "static",
 ]
-CU_SOURCES = ["phe_api.cu", "pipe_peak.cu", "shape_37_1.cu", "shape_37_2.cu", "shape_37_4.cu", "shape_28_2.cu", "shape_28_4.cu", "shape_28_8.cu"]
-HEADERS = ["mont28.cuh", "paillier_items.cuh", "phe_kernels.cuh", "phe_launch.cuh", "phe_shapes.hpp", "hostbn.hpp",
+CU_SOURCES = ["phe_api.cu", "pipe_peak.cu"] + ["shape_%d_%d.cu" % s for s in ((20, 1), (20, 2), (20, 4), (20, 8), (15, 4), (15, 8))]
+HEADERS = ["mont52.cuh", "paillier_items.cuh", "phe_kernels.cuh", "phe_launch.cuh", "phe_shapes.hpp", "hostbn.hpp",
            os.path.join("..", "..", "include", "phe_b200.h")]
 
 

@@ -256,9 +256,10 @@ def host_mont_block(modulus, mod_words, L, TPI):
     kp = lib().phe_host_mont_block(_p(int_to_words(modulus, mod_words)), mod_words, L, TPI, None, None)
     if kp <= 0:
         raise RuntimeError(lib().phe_last_error().decode())
-    out = np.zeros(5 * kp, dtype=np.uint32)
-    n0 = ctypes.c_uint32()
-    lib().phe_host_mont_block(_p(int_to_words(modulus, mod_words)), mod_words, L, TPI, _p(out), ctypes.byref(n0))
+    out = np.zeros(5 * kp, dtype=np.float64)
+    n0 = ctypes.c_uint64()
+    lib().phe_host_mont_block(_p(int_to_words(modulus, mod_words)), mod_words, L, TPI,
+                              out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(n0))
     return out.reshape(5, kp), n0.value
 
 

@@ -1,0 +1,414 @@
+// mont52.cuh -- radix-2^52 cooperative Montgomery arithmetic on the FP64 pipe of sm_100a.
+//
+// Replaces the reference's ipcl::modExp -> mbx_exp_mb8 inner loop (reached from
+// /root/reference/src/ipcl_python/bindings/ipcl_bindings_classes.cpp:53-60 (encrypt), :127-133 (decrypt),
+// :318-325 (CipherText + and *)).  mbx_exp_mb8 itself keeps radix-2^52 digits in 64-bit AVX-512 lanes and
+// multiplies them with vpmadd52{l,h}uq; the B200 has no 52-bit integer multiplier, but its FP64 pipe issues
+// DFMA at twice the rate of IMAD.WIDE (profiles/r01_pipe_probe2.json: 17.2 vs 8.2 T lane-ops/s) and one DFMA
+// covers a 52x52-bit partial product half, i.e. 2.64 32x32 MACs' worth of bits in two instructions.
+//
+// Exact double-word product of two 52-bit integers held in doubles (Emmart/Zheng/Weems, ARITH 2018):
+//     ph = fma_rz(a, b, 2^104)            = 2^104 + hi * 2^52        (hi = floor(a b / 2^52) sits in the mantissa)
+//     pl = fma_rz(a, b, (2^104 + 2^52) - ph) = 2^52 + lo              (lo = a b mod 2^52 sits in the mantissa)
+// The raw IEEE bit patterns of ph and pl are summed into 64-bit integer column accumulators (IADD3 on the ALU
+// pipe, which is otherwise idle); the exponent-field constants 0x467<<52 and 0x433<<52 only touch the top 12
+// bits, so everything done modulo 2^52 (the Montgomery quotient digit) can ignore them, and each column is
+// pre-loaded with minus the total bias it will collect over its lifetime, so it is a true integer when retired.
+//
+// Layout: a K = L*TPI limb number is spread over TPI adjacent lanes ("group"); lane t holds limbs
+// [t*L, (t+1)*L) as doubles in registers.  The multiplier operand b is read row by row from shared memory
+// (doubles, [TPI][LP] padded layout).  All limbs entering and leaving montmul are exact integers < 2^52
+// (required: a product must stay below 2^104).
+//
+// The same source compiles for the host (lock-step lane emulator of the CPU tests: tests/emu); the host build
+// must run with the rounding mode set to FE_TOWARDZERO and be compiled with -frounding-math.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#if !defined(__CUDA_ARCH__)
+#include <cmath>
+#endif
+
+#if defined(__CUDACC__)
+#define PHE_HD __host__ __device__ __forceinline__
+#define PHE_D __device__ __forceinline__
+#else
+#define PHE_HD inline
+#define PHE_D inline
+#endif
+
+namespace phe {
+
+constexpr int LW = 52;
+constexpr uint64_t M52 = (1ull << 52) - 1ull;
+constexpr uint64_t BIAS_LO = 0x433ull << 52;   // bit pattern of 2^52
+constexpr uint64_t BIAS_HI = 0x467ull << 52;   // bit pattern of 2^104
+constexpr double TWO52 = 4503599627370496.0;                      // 2^52
+constexpr double TWO104 = 20282409603651670423947251286016.0;     // 2^104
+constexpr double TWO104P52 = 20282409603651674927546878656512.0;  // 2^104 + 2^52
+
+// limbs per lane padded to an even count: every lane block starts 16-byte aligned
+template <int L> struct Pad { static constexpr int LP = (L + 1) & ~1; };
+
+template <int L, int TPI> struct Shape {
+  static constexpr int LP = Pad<L>::LP;
+  static constexpr int K = L * TPI;
+  static constexpr int KP = LP * TPI;      // doubles per entry
+  static constexpr int BITS = K * LW;
+};
+
+PHE_HD double u2d(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)v);
+#else
+  double d; std::memcpy(&d, &v, 8); return d;
+#endif
+}
+PHE_HD uint64_t d2u(double d) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(d);
+#else
+  uint64_t v; std::memcpy(&v, &d, 8); return v;
+#endif
+}
+PHE_HD double fma_rz(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rz(a, b, c);
+#else
+  return std::fma(a, b, c);   // host: thread rounding mode is FE_TOWARDZERO (tests/emu)
+#endif
+}
+// integer < 2^52 <-> limb (double holding that integer)
+PHE_HD double limb_of(uint64_t x) { return u2d(x | BIAS_LO) - TWO52; }
+PHE_HD uint64_t int_of(double d) { return d2u(d + TWO52) & M52; }
+
+#if defined(__CUDACC__)
+template <int TPI> struct DevEnv {
+  static PHE_D int lane() { return (int)(threadIdx.x & (TPI - 1)); }
+  static PHE_D uint32_t bcast(uint32_t v, int src) {
+    if (TPI == 1) return v;
+    return __shfl_sync(0xffffffffu, v, src, TPI);
+  }
+  static PHE_D uint32_t from_above(uint32_t v) {
+    if (TPI == 1) return 0u;
+    return __shfl_down_sync(0xffffffffu, v, 1, TPI);
+  }
+  static PHE_D uint32_t from_below(uint32_t v) {
+    if (TPI == 1) return 0u;
+    return __shfl_up_sync(0xffffffffu, v, 1, TPI);
+  }
+  // true if the predicate holds in any lane of (a superset of) the group; callers are warp-convergent
+  static PHE_D bool any(bool p) {
+    if (TPI == 1) return p;
+    return __any_sync(0xffffffffu, p) != 0;
+  }
+  static PHE_D void sync() { __syncwarp(); }
+};
+#endif
+
+template <class Env> PHE_HD uint64_t bcast64(uint64_t v, int src) {
+  const uint32_t lo = Env::bcast((uint32_t)v, src), hi = Env::bcast((uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+template <class Env> PHE_HD uint64_t from_above64(uint64_t v) {
+  const uint32_t lo = Env::from_above((uint32_t)v), hi = Env::from_above((uint32_t)(v >> 32));
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// bias a column must be pre-charged with (negated) when it will still receive `nlo` low halves and `nhi` high halves
+PHE_HD constexpr uint64_t bias_of(int nlo, int nhi) {
+  return (uint64_t)nlo * BIAS_LO + (uint64_t)nhi * BIAS_HI;   // mod 2^64
+}
+
+template <int L> PHE_HD uint32_t ripple(uint64_t (&x)[L], uint32_t cin) {
+  uint64_t c = cin;
+#pragma unroll
+  for (int j = 0; j < L; ++j) { const uint64_t v = x[j] + c; x[j] = v & M52; c = v >> LW; }
+  return (uint32_t)c;
+}
+
+// Columns (true integers, each < 2^63) -> exact limbs < 2^52 across the whole group.  Value must fit in K limbs.
+template <int L, int TPI, class Env> PHE_HD void normalize_exact(uint64_t (&x)[L]) {
+  const int lane = Env::lane();
+  uint32_t cout = ripple<L>(x, 0u);
+#pragma unroll 1
+  for (int s = 1; s < TPI; ++s) {
+    uint32_t cin = Env::from_below(cout);
+    if (lane == 0) cin = 0;
+    x[0] += cin;
+    cout = 0;
+    if (Env::any(x[0] > M52)) cout = ripple<L>(x, 0u);   // a second-order carry: probability ~2^-40 per product
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Product spans.  mac_first: column += lo(x*y), hprev = hi(x*y).  mac_span: for c in [C0, C1):
+// acc[(c + rot) % L] += lo(x[c]*y) + hprev; hprev = hi(x[c]*y)  -- written in batches of G independent
+// ph / sub / pl chains so that the FP64 pipe always has several products in flight.  G covers the whole span:
+// with smaller batches (5, and for some kernels 10) ptxas re-serialises the chains one product at a time
+// (~17 stall cycles per DFMA instead of ~7 in the SASS control words, 180 instead of 250 registers).
+// x may be a register array or a pointer (modulus limbs in shared memory: identical for every item of a CTA,
+// so they cost broadcast LDS.128 instead of 2L live registers per lane).
+// ------------------------------------------------------------------------------------------------
+#ifndef PHE52_G
+#define PHE52_G 20
+#endif
+PHE_HD void mac_first(uint64_t& col, double x, double y, uint64_t& hprev) {
+  const double ph = fma_rz(x, y, TWO104);
+  const double pl = fma_rz(x, y, TWO104P52 - ph);
+  col += d2u(pl);
+  hprev = d2u(ph);
+}
+
+template <int L, int C0, int C1, class X, int G = PHE52_G>
+PHE_HD void mac_span(uint64_t (&acc)[L], const X& x, double y, uint64_t& hprev, int rot) {
+#pragma unroll
+  for (int c = C0; c < C1; c += G) {
+    double xv[G], ph[G], pl[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) if (c + g < C1) xv[g] = x[c + g];
+#pragma unroll
+    for (int g = 0; g < G; ++g) if (c + g < C1) ph[g] = fma_rz(xv[g], y, TWO104);
+#pragma unroll
+    for (int g = 0; g < G; ++g) if (c + g < C1) pl[g] = TWO104P52 - ph[g];
+#pragma unroll
+    for (int g = 0; g < G; ++g) if (c + g < C1) pl[g] = fma_rz(xv[g], y, pl[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) if (c + g < C1) { acc[(c + g + rot) % L] += d2u(pl[g]) + hprev; hprev = d2u(ph[g]); }
+  }
+}
+
+// The row loop is unrolled U rows at a time (U divides L): inside a chunk column c of row u lives in
+// acc[(c + u) % L]; after the chunk the accumulators are rotated back by U places.  A fully unrolled L-row body
+// (77 KB at L = 20) misses the 32 KB L1.5 instruction cache on every pass -- ncu: no_instruction = 2.3 stalled
+// warps per issue -- so the body is kept under ~20 KB.
+#ifndef PHE52_U
+#define PHE52_U 5
+#endif
+template <int L> struct Unroll { static constexpr int U = (L % PHE52_U == 0) ? PHE52_U : (L % 5 == 0) ? 5 : (L % 4 == 0) ? 4 : (L % 3 == 0) ? 3 : (L % 2 == 0) ? 2 : 1; };
+
+// index of limb `row` in the padded [TPI][LP] layout
+template <int L> PHE_HD int padded_index(int row) {
+  constexpr int LP = Pad<L>::LP;
+  if (LP == L) return row;
+  return row + (row / L) * (LP - L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Montgomery product, R = 2^(52*L*TPI):  r = a * b * R^-1 mod n, exact limbs, value < a*b/R + n, i.e. < 2n for
+// a < 4n, b < 2n (R >= 8n: every shape is chosen with at least 8 bits of headroom).
+//   a: registers; b: shared memory doubles [TPI][LP]; n_entry: modulus, padded entry in shared memory;
+//   all exact limbs.  n0inv = -n^-1 mod 2^52.
+//   CAPQ: also store the Montgomery quotient digits q_i to qcap (memory, padded [TPI][LP] layout, lane 0 writes).
+// Row i adds a*b_i (A-part) and n*q_i (N-part) and retires column 0.  The loop is software-pipelined so the
+// quotient digit never sits on the critical path: iteration i does N-part(i) for columns 0,1, retires column 0,
+// adds a[0]*b_(i+1), derives q_(i+1) and starts its broadcast, and only then runs the remaining 2(L-1) products
+// of N-part(i) and A-part(i+1), which hide the IMAD/SHFL latency of the digit.
+// ------------------------------------------------------------------------------------------------
+template <int L, int TPI, class Env, bool CAPQ = false>
+PHE_HD void montmul(double (&r)[L], const double (&a)[L], const double* b, const double* n_entry, uint64_t n0inv,
+                    uint64_t* qcap = nullptr) {
+  static_assert(L >= 2 && L <= 64, "limbs per lane out of range");
+  constexpr int K = L * TPI;
+  constexpr int U = Unroll<L>::U;
+  const int lane = Env::lane();
+  const double* n = n_entry + lane * Pad<L>::LP;
+  const uint64_t topmask = (lane == TPI - 1) ? 0ull : ~0ull;
+  constexpr uint64_t INIT = 0ull - bias_of(2 * L, 2 * L);
+  uint64_t acc[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) acc[j] = 0ull - bias_of(2 * (j + 1), 2 * j);
+
+  uint64_t topA, q;
+  double qd;
+  {  // prologue: A-part of row 0 and its quotient digit
+    const double b0 = b[0];
+    uint64_t h;
+    mac_first(acc[0], a[0], b0, h);
+    q = bcast64<Env>((acc[0] * n0inv) & M52, 0);
+    mac_span<L, 1, L>(acc, a, b0, h, 0);
+    topA = h;
+    qd = limb_of(q);
+  }
+#pragma unroll 1
+  for (int row0 = 0; row0 < K; row0 += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {   // row i = row0 + u; column c of row i lives in acc[(c + u) % L]
+      const int row = row0 + u;
+      const bool last = (u == U - 1) && (row == K - 1);
+      if (CAPQ) { if (lane == 0) qcap[padded_index<L>(row)] = q; }
+      uint64_t hN, hA = 0;
+      const double n0 = n[0], n1 = n[1];
+      mac_first(acc[u % L], n0, qd, hN);
+      {
+        const double ph = fma_rz(n1, qd, TWO104);
+        const double pl = fma_rz(n1, qd, TWO104P52 - ph);
+        const uint64_t low = acc[u % L];                  // column 0 is complete: retire it
+        acc[(u + 1) % L] += d2u(pl) + hN + (low >> LW);
+        hN = d2u(ph);
+        acc[u % L] = from_above64<Env>(low & M52) & topmask;   // becomes the new top column (column L of row i)
+      }
+      double bn = 0.0;
+      if (!last) {
+        bn = b[padded_index<L>(row + 1)];
+        mac_first(acc[(u + 1) % L], a[0], bn, hA);
+        q = bcast64<Env>((acc[(u + 1) % L] * n0inv) & M52, 0);
+      }
+      mac_span<L, 2, L>(acc, n, qd, hN, u);
+      acc[u % L] += topA + hN + INIT;
+      if (!last) {
+        mac_span<L, 1, L>(acc, a, bn, hA, u + 1);
+        topA = hA;
+        qd = limb_of(q);
+      }
+    }
+    if (U != L) {   // rotate back: column c returns to acc[c]
+      uint64_t t[L];
+#pragma unroll
+      for (int j = 0; j < L; ++j) t[j] = acc[(j + U) % L];
+#pragma unroll
+      for (int j = 0; j < L; ++j) acc[j] = t[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < L; ++j) acc[j] += bias_of(2 * (j + 1), 2 * j);
+  normalize_exact<L, TPI, Env>(acc);
+#pragma unroll
+  for (int j = 0; j < L; ++j) r[j] = limb_of(acc[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact helpers on integer limbs (used once per result, not in the exponentiation loop)
+// ------------------------------------------------------------------------------------------------
+template <int L> PHE_HD void ints_of(uint64_t (&x)[L], const double (&d)[L]) {
+#pragma unroll
+  for (int j = 0; j < L; ++j) x[j] = int_of(d[j]);
+}
+template <int L> PHE_HD void limbs_of(double (&d)[L], const uint64_t (&x)[L]) {
+#pragma unroll
+  for (int j = 0; j < L; ++j) d[j] = limb_of(x[j]);
+}
+
+// x (exact) -= y (exact) across the group; returns 1 in every lane if the result went negative
+// (then x holds the result mod 2^(52K)).
+template <int L, int TPI, class Env> PHE_HD uint32_t sub_exact(uint64_t (&x)[L], const uint64_t (&y)[L]) {
+  const int lane = Env::lane();
+  uint32_t bw = 0;
+#pragma unroll
+  for (int j = 0; j < L; ++j) { const uint64_t v = x[j] - y[j] - bw; x[j] = v & M52; bw = (uint32_t)(v >> 63); }
+  uint32_t any = bw;   // a lane borrows out at most once over all rounds; the top lane's is the sign
+#pragma unroll 1
+  for (int s = 1; s < TPI; ++s) {
+    uint32_t b2 = Env::from_below(bw);
+    if (lane == 0) b2 = 0;
+    bw = 0;
+    if (Env::any(b2 != 0)) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) { const uint64_t v = x[j] - b2; x[j] = v & M52; b2 = (uint32_t)(v >> 63); }
+      bw = b2;
+    }
+    any |= bw;
+  }
+  return Env::bcast(any, TPI - 1);
+}
+
+// x (exact) += y (exact) across the group (carry out of the top is dropped).
+template <int L, int TPI, class Env> PHE_HD void add_exact(uint64_t (&x)[L], const uint64_t (&y)[L]) {
+#pragma unroll
+  for (int j = 0; j < L; ++j) x[j] += y[j];
+  normalize_exact<L, TPI, Env>(x);
+}
+
+// if x >= n: x -= n   (x exact)
+template <int L, int TPI, class Env> PHE_HD void cond_sub(uint64_t (&x)[L], const uint64_t (&n)[L]) {
+  uint64_t d[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) d[j] = x[j];
+  const uint32_t neg = sub_exact<L, TPI, Env>(d, n);
+  if (!neg) {
+#pragma unroll
+    for (int j = 0; j < L; ++j) x[j] = d[j];
+  }
+}
+
+// this lane's integer limbs of a padded entry
+template <int L, int TPI, class Env> PHE_HD void ints_from_entry(uint64_t (&x)[L], const double* entry) {
+  const double* s = entry + Env::lane() * Pad<L>::LP;
+#pragma unroll
+  for (int j = 0; j < L; ++j) x[j] = int_of(s[j]);
+}
+
+// montmul result (< 2n, exact limbs) -> canonical integer limbs in [0, n)
+template <int L, int TPI, class Env> PHE_HD void canonical_ints(uint64_t (&x)[L], const double (&v)[L], const double* n_entry) {
+  uint64_t ni[L];
+  ints_of<L>(x, v);
+  ints_from_entry<L, TPI, Env>(ni, n_entry);
+  cond_sub<L, TPI, Env>(x, ni);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout conversion
+// ------------------------------------------------------------------------------------------------
+
+// Integer limbs [lane*L, lane*L+L) of the little-endian u32 word array w[0..nwords) (words beyond are zero).
+template <int L, int TPI, class Env>
+PHE_HD void ints_from_words(uint64_t (&x)[L], const uint32_t* w, int nwords) {
+  const int lane = Env::lane();
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    const int bit = (lane * L + j) * LW;
+    const int wi = bit >> 5;
+    const uint32_t sh = (uint32_t)(bit & 31);
+    const uint64_t w0 = (wi < nwords) ? w[wi] : 0u;
+    const uint64_t w1 = (wi + 1 < nwords) ? w[wi + 1] : 0u;
+    const uint64_t w2 = (wi + 2 < nwords) ? w[wi + 2] : 0u;
+    uint64_t v = (w0 | (w1 << 32)) >> sh;
+    if (sh) v |= w2 << (64 - sh);
+    x[j] = v & M52;
+  }
+}
+template <int L, int TPI, class Env>
+PHE_HD void limbs_from_words(double (&x)[L], const uint32_t* w, int nwords) {
+  uint64_t t[L];
+  ints_from_words<L, TPI, Env>(t, w, nwords);
+  limbs_of<L>(x, t);
+}
+
+// Lane-block padded limb array ([TPI][LP] doubles, shared or global memory) <- registers.  Caller syncs.
+template <int L, int TPI, class Env> PHE_HD void limbs_to_mem(double* dst, const double (&x)[L]) {
+  constexpr int LP = Pad<L>::LP;
+  double* d = dst + Env::lane() * LP;
+#pragma unroll
+  for (int j = 0; j < L; ++j) d[j] = x[j];
+#pragma unroll
+  for (int j = L; j < LP; ++j) d[j] = 0.0;
+}
+template <int L, int TPI, class Env> PHE_HD void limbs_from_mem(double (&x)[L], const double* src) {
+  constexpr int LP = Pad<L>::LP;
+  const double* s = src + Env::lane() * LP;
+#pragma unroll
+  for (int j = 0; j < L; ++j) x[j] = s[j];
+}
+template <int L, int TPI, class Env> PHE_HD void ints_to_mem(uint64_t* dst, const uint64_t (&x)[L]) {
+  constexpr int LP = Pad<L>::LP;
+  uint64_t* d = dst + Env::lane() * LP;
+#pragma unroll
+  for (int j = 0; j < L; ++j) d[j] = x[j];
+#pragma unroll
+  for (int j = L; j < LP; ++j) d[j] = 0ull;
+}
+
+// Word v of the number whose exact integer limbs sit in the padded array.
+template <int L, int TPI> PHE_HD uint32_t word_from_ints(const uint64_t* limbs, int v) {
+  constexpr int LP = Pad<L>::LP;
+  constexpr int K = L * TPI;
+  const int bit = v * 32;
+  const int g = bit / LW;
+  const int o = bit - g * LW;
+  uint64_t u = 0;
+  if (g < K) u = limbs[(g / L) * LP + (g % L)] >> o;
+  if (o > LW - 32 && g + 1 < K) u |= limbs[((g + 1) / L) * LP + ((g + 1) % L)] << (LW - o);
+  return (uint32_t)u;
+}
+
+}  // namespace phe

@@ -1,49 +1,47 @@
-// paillier_items.cuh -- per-item (one bignum per lane group) bodies of the Paillier hot path.
-// Each body is a template over Env so that the CUDA kernels (phe_kernels.cu) and the host lockstep
-// emulator (tests/emu) run the same code.
+// paillier_items.cuh -- per-item (one bignum per lane group) bodies of the Paillier hot path on the radix-2^52
+// FP64 Montgomery engine (mont52.cuh).  Each body is a template over Env so that the CUDA kernels
+// (phe_kernels.cuh) and the host lockstep emulator (tests/emu) run the same code.
 //
-// Constant blocks ("entries") live in the padded limb layout [TPI][LP] (KP = TPI*LP u32 words each).
+// Constant blocks ("entries") are doubles in the padded limb layout [TPI][LP] (KP doubles each), every limb an
+// exact integer < 2^52.  Every body funnels its Montgomery products through ONE montmul call site: the unrolled
+// product is ~22 KB of code and the L1.5 instruction cache holds 32 KB.
 #pragma once
-#include "mont28.cuh"
+#include "mont52.cuh"
 
 namespace phe {
 
 // Shared-memory regions private to one lane group.
 struct GroupSmem {
-  uint32_t* b0;   // KP words: multiplier operand buffer
-  uint32_t* b1;   // KP words: second operand buffer / limb staging for stores
+  double* b0;   // KP doubles: multiplier operand buffer
+  double* b1;   // KP doubles: second operand buffer / integer limb staging for stores
 };
 
-template <int L, int TPI> struct Shape {
-  static constexpr int LP = Pad<L>::LP;
-  static constexpr int K = L * TPI;
-  static constexpr int KP = LP * TPI;
-  static constexpr int BITS = K * LW;
-};
+struct alignas(16) D2 { double x, y; };
 
 // entry (padded limb layout, global or shared) -> this lane's registers
-template <int L, int TPI, class Env> PHE_HD void load_entry(uint32_t (&x)[L], const uint32_t* e) {
-  limbs_from_smem<L, TPI, Env>(x, e);
+template <int L, int TPI, class Env> PHE_HD void load_entry(double (&x)[L], const double* e) {
+  limbs_from_mem<L, TPI, Env>(x, e);
 }
 
-// cooperative copy of one padded entry (KP words) into a group smem buffer; lane copies its own block
-template <int L, int TPI, class Env> PHE_HD void copy_entry(uint32_t* dst, const uint32_t* src) {
+// cooperative copy of one padded entry (KP doubles) into a group buffer; each lane copies its own block
+template <int L, int TPI, class Env> PHE_HD void copy_entry(double* dst, const double* src) {
   constexpr int LP = Pad<L>::LP;
   const int lane = Env::lane();
-  const U4* s = reinterpret_cast<const U4*>(src + lane * LP);
-  U4* d = reinterpret_cast<U4*>(dst + lane * LP);
+  const D2* s = reinterpret_cast<const D2*>(src + lane * LP);
+  D2* d = reinterpret_cast<D2*>(dst + lane * LP);
 #pragma unroll
-  for (int j = 0; j < LP / 4; ++j) d[j] = s[j];
+  for (int j = 0; j < LP / 2; ++j) d[j] = s[j];
 }
 
-// canonical exact limbs (registers) -> little-endian u32 words in global memory
+// canonical integer limbs (registers) -> little-endian u32 words in global memory
 template <int L, int TPI, class Env>
-PHE_HD void store_words(uint32_t* out, int nwords, const uint32_t (&x)[L], uint32_t* stage) {
+PHE_HD void store_words(uint32_t* out, int nwords, const uint64_t (&x)[L], double* stage) {
+  uint64_t* st = reinterpret_cast<uint64_t*>(stage);
   Env::sync();
-  limbs_to_smem<L, TPI, Env>(stage, x);
+  ints_to_mem<L, TPI, Env>(st, x);
   Env::sync();
   if (out) {   // null: this group is a padding duplicate of the last item (block-uniform loops), skip the store
-    for (int v = Env::lane(); v < nwords; v += TPI) out[v] = word_from_smem_limbs<L, TPI>(stage, v);
+    for (int v = Env::lane(); v < nwords; v += TPI) out[v] = word_from_ints<L, TPI>(st, v);
   }
   Env::sync();
 }
@@ -53,53 +51,59 @@ PHE_HD uint32_t get_bits(const uint32_t* w, int nwords, int pos, int width) {
   const int wi = pos >> 5;
   const uint32_t lo = (wi < nwords) ? w[wi] : 0u;
   const uint32_t hi = (wi + 1 < nwords) ? w[wi + 1] : 0u;
-  return funnel_r(lo, hi, (uint32_t)(pos & 31)) & ((1u << width) - 1u);
+  const uint32_t sh = (uint32_t)(pos & 31);
+  const uint64_t two = ((uint64_t)hi << 32) | lo;
+  return (uint32_t)(two >> sh) & ((1u << width) - 1u);
+}
+
+// x (montmul result) -> canonical, + 1, exact limbs again (1 + m n < n^2 always)
+template <int L, int TPI, class Env> PHE_HD void canonical_plus_one(double (&x)[L], const double* n_entry) {
+  uint64_t xi[L];
+  canonical_ints<L, TPI, Env>(xi, x, n_entry);
+  if (Env::lane() == 0) xi[0] += 1ull;
+  normalize_exact<L, TPI, Env>(xi);
+  limbs_of<L>(x, xi);
 }
 
 // ------------------------------------------------------------------------------------------------
 // HE add: out = a * b mod N  (ipcl::CipherText::operator+ -> raw_add; ipcl_bindings_classes.cpp:318-321)
 // ------------------------------------------------------------------------------------------------
 template <int L, int TPI, class Env>
-PHE_HD void item_modmul(const uint32_t* a_w, const uint32_t* b_w, uint32_t* out_w, int nwords,
-                        const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* r2, GroupSmem sm) {
-  uint32_t x[L];
-  {
-    uint32_t y[L];
-    limbs_from_words<L, TPI, Env>(y, b_w, nwords);
-    Env::sync();
-    limbs_to_smem<L, TPI, Env>(sm.b0, y);
-  }
+PHE_HD void item_modmul(const uint32_t* a_w, const uint32_t* b_w, uint32_t* out_w, int nwords, const double* n_entry,
+                        uint64_t n0inv, const double* r2, GroupSmem sm) {
+  double x[L];
+  limbs_from_words<L, TPI, Env>(x, b_w, nwords);
+  Env::sync();
+  limbs_to_mem<L, TPI, Env>(sm.b0, x);
   limbs_from_words<L, TPI, Env>(x, a_w, nwords);
   Env::sync();
-  const uint32_t* bp = sm.b0;
+  const double* bp = sm.b0;
 #pragma unroll 1
   for (int step = 0; step < 2; ++step) {   // one montmul call site: a*b*R^-1, then *R^2*R^-1
-    montmul<L, TPI, Env>(x, x, bp, n, n0inv);
+    montmul<L, TPI, Env>(x, x, bp, n_entry, n0inv);
     bp = r2;
   }
-  canonicalize<L, TPI, Env>(x, n);
-  store_words<L, TPI, Env>(out_w, nwords, x, sm.b1);
+  uint64_t xi[L];
+  canonical_ints<L, TPI, Env>(xi, x, n_entry);
+  store_words<L, TPI, Env>(out_w, nwords, xi, sm.b1);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sliding-free fixed-window exponentiation, one montmul call site.
+// Fixed-window exponentiation, one montmul call site.
 //   base: either words (to-Montgomery conversion done here) or a Montgomery-form entry (base_mont).
 //   exponent: little-endian words, ebits significant bits (uniform across the launch).
-//   table: (1<<WIN) entries of KP words in global memory, private to this group.
+//   table: (1<<WIN) entries of KP doubles in global memory, private to this group.
 //   result: canonical words (out_w) after leaving the Montgomery domain.
 // Replaces ipcl::modExp element: a^e mod N.
 // ------------------------------------------------------------------------------------------------
 template <int L, int TPI, class Env, int WIN>
-PHE_HD void item_powm(const uint32_t* base_w, int base_words, const uint32_t* base_mont,
-                      const uint32_t* e_w, int e_words, int ebits, uint32_t* out_w, int out_words,
-                      const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* r2, const uint32_t* oneM,
-                      const uint32_t* one_plain, uint32_t* tbl, GroupSmem sm) {
+PHE_HD void item_powm(const uint32_t* base_w, int base_words, const double* base_mont, const uint32_t* e_w,
+                      int e_words, int ebits, uint32_t* out_w, int out_words, const double* n_entry, uint64_t n0inv,
+                      const double* r2, const double* oneM, const double* one_plain, double* tbl, GroupSmem sm) {
   constexpr int KP = Shape<L, TPI>::KP;
-  constexpr int LP = Pad<L>::LP;
   constexpr int TS = 1 << WIN;
-  const int lane = Env::lane();
   const int nd = (ebits + WIN - 1) / WIN;   // number of digits (>= 1)
-  uint32_t x[L];
+  double x[L];
 
   enum { P_TOMONT = 0, P_TABLE = 1, P_SQR = 2, P_MUL = 3, P_FROMMONT = 4 };
   int phase, ti = 2, sq = 0, w = nd - 2;
@@ -112,20 +116,15 @@ PHE_HD void item_powm(const uint32_t* base_w, int base_words, const uint32_t* ba
     phase = P_TOMONT;
   }
 
-  const uint32_t* bp = r2;
+  const double* bp = r2;
 #pragma unroll 1
   for (;;) {
     if (phase == -1) {
       // x holds xM: start the table
       Env::sync();
-      limbs_to_smem<L, TPI, Env>(sm.b0, x);                 // b0 = xM for the whole table build
-      limbs_to_smem<L, TPI, Env>(tbl + 1 * KP, x);          // T[1]
-      { // T[0] = R mod n
-        const U4* s = reinterpret_cast<const U4*>(oneM + lane * LP);
-        U4* d = reinterpret_cast<U4*>(tbl + lane * LP);
-#pragma unroll
-        for (int j = 0; j < LP / 4; ++j) d[j] = s[j];
-      }
+      limbs_to_mem<L, TPI, Env>(sm.b0, x);                  // b0 = xM for the whole table build
+      limbs_to_mem<L, TPI, Env>(tbl + 1 * KP, x);           // T[1]
+      copy_entry<L, TPI, Env>(tbl, oneM);                   // T[0] = R mod n
       Env::sync();
       if (TS > 2) { phase = P_TABLE; bp = sm.b0; }
       else phase = -2;
@@ -139,7 +138,7 @@ PHE_HD void item_powm(const uint32_t* base_w, int base_words, const uint32_t* ba
     }
     if (phase == P_SQR) {
       Env::sync();
-      limbs_to_smem<L, TPI, Env>(sm.b1, x);
+      limbs_to_mem<L, TPI, Env>(sm.b1, x);
       Env::sync();
       bp = sm.b1;
     } else if (phase == P_MUL) {
@@ -150,12 +149,12 @@ PHE_HD void item_powm(const uint32_t* base_w, int base_words, const uint32_t* ba
       bp = sm.b1;
     }
 
-    montmul<L, TPI, Env>(x, x, bp, n, n0inv);
+    montmul<L, TPI, Env>(x, x, bp, n_entry, n0inv);
 
     if (phase == P_TOMONT) {
       phase = -1;
     } else if (phase == P_TABLE) {
-      limbs_to_smem<L, TPI, Env>(tbl + ti * KP, x);
+      limbs_to_mem<L, TPI, Env>(tbl + ti * KP, x);
       if (++ti == TS) phase = -2;
     } else if (phase == P_SQR) {
       if (++sq == WIN) phase = P_MUL;
@@ -166,34 +165,37 @@ PHE_HD void item_powm(const uint32_t* base_w, int base_words, const uint32_t* ba
       break;
     }
   }
-  canonicalize<L, TPI, Env>(x, n);
-  store_words<L, TPI, Env>(out_w, out_words, x, sm.b1);
+  uint64_t xi[L];
+  canonical_ints<L, TPI, Env>(xi, x, n_entry);
+  store_words<L, TPI, Env>(out_w, out_words, xi, sm.b1);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Decrypt pre-reduction: xM = c * R mod x^2 from the double-width ciphertext c = c_lo + 2^(32*hw) c_hi:
 //   xM = montmul(c_lo, R^2) + montmul(c_hi, 2^(32 hw) R^2)   (both constants mod x^2).
-// Output: Montgomery-form entry (padded limbs, almost normalised, value < 4 x^2) in global memory.
+// Output: Montgomery-form entry (padded exact limbs, value < 4 x^2) in global memory.
 // Part of ipcl::PrivateKey::decrypt -> decryptCRT (ipcl_bindings_classes.cpp:127-133): "c mod p^2".
 // ------------------------------------------------------------------------------------------------
 template <int L, int TPI, class Env>
-PHE_HD void item_dec_prep(const uint32_t* c_w, int hw, uint32_t* out_entry, const uint32_t (&n)[L], uint32_t n0inv,
-                          const uint32_t* r2, const uint32_t* k2, GroupSmem sm) {
-  uint32_t x[L], acc[L];
+PHE_HD void item_dec_prep(const uint32_t* c_w, int hw, double* out_entry, const double* n_entry, uint64_t n0inv,
+                          const double* r2, const double* k2, GroupSmem sm) {
+  double x[L];
+  uint64_t acc[L];
 #pragma unroll
   for (int j = 0; j < L; ++j) acc[j] = 0;
-  const uint32_t* bp = r2;
+  const double* bp = r2;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     limbs_from_words<L, TPI, Env>(x, c_w + half * hw, hw);
-    montmul<L, TPI, Env>(x, x, bp, n, n0inv);
+    montmul<L, TPI, Env>(x, x, bp, n_entry, n0inv);
 #pragma unroll
-    for (int j = 0; j < L; ++j) acc[j] += x[j];
+    for (int j = 0; j < L; ++j) acc[j] += int_of(x[j]);
     bp = k2;
   }
   (void)sm;
-  normalize_exact<L, TPI, Env>(acc);   // value < 4 x^2 < R: fits; exact limbs keep the column bound of montmul
-  limbs_to_smem<L, TPI, Env>(out_entry, acc);
+  normalize_exact<L, TPI, Env>(acc);   // value < 4 x^2 < R: fits
+  limbs_of<L>(x, acc);
+  limbs_to_mem<L, TPI, Env>(out_entry, x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -205,15 +207,15 @@ PHE_HD void item_dec_prep(const uint32_t* c_w, int hw, uint32_t* out_entry, cons
 // ------------------------------------------------------------------------------------------------
 template <int L, int TPI, class Env, int WB>
 PHE_HD void item_encrypt_comb(const uint32_t* m_w, int m_words, const uint32_t* r_w, int r_words, int nwin,
-                              uint32_t* out_w, int out_words, const uint32_t (&n)[L], uint32_t n0inv,
-                              const uint32_t* nR, const uint32_t* comb, GroupSmem sm) {
+                              uint32_t* out_w, int out_words, const double* n_entry, uint64_t n0inv,
+                              const double* nR, const double* comb, GroupSmem sm) {
   constexpr int KP = Shape<L, TPI>::KP;
-  const int lane = Env::lane();
-  uint32_t x[L];
+  double x[L];
+  uint64_t xi[L];
   int j = 1;
   // step kinds: 0 comb multiply, 1 raw (m * nR), 2 final (raw * obf)
   int kind;
-  const uint32_t* bp;
+  const double* bp;
   if (r_w) {
     const uint32_t d0 = get_bits(r_w, r_words, 0, WB);
     load_entry<L, TPI, Env>(x, comb + (size_t)d0 * KP);
@@ -232,7 +234,7 @@ PHE_HD void item_encrypt_comb(const uint32_t* m_w, int m_words, const uint32_t* 
     } else if (kind == 1) {
       if (r_w) {   // park obf*R in b1
         Env::sync();
-        limbs_to_smem<L, TPI, Env>(sm.b1, x);
+        limbs_to_mem<L, TPI, Env>(sm.b1, x);
         Env::sync();
       }
       limbs_from_words<L, TPI, Env>(x, m_w, m_words);
@@ -241,61 +243,62 @@ PHE_HD void item_encrypt_comb(const uint32_t* m_w, int m_words, const uint32_t* 
       bp = sm.b1;
     }
 
-    montmul<L, TPI, Env>(x, x, bp, n, n0inv);
+    montmul<L, TPI, Env>(x, x, bp, n_entry, n0inv);
 
     if (kind == 0) {
       if (++j == nwin) kind = 1;
     } else if (kind == 1) {
-      // x == m*n (mod n^2), < 2 n^2: make it exact and add 1 (1 + m n < n^2 always)
-      canonicalize<L, TPI, Env>(x, n);
-      if (lane == 0) x[0] += 1u;
-      normalize_exact<L, TPI, Env>(x);
-      if (!r_w) break;
+      // x == m*n (mod n^2), < 2 n^2: make it canonical and add 1
+      if (!r_w) {
+        canonical_ints<L, TPI, Env>(xi, x, n_entry);
+        if (Env::lane() == 0) xi[0] += 1ull;
+        normalize_exact<L, TPI, Env>(xi);
+        break;
+      }
+      canonical_plus_one<L, TPI, Env>(x, n_entry);
       kind = 2;
     } else {
-      canonicalize<L, TPI, Env>(x, n);
+      canonical_ints<L, TPI, Env>(xi, x, n_entry);
       break;
     }
   }
-  store_words<L, TPI, Env>(out_w, out_words, x, sm.b0);
+  store_words<L, TPI, Env>(out_w, out_words, xi, sm.b0);
 }
 
 // ------------------------------------------------------------------------------------------------
 // ct = (1 + m n) * obf mod n^2 with obf given as canonical words (classic r^n path, or apply_obfuscator
-// on an existing ciphertext when m_w == nullptr: ct = ct_in * obf).
+// on an existing ciphertext).
 // ------------------------------------------------------------------------------------------------
 template <int L, int TPI, class Env>
 PHE_HD void item_encrypt_finish(const uint32_t* m_w, int m_words, const uint32_t* obf_w, uint32_t* out_w,
-                                int out_words, const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* nR,
-                                const uint32_t* r2, GroupSmem sm) {
-  const int lane = Env::lane();
-  uint32_t x[L];
+                                int out_words, const double* n_entry, uint64_t n0inv, const double* nR,
+                                const double* r2, GroupSmem sm) {
+  double x[L];
   // b1 = obf * R
   limbs_from_words<L, TPI, Env>(x, obf_w, out_words);
-  const uint32_t* bp = r2;
+  const double* bp = r2;
   int kind = 0;
 #pragma unroll 1
   for (;;) {
-    montmul<L, TPI, Env>(x, x, bp, n, n0inv);
+    montmul<L, TPI, Env>(x, x, bp, n_entry, n0inv);
     if (kind == 0) {
       Env::sync();
-      limbs_to_smem<L, TPI, Env>(sm.b1, x);
+      limbs_to_mem<L, TPI, Env>(sm.b1, x);
       Env::sync();
       limbs_from_words<L, TPI, Env>(x, m_w, m_words);
       bp = nR;
       kind = 1;
     } else if (kind == 1) {
-      canonicalize<L, TPI, Env>(x, n);
-      if (lane == 0) x[0] += 1u;
-      normalize_exact<L, TPI, Env>(x);
+      canonical_plus_one<L, TPI, Env>(x, n_entry);
       bp = sm.b1;
       kind = 2;
     } else {
-      canonicalize<L, TPI, Env>(x, n);
       break;
     }
   }
-  store_words<L, TPI, Env>(out_w, out_words, x, sm.b0);
+  uint64_t xi[L];
+  canonical_ints<L, TPI, Env>(xi, x, n_entry);
+  store_words<L, TPI, Env>(out_w, out_words, xi, sm.b0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -305,7 +308,9 @@ PHE_HD void item_encrypt_finish(const uint32_t* m_w, int m_words, const uint32_t
 //       m_x = Lx * h_x mod x
 //   m = m_p + ((m_q - m_p) * p^-1 mod q) * p
 // ipcl::PrivateKey::decryptCRT: computeLfun, *hp/hq, computeCRT.
-// Constant entries (cst, KP words each): see DecTailConst.
+// Constant entries (cst, KP doubles each): see DecTailConst.  Six Montgomery products through one call site:
+//   step 0/2: quotient capture for p / q      step 1/3: * h_p R / * h_q R
+//   step 4:   (m_q - m_p) * p^-1 R mod q      step 5:   h * p R mod n
 // ------------------------------------------------------------------------------------------------
 enum DecTailConst {
   DT_P = 0,       // p padded
@@ -321,52 +326,68 @@ enum DecTailConst {
 
 template <int L, int TPI, class Env>
 PHE_HD void item_dec_tail(const uint32_t* up_w, const uint32_t* uq_w, int u_words, uint32_t* m_w, int m_words,
-                          const uint32_t* cst, const uint32_t* n0invs /* [p, q, n] */, GroupSmem sm) {
+                          const double* cst, const uint64_t* n0invs /* [p, q, n] */, GroupSmem sm) {
   constexpr int KP = Shape<L, TPI>::KP;
+  constexpr int LP = Pad<L>::LP;
   const int lane = Env::lane();
-  uint32_t mod[L], x[L], mp[L], one[L];
-  load_entry<L, TPI, Env>(one, cst + DT_ONE * KP);
+  double x[L];
+  uint64_t xi[L], mp[L], one[L];
+  uint64_t* qbuf = reinterpret_cast<uint64_t*>(sm.b1);
+  ints_from_entry<L, TPI, Env>(one, cst + DT_ONE * KP);
 #pragma unroll
   for (int j = 0; j < L; ++j) mp[j] = 0;
 
 #pragma unroll 1
-  for (int idx = 0; idx < 2; ++idx) {
-    load_entry<L, TPI, Env>(mod, cst + (idx ? DT_Q : DT_P) * KP);
-    const uint32_t n0 = n0invs[idx];
-    limbs_from_words<L, TPI, Env>(x, idx ? uq_w : up_w, u_words);
-    sub_exact<L, TPI, Env>(x, one);                                  // u - 1  (u >= 1)
-    uint32_t q[L];
+  for (int step = 0; step < 6; ++step) {
+    const int idx = (step >> 1) & 1;                       // 0: p, 1: q   (steps 0..3)
+    const double* mod_e = cst + (step < 2 ? DT_P : step < 5 ? DT_Q : DT_N) * KP;
+    const uint64_t n0 = n0invs[step < 2 ? 0 : step < 5 ? 1 : 2];
+    const double* bp;
+    if (step == 0 || step == 2) {
+      ints_from_words<L, TPI, Env>(xi, idx ? uq_w : up_w, u_words);
+      sub_exact<L, TPI, Env>(xi, one);                      // u - 1  (u >= 1)
+      limbs_of<L>(x, xi);
+      bp = cst + DT_ONE * KP;
+      Env::sync();
+    } else if (step == 1 || step == 3) {
+      bp = cst + (idx ? DT_HQM : DT_HPM) * KP;
+    } else if (step == 4) {
+      bp = cst + DT_PINVM * KP;
+    } else {
+      bp = cst + DT_PMN * KP;
+    }
+
+    if (step == 0 || step == 2) montmul<L, TPI, Env, true>(x, x, bp, mod_e, n0, qbuf);   // q = -(u-1) x^-1 mod R
+    else montmul<L, TPI, Env>(x, x, bp, mod_e, n0);
+
+    if (step == 0 || step == 2) {
+      // Lx = -q mod R = (~q) + 1 over K limbs
+      Env::sync();
 #pragma unroll
-    for (int j = 0; j < L; ++j) q[j] = 0;
-    uint32_t junk[L];
-    montmul<L, TPI, Env, true>(junk, x, cst + DT_ONE * KP, mod, n0, q);   // q = -(u-1) x^-1 mod R
-    // Lx = -q mod R = (~q) + 1 over K limbs
+      for (int j = 0; j < L; ++j) xi[j] = (~qbuf[lane * LP + j]) & M52;
+      if (lane == 0) xi[0] += 1ull;
+      normalize_exact<L, TPI, Env>(xi);
+      limbs_of<L>(x, xi);
+    } else if (step == 1) {
+      canonical_ints<L, TPI, Env>(mp, x, mod_e);            // m_p in [0, p)
+    } else if (step == 3) {
+      canonical_ints<L, TPI, Env>(xi, x, mod_e);            // m_q in [0, q)
+      const uint32_t neg = sub_exact<L, TPI, Env>(xi, mp);  // m_q - m_p
+      uint64_t addend[L], qi[L];
+      ints_from_entry<L, TPI, Env>(qi, mod_e);
 #pragma unroll
-    for (int j = 0; j < L; ++j) x[j] = (~q[j]) & LMASK;
-    if (lane == 0) x[0] += 1u;
-    normalize_exact<L, TPI, Env>(x);
-    montmul<L, TPI, Env>(x, x, cst + (idx ? DT_HQM : DT_HPM) * KP, mod, n0);
-    canonicalize<L, TPI, Env>(x, mod);                               // m_x in [0, x)
-    if (idx == 0) {
-#pragma unroll
-      for (int j = 0; j < L; ++j) mp[j] = x[j];
+      for (int j = 0; j < L; ++j) addend[j] = neg ? qi[j] : 0ull;
+      add_exact<L, TPI, Env>(xi, addend);                   // + q if negative: wraps back into range
+      limbs_of<L>(x, xi);
+    } else if (step == 4) {
+      canonical_ints<L, TPI, Env>(xi, x, mod_e);            // h in [0, q)
+      limbs_of<L>(x, xi);
+    } else if (step == 5) {
+      canonical_ints<L, TPI, Env>(xi, x, mod_e);            // h * p (< n)
+      add_exact<L, TPI, Env>(xi, mp);                       // m
     }
   }
-  // here: mod = q, x = m_q
-  const uint32_t neg = sub_exact<L, TPI, Env>(x, mp);                // m_q - m_p
-  {                                                                  // + q if negative (branch-free: shuffles inside)
-    uint32_t addend[L];
-#pragma unroll
-    for (int j = 0; j < L; ++j) addend[j] = neg ? mod[j] : 0u;
-    add_exact<L, TPI, Env>(x, addend);                               // wraps back into range
-  }
-  montmul<L, TPI, Env>(x, x, cst + DT_PINVM * KP, mod, n0invs[1]);
-  canonicalize<L, TPI, Env>(x, mod);                                 // h in [0, q)
-  load_entry<L, TPI, Env>(mod, cst + DT_N * KP);
-  montmul<L, TPI, Env>(x, x, cst + DT_PMN * KP, mod, n0invs[2]);
-  canonicalize<L, TPI, Env>(x, mod);                                 // h * p (< n)
-  add_exact<L, TPI, Env>(x, mp);                                     // m
-  store_words<L, TPI, Env>(m_w, m_words, x, sm.b0);
+  store_words<L, TPI, Env>(m_w, m_words, xi, sm.b0);
 }
 
 }  // namespace phe

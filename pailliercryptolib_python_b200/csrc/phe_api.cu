@@ -19,7 +19,7 @@
 using hbn::BN;
 
 namespace phe {
-extern const ShapeOps g_ops_37_1, g_ops_37_2, g_ops_37_4, g_ops_28_2, g_ops_28_4, g_ops_28_8;
+extern const ShapeOps g_ops_20_1, g_ops_20_2, g_ops_20_4, g_ops_20_8, g_ops_15_4, g_ops_15_8;
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launch_counter() { return g_launches.load(); }
@@ -82,7 +82,7 @@ static bool timing_read(int kind, double* ms, unsigned long long* n) {
   return true;
 }
 const ShapeOps* shape_ops(int L, int TPI) {
-  const ShapeOps* all[] = {&g_ops_37_1, &g_ops_37_2, &g_ops_37_4, &g_ops_28_2, &g_ops_28_4, &g_ops_28_8};
+  const ShapeOps* all[] = {&g_ops_20_1, &g_ops_20_2, &g_ops_20_4, &g_ops_20_8, &g_ops_15_4, &g_ops_15_8};
   for (auto* o : all) if (o->L == L && o->TPI == TPI) return o;
   return nullptr;
 }
@@ -99,7 +99,7 @@ int fail(const std::string& m) { t_err = m; return 1; }
 
 // smallest shape whose capacity covers mod_bits + 8 (R >= 2^8 N keeps every Montgomery product < 2N)
 const ShapeOps* shape_for_bits(int mod_bits) {
-  static const int order[][2] = {{37, 1}, {28, 2}, {37, 2}, {28, 4}, {37, 4}, {28, 8}};
+  static const int order[][2] = {{20, 1}, {20, 2}, {15, 4}, {20, 4}, {15, 8}, {20, 8}};   // 1040 .. 8320 bits
   for (auto& s : order) {
     const ShapeOps* o = shape_ops(s[0], s[1]);
     if (o && o->capacity_bits >= mod_bits + 8) return o;
@@ -107,33 +107,45 @@ const ShapeOps* shape_for_bits(int mod_bits) {
   return nullptr;
 }
 
-// value -> padded limb entry [TPI][LP]
-void to_entry(const BN& v, const ShapeOps* o, uint32_t* out) {
+// Entries are doubles on the device; host vectors and DevBuf count u32 words: EW(o) words per entry.
+inline size_t EW(const ShapeOps* o) { return 2 * (size_t)o->KP; }
+
+// value -> padded limb entry [TPI][LP]: every 52-bit limb as the double holding that integer
+void to_entry(const BN& v, const ShapeOps* o, uint32_t* out_words) {
   const int LP = o->KP / o->TPI;
-  std::memset(out, 0, (size_t)o->KP * 4);
+  std::vector<double> ent((size_t)o->KP, 0.0);
   if (v.bits() > (size_t)o->capacity_bits) throw std::runtime_error("to_entry: value exceeds shape capacity");
   for (int g = 0; g < o->L * o->TPI; ++g) {
     const size_t bit = (size_t)g * LW;
     const size_t wi = bit >> 5, sh = bit & 31;
-    uint64_t two = 0;
-    if (wi < v.w.size()) two = v.w[wi];
-    if (wi + 1 < v.w.size()) two |= (uint64_t)v.w[wi + 1] << 32;
-    out[(g / o->L) * LP + (g % o->L)] = (uint32_t)(two >> sh) & LMASK;
+    unsigned __int128 three = 0;
+    for (int k = 0; k < 3; ++k)
+      if (wi + k < v.w.size()) three |= (unsigned __int128)v.w[wi + k] << (32 * k);
+    ent[(g / o->L) * LP + (g % o->L)] = (double)((uint64_t)(three >> sh) & M52);
   }
+  std::memcpy(out_words, ent.data(), ent.size() * sizeof(double));
+}
+
+// -n^-1 mod 2^52 for odd n
+uint64_t neg_inv52(const BN& n) {
+  const uint64_t n0 = (uint64_t)n.w[0] | (n.w.size() > 1 ? (uint64_t)n.w[1] << 32 : 0ull);
+  uint64_t x = 1;
+  for (int i = 0; i < 6; ++i) x *= 2ull - n0 * x;
+  return (0ull - x) & M52;
 }
 
 // Montgomery block (ME_COUNT entries) for modulus N with context-specific extra value
-std::vector<uint32_t> mont_block(const BN& N, const BN& extra, const ShapeOps* o, uint32_t* n0inv) {
+std::vector<uint32_t> mont_block(const BN& N, const BN& extra, const ShapeOps* o, uint64_t* n0inv) {
   if (!N.is_odd()) throw std::runtime_error("modulus must be odd");
-  std::vector<uint32_t> blk((size_t)ME_COUNT * o->KP);
+  std::vector<uint32_t> blk((size_t)ME_COUNT * EW(o));
   const BN R = hbn::shl(BN(1), o->capacity_bits);
   const BN Rm = hbn::mod(R, N);
-  to_entry(N, o, &blk[(size_t)ME_N * o->KP]);
-  to_entry(hbn::mulmod(Rm, Rm, N), o, &blk[(size_t)ME_R2 * o->KP]);
-  to_entry(Rm, o, &blk[(size_t)ME_ONEM * o->KP]);
-  to_entry(BN(1), o, &blk[(size_t)ME_ONE * o->KP]);
-  to_entry(extra, o, &blk[(size_t)ME_X0 * o->KP]);
-  *n0inv = hbn::neg_inv28(N.low());
+  to_entry(N, o, &blk[(size_t)ME_N * EW(o)]);
+  to_entry(hbn::mulmod(Rm, Rm, N), o, &blk[(size_t)ME_R2 * EW(o)]);
+  to_entry(Rm, o, &blk[(size_t)ME_ONEM * EW(o)]);
+  to_entry(BN(1), o, &blk[(size_t)ME_ONE * EW(o)]);
+  to_entry(extra, o, &blk[(size_t)ME_X0 * EW(o)]);
+  *n0inv = neg_inv52(N);
   return blk;
 }
 
@@ -214,7 +226,7 @@ struct phe_privkey {
   mutable MontCtxArgs ctx[2]{};
   int ebits[2] = {0, 0};
   int hw = 0;  // words of x^2 (= n_words)
-  uint32_t n0invs[3] = {0, 0, 0};
+  uint64_t n0invs[3] = {0, 0, 0};
   mutable DevBuf ws_in, ws_out, ws_mont[2], ws_u[2], ws_tbl;
   mutable std::mutex mu;
   mutable bool dev_ready = false;
@@ -230,16 +242,16 @@ int pk_ensure_device(const phe_pubkey* pk) {
   if (phe_device_count() <= 0) return fail("no CUDA device (the compute path has no CPU fallback)");
   CUDA_TRY(cudaGetDevice(const_cast<int*>(&pk->device)));
   PHE_TRY(upload(pk->d_ctx, pk->h_ctx));
-  pk->ctx.entries = pk->d_ctx.p;
+  pk->ctx.entries = reinterpret_cast<const double*>(pk->d_ctx.p);
   if (pk->djn) {
     // fixed-base comb table T[j][d] = hs^(d 2^(8j)) R mod n^2
-    PHE_TRY(pk->d_comb.ensure((size_t)pk->nwin * 256 * pk->ops->KP));
+    PHE_TRY(pk->d_comb.ensure((size_t)pk->nwin * 256 * EW(pk->ops)));
     std::vector<uint32_t> hsw(2 * (size_t)pk->n_words);
     pk->hs.to_words(hsw.data(), hsw.size());
     DevBuf dhs;
     PHE_TRY(upload(dhs, hsw));
     CombArgs ca{};
-    ca.hs_w = dhs.p; ca.hs_words = 2 * pk->n_words; ca.nwin = pk->nwin; ca.comb = pk->d_comb.p; ca.ctx = pk->ctx;
+    ca.hs_w = dhs.p; ca.hs_words = 2 * pk->n_words; ca.nwin = pk->nwin; ca.comb = reinterpret_cast<double*>(pk->d_comb.p); ca.ctx = pk->ctx;
     cudaError_t e = pk->ops->comb_build(ca, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     dhs.release();
@@ -257,7 +269,7 @@ int sk_ensure_device(const phe_privkey* sk) {
   }
   for (int y = 0; y < 2; ++y) {
     PHE_TRY(upload(sk->d_ctx[y], sk->h_ctx[y]));
-    sk->ctx[y].entries = sk->d_ctx[y].p;
+    sk->ctx[y].entries = reinterpret_cast<const double*>(sk->d_ctx[y].p);
     PHE_TRY(upload(sk->d_exp[y], sk->h_exp[y]));
   }
   PHE_TRY(upload(sk->d_tail, sk->h_tail));
@@ -280,7 +292,7 @@ int launch_powm(const ShapeOps* o, const MontCtxArgs& ctx, const uint32_t* d_bas
   p.out_w[0] = d_out; p.out_w[1] = nullptr;
   p.out_words = out_words; p.count = count;
   p.ctx[0] = ctx; p.ctx[1] = ctx;
-  p.tbl = tbl.p;
+  p.tbl = reinterpret_cast<double*>(tbl.p);
   CUDA_TRY(o->powm(win, p, 1, s));
   return 0;
 }
@@ -300,7 +312,7 @@ int obfuscators_dev(const phe_pubkey* pk, const uint32_t* d_r, int r_words, size
       EncCombArgs a{};
       a.m_w = pk->ws_d.p; a.m_words = 0;   // zero words: m = 0 for every item
       a.r_w = d_r + off * r_words; a.r_words = r_words; a.nwin = pk->nwin;
-      a.out_w = d_obf + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = pk->d_comb.p;
+      a.out_w = d_obf + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
       CUDA_TRY(pk->ops->encrypt_comb(a, s));
     }
     return 0;
@@ -351,7 +363,7 @@ int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, co
       EncCombArgs a{};
       a.m_w = d_m + off * pk->n_words; a.m_words = pk->n_words;
       a.r_w = d_r ? d_r + off * r_words : nullptr; a.r_words = r_words; a.nwin = pk->nwin;
-      a.out_w = d_ct + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = pk->d_comb.p;
+      a.out_w = d_ct + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
       if (d_r && (size_t)r_words * 32 < (size_t)pk->nwin * 8) return fail("phe_encrypt: r_words too small for randbits");
       CUDA_TRY(pk->ops->encrypt_comb(a, s));
     }
@@ -404,7 +416,7 @@ int decrypt_dev_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, 
   const int hw = sk->hw, cw = 2 * hw;
   const size_t chunk = std::min(count, CHUNK);
   for (int y = 0; y < 2; ++y) {
-    PHE_TRY(sk->ws_mont[y].ensure(chunk * o->KP));
+    PHE_TRY(sk->ws_mont[y].ensure(chunk * EW(o)));
     PHE_TRY(sk->ws_u[y].ensure(chunk * hw));
   }
   PHE_TRY(sk->ws_tbl.ensure(o->powm_tbl_words(5, 2, (int)chunk)));
@@ -412,19 +424,19 @@ int decrypt_dev_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, 
     const int c = (int)std::min(CHUNK, count - off);
     DecPrepArgs dp{};
     dp.c_w = d_ct + off * cw; dp.hw = hw; dp.count = c;
-    for (int y = 0; y < 2; ++y) { dp.out[y] = sk->ws_mont[y].p; dp.ctx[y] = sk->ctx[y]; }
+    for (int y = 0; y < 2; ++y) { dp.out[y] = reinterpret_cast<double*>(sk->ws_mont[y].p); dp.ctx[y] = sk->ctx[y]; }
     CUDA_TRY(o->dec_prep(dp, s));
     PowmArgs p{};
     p.base_w = nullptr; p.base_words = 0; p.e_words = hw; p.e_stride = 0; p.out_words = hw; p.count = c;
     for (int y = 0; y < 2; ++y) {
-      p.base_mont[y] = sk->ws_mont[y].p; p.e_w[y] = sk->d_exp[y].p; p.ebits[y] = sk->ebits[y];
+      p.base_mont[y] = reinterpret_cast<const double*>(sk->ws_mont[y].p); p.e_w[y] = sk->d_exp[y].p; p.ebits[y] = sk->ebits[y];
       p.out_w[y] = sk->ws_u[y].p; p.ctx[y] = sk->ctx[y];
     }
-    p.tbl = sk->ws_tbl.p;
+    p.tbl = reinterpret_cast<double*>(sk->ws_tbl.p);
     CUDA_TRY(o->powm(5, p, 2, s));
     DecTailArgs t{};
     t.up_w = sk->ws_u[0].p; t.uq_w = sk->ws_u[1].p; t.u_words = hw; t.m_w = d_m + off * hw; t.m_words = hw;
-    t.count = c; t.cst = sk->d_tail.p;
+    t.count = c; t.cst = reinterpret_cast<const double*>(sk->d_tail.p);
     for (int i = 0; i < 3; ++i) t.n0invs[i] = sk->n0invs[i];
     CUDA_TRY(o->dec_tail(t, s));
   }
@@ -437,7 +449,7 @@ int decrypt_dev_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, 
 extern "C" {
 
 const char* phe_last_error(void) { return t_err.c_str(); }
-const char* phe_version(void) { return "phe_b200 0.1 (sm_100a, radix-2^28 IMAD.WIDE Montgomery)"; }
+const char* phe_version(void) { return "phe_b200 0.2 (sm_100a, radix-2^52 DFMA Montgomery)"; }
 
 int phe_device_count(void) {
   int n = 0;
@@ -470,7 +482,7 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
     std::unique_ptr<phe_pubkey> pk(new phe_pubkey);
     pk->bits = bits; pk->n_words = n_words; pk->djn = djn ? 1 : 0; pk->n = N; pk->nsq = hbn::mul(N, N);
     pk->ops = shape_for_bits(2 * n_words * 32);
-    if (!pk->ops) return fail("phe_pubkey_create: key too large (n^2 up to 6144 bits supported)");
+    if (!pk->ops) return fail("phe_pubkey_create: key too large (n^2 up to 8192 bits supported)");
     const BN R = hbn::shl(BN(1), pk->ops->capacity_bits);
     pk->h_ctx = mont_block(pk->nsq, hbn::mulmod(N, hbn::mod(R, pk->nsq), pk->nsq), pk->ops, &pk->ctx.n0inv);
     if (djn) {
@@ -538,8 +550,8 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
       hx[y] = hbn::modinv_prime(hbn::mod(Lx, X[y]), X[y]);
     }
     const BN pinv = hbn::modinv_prime(hbn::mod(P, Q), Q);
-    std::vector<uint32_t> tail((size_t)DT_COUNT * o->KP);
-    auto put = [&](int idx, const BN& v) { to_entry(v, o, &tail[(size_t)idx * o->KP]); };
+    std::vector<uint32_t> tail((size_t)DT_COUNT * EW(o));
+    auto put = [&](int idx, const BN& v) { to_entry(v, o, &tail[(size_t)idx * EW(o)]); };
     put(DT_P, P); put(DT_Q, Q); put(DT_N, pk->n);
     put(DT_HPM, hbn::mulmod(hx[0], hbn::mod(R, P), P));
     put(DT_HQM, hbn::mulmod(hx[1], hbn::mod(R, Q), Q));
@@ -547,9 +559,9 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
     put(DT_PMN, hbn::mulmod(P, hbn::mod(R, pk->n), pk->n));
     put(DT_ONE, BN(1));
     sk->h_tail = tail;
-    sk->n0invs[0] = hbn::neg_inv28(P.low());
-    sk->n0invs[1] = hbn::neg_inv28(Q.low());
-    sk->n0invs[2] = hbn::neg_inv28(pk->n.low());
+    sk->n0invs[0] = neg_inv52(P);
+    sk->n0invs[1] = neg_inv52(Q);
+    sk->n0invs[2] = neg_inv52(pk->n);
     *out = sk.release();
     return 0;
   } catch (const std::exception& e) { return fail(std::string("phe_privkey_create: ") + e.what()); }
@@ -786,7 +798,7 @@ int phe_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulu
     const BN N = BN::from_words(modulus, words);
     if (!N.is_odd()) return fail("phe_modexp: modulus must be odd");
     const ShapeOps* o = shape_for_bits((int)N.bits());
-    if (!o) return fail("phe_modexp: modulus too large (up to 6264 bits)");
+    if (!o) return fail("phe_modexp: modulus too large (up to 8312 bits)");
     MontCtxArgs ctx{};
     std::vector<uint32_t> blk = mont_block(N, BN(), o, &ctx.n0inv);
     // bases must be < modulus for the Montgomery bound; reduce on the host only if needed
@@ -801,7 +813,7 @@ int phe_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulu
     const uint32_t* bsrc = bred.empty() ? base : bred.data();
     DevBuf dctx, db, de, dout, tbl;
     int rc = upload(dctx, blk);
-    ctx.entries = dctx.p;
+    ctx.entries = reinterpret_cast<const double*>(dctx.p);
     if (!rc) rc = db.ensure(count * words);
     if (!rc) rc = de.ensure(count * words);
     if (!rc) rc = dout.ensure(count * words);
@@ -828,12 +840,12 @@ int phe_host_shape_for_bits(int mod_bits, int* L_out, int* TPI_out) {
   return 0;
 }
 
-int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, uint32_t* out, uint32_t* n0inv_out) {
+int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, double* out, uint64_t* n0inv_out) {
   try {
     const ShapeOps* o = shape_ops(L, TPI);
     if (!o) { fail("unknown shape"); return -1; }
     if (!out) return o->KP;
-    uint32_t n0 = 0;
+    uint64_t n0 = 0;
     std::vector<uint32_t> blk = mont_block(BN::from_words(mod, mod_words), BN(), o, &n0);
     std::memcpy(out, blk.data(), blk.size() * 4);
     if (n0inv_out) *n0inv_out = n0;

@@ -5,7 +5,12 @@
 // clone a WARPSYNC'd slow path).  Lanes whose item index is past the end recompute the last item and skip
 // the store.
 //
-// Shared memory: [CTA-shared constant entries][per group: b0, b1].
+// Shared memory (doubles): [CTA-shared constant entries][per group: b0, b1].  The modulus is read from its
+// shared-memory entry inside montmul, so no kernel keeps it in registers.
+// __launch_bounds__(NT, MinCtas<L>::V) for L = 20: 255 registers per thread, 2 CTAs (8 warps) per SM -- ptxas needs the
+// head-room to keep many independent product chains in flight.  For L = 15 ptxas always settles on a 168-register,
+// one-chain-at-a-time schedule, so those shapes run 3 CTAs (12 warps) per SM and hide the latency with warps
+// instead (tools/mont52_probe.cu: 8.8 vs 9.8 T MAC32-equivalents/s).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -14,17 +19,18 @@
 namespace phe {
 
 constexpr int NT = 128;  // threads per CTA
+template <int L> struct MinCtas { static constexpr int V = (L <= 15) ? 3 : 2; };
 
 template <int L, int TPI> struct KShape {
   static constexpr int KP = Shape<L, TPI>::KP;
   static constexpr int GPB = NT / TPI;  // groups per CTA
   static constexpr size_t smem_bytes(int n_shared_entries) {
-    return (size_t)(n_shared_entries + 2 * GPB) * KP * sizeof(uint32_t);
+    return (size_t)(n_shared_entries + 2 * GPB) * KP * sizeof(double);
   }
 };
 
 template <int L, int TPI>
-__device__ __forceinline__ GroupSmem group_smem(uint32_t* smem, int n_shared_entries) {
+__device__ __forceinline__ GroupSmem group_smem(double* smem, int n_shared_entries) {
   constexpr int KP = Shape<L, TPI>::KP;
   const int g = threadIdx.x / TPI;
   GroupSmem sm;
@@ -34,10 +40,10 @@ __device__ __forceinline__ GroupSmem group_smem(uint32_t* smem, int n_shared_ent
 }
 
 template <int KP>
-__device__ __forceinline__ void stage_entries(uint32_t* smem, const uint32_t* src, int n_entries) {
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(smem);
-  for (int i = threadIdx.x; i < n_entries * KP / 4; i += NT) d[i] = s[i];
+__device__ __forceinline__ void stage_entries(double* smem, const double* src, int n_entries) {
+  const double2* s = reinterpret_cast<const double2*>(src);
+  double2* d = reinterpret_cast<double2*>(smem);
+  for (int i = threadIdx.x; i < n_entries * KP / 2; i += NT) d[i] = s[i];
   __syncthreads();
 }
 
@@ -46,30 +52,28 @@ enum MontEntry { ME_N = 0, ME_R2 = 1, ME_ONEM = 2, ME_ONE = 3, ME_X0 = 4, ME_COU
 // ME_X0: context-specific extra (n*R mod n^2 for the n^2 context; 2^(32 hw) R^2 mod x^2 for x^2 contexts)
 
 struct MontCtxArgs {
-  const uint32_t* entries;  // ME_COUNT entries of KP words
-  uint32_t n0inv;
+  const double* entries;  // ME_COUNT entries of KP doubles
+  uint64_t n0inv;         // -n^-1 mod 2^52
 };
 
 // ---- HE add ------------------------------------------------------------------------------------
 // b_stride = 0 broadcasts a single b (ipcl CipherText::operator+ with other.size == 1)
 template <int L, int TPI>
-__global__ void __launch_bounds__(NT) k_modmul(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+__global__ void __launch_bounds__(NT, MinCtas<L>::V) k_modmul(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
                                                size_t b_stride, uint32_t* __restrict__ out, int nwords, int count,
                                                MontCtxArgs ctx) {
   using Env = DevEnv<TPI>;
   using KS = KShape<L, TPI>;
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(16) double smem[];
   stage_entries<KS::KP>(smem, ctx.entries, ME_COUNT);
   GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
-  uint32_t n[L];
-  load_entry<L, TPI, Env>(n, smem + ME_N * KS::KP);
   const int g = threadIdx.x / TPI;
   for (int base = blockIdx.x * KS::GPB; base < count; base += gridDim.x * KS::GPB) {
     const int want = base + g;
     const int item = want < count ? want : count - 1;
     uint32_t* dst = out + (size_t)item * nwords;
     item_modmul<L, TPI, Env>(a + (size_t)item * nwords, b + (size_t)item * b_stride, want < count ? dst : nullptr,
-                             nwords, n, ctx.n0inv, smem + ME_R2 * KS::KP, sm);
+                             nwords, smem + ME_N * KS::KP, ctx.n0inv, smem + ME_R2 * KS::KP, sm);
   }
 }
 
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(NT) k_modmul(const uint32_t* __restrict__ a, c
 struct PowmArgs {
   const uint32_t* base_w;      // [count][base_words] or null
   int base_words;
-  const uint32_t* base_mont[2];  // [count][KP] Montgomery-form entries or null
+  const double* base_mont[2];  // [count][KP] Montgomery-form entries or null
   const uint32_t* e_w[2];      // exponent words
   int e_words;
   size_t e_stride;             // 0: shared exponent
@@ -88,29 +92,27 @@ struct PowmArgs {
   int out_words;
   int count;
   MontCtxArgs ctx[2];
-  uint32_t* tbl;               // [gridDim.y * gridDim.x * GPB][1<<WIN][KP] scratch
+  double* tbl;                 // [gridDim.y * gridDim.x * GPB][1<<WIN][KP] scratch
 };
 
 template <int L, int TPI, int WIN>
-__global__ void __launch_bounds__(NT) k_powm(PowmArgs p) {
+__global__ void __launch_bounds__(NT, MinCtas<L>::V) k_powm(PowmArgs p) {
   using Env = DevEnv<TPI>;
   using KS = KShape<L, TPI>;
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(16) double smem[];
   const int y = blockIdx.y;
   stage_entries<KS::KP>(smem, p.ctx[y].entries, ME_COUNT);
   GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
-  uint32_t n[L];
-  load_entry<L, TPI, Env>(n, smem + ME_N * KS::KP);
   const int g = threadIdx.x / TPI;
-  uint32_t* tbl = p.tbl + ((size_t)(y * gridDim.x + blockIdx.x) * KS::GPB + g) * ((size_t)KS::KP << WIN);
+  double* tbl = p.tbl + ((size_t)(y * gridDim.x + blockIdx.x) * KS::GPB + g) * ((size_t)KS::KP << WIN);
   for (int base = blockIdx.x * KS::GPB; base < p.count; base += gridDim.x * KS::GPB) {
     const int want = base + g;
     const int item = want < p.count ? want : p.count - 1;
     item_powm<L, TPI, Env, WIN>(p.base_w ? p.base_w + (size_t)item * p.base_words : nullptr, p.base_words,
                                 p.base_mont[y] ? p.base_mont[y] + (size_t)item * KS::KP : nullptr,
                                 p.e_w[y] + (size_t)item * p.e_stride, p.e_words, p.ebits[y],
-                                want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
-                                p.ctx[y].n0inv, smem + ME_R2 * KS::KP, smem + ME_ONEM * KS::KP,
+                                want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words,
+                                smem + ME_N * KS::KP, p.ctx[y].n0inv, smem + ME_R2 * KS::KP, smem + ME_ONEM * KS::KP,
                                 smem + ME_ONE * KS::KP, tbl, sm);
   }
 }
@@ -119,27 +121,25 @@ __global__ void __launch_bounds__(NT) k_powm(PowmArgs p) {
 struct DecPrepArgs {
   const uint32_t* c_w;  // [count][2*hw]
   int hw;
-  uint32_t* out[2];     // [count][KP]
+  double* out[2];       // [count][KP]
   int count;
   MontCtxArgs ctx[2];
 };
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT) k_dec_prep(DecPrepArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_dec_prep(DecPrepArgs p) {
   using Env = DevEnv<TPI>;
   using KS = KShape<L, TPI>;
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(16) double smem[];
   const int y = blockIdx.y;
   stage_entries<KS::KP>(smem, p.ctx[y].entries, ME_COUNT);
   GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
-  uint32_t n[L];
-  load_entry<L, TPI, Env>(n, smem + ME_N * KS::KP);
   const int g = threadIdx.x / TPI;
   for (int base = blockIdx.x * KS::GPB; base < p.count; base += gridDim.x * KS::GPB) {
     const int want = base + g;
     const int item = want < p.count ? want : p.count - 1;
     // lanes past the end redo the last item and write identical data: benign
-    item_dec_prep<L, TPI, Env>(p.c_w + (size_t)item * 2 * p.hw, p.hw, p.out[y] + (size_t)item * KS::KP, n,
-                               p.ctx[y].n0inv, smem + ME_R2 * KS::KP, smem + ME_X0 * KS::KP, sm);
+    item_dec_prep<L, TPI, Env>(p.c_w + (size_t)item * 2 * p.hw, p.hw, p.out[y] + (size_t)item * KS::KP,
+                               smem + ME_N * KS::KP, p.ctx[y].n0inv, smem + ME_R2 * KS::KP, smem + ME_X0 * KS::KP, sm);
   }
 }
 
@@ -151,14 +151,14 @@ struct DecTailArgs {
   uint32_t* m_w;
   int m_words;
   int count;
-  const uint32_t* cst;     // DT_COUNT entries
-  uint32_t n0invs[3];
+  const double* cst;       // DT_COUNT entries
+  uint64_t n0invs[3];
 };
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT) k_dec_tail(DecTailArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_dec_tail(DecTailArgs p) {
   using Env = DevEnv<TPI>;
   using KS = KShape<L, TPI>;
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(16) double smem[];
   stage_entries<KS::KP>(smem, p.cst, DT_COUNT);
   GroupSmem sm = group_smem<L, TPI>(smem, DT_COUNT);
   const int g = threadIdx.x / TPI;
@@ -182,17 +182,15 @@ struct EncCombArgs {
   int out_words;
   int count;
   MontCtxArgs ctx;       // n^2 context; ME_X0 = n*R mod n^2
-  const uint32_t* comb;  // [nwin][256][KP]
+  const double* comb;    // [nwin][256][KP]
 };
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT) k_encrypt_comb(EncCombArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_encrypt_comb(EncCombArgs p) {
   using Env = DevEnv<TPI>;
   using KS = KShape<L, TPI>;
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(16) double smem[];
   stage_entries<KS::KP>(smem, p.ctx.entries, ME_COUNT);
   GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
-  uint32_t n[L];
-  load_entry<L, TPI, Env>(n, smem + ME_N * KS::KP);
   const int g = threadIdx.x / TPI;
   for (int base = blockIdx.x * KS::GPB; base < p.count; base += gridDim.x * KS::GPB) {
     const int want = base + g;
@@ -200,7 +198,7 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT) k_encrypt_comb(E
     item_encrypt_comb<L, TPI, Env, 8>(p.m_w + (size_t)item * p.m_words, p.m_words,
                                       p.r_w ? p.r_w + (size_t)item * p.r_words : nullptr, p.r_words, p.nwin,
                                       want < p.count ? p.out_w + (size_t)item * p.out_words : nullptr, p.out_words,
-                                      n, p.ctx.n0inv, smem + ME_X0 * KS::KP, p.comb, sm);
+                                      smem + ME_N * KS::KP, p.ctx.n0inv, smem + ME_X0 * KS::KP, p.comb, sm);
   }
 }
 
@@ -215,22 +213,20 @@ struct EncFinishArgs {
   MontCtxArgs ctx;
 };
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT) k_encrypt_finish(EncFinishArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_encrypt_finish(EncFinishArgs p) {
   using Env = DevEnv<TPI>;
   using KS = KShape<L, TPI>;
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(16) double smem[];
   stage_entries<KS::KP>(smem, p.ctx.entries, ME_COUNT);
   GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
-  uint32_t n[L];
-  load_entry<L, TPI, Env>(n, smem + ME_N * KS::KP);
   const int g = threadIdx.x / TPI;
   for (int base = blockIdx.x * KS::GPB; base < p.count; base += gridDim.x * KS::GPB) {
     const int want = base + g;
     const int item = want < p.count ? want : p.count - 1;
     item_encrypt_finish<L, TPI, Env>(p.m_w + (size_t)item * p.m_words, p.m_words,
                                      p.obf_w + (size_t)item * p.out_words,
-                                     want < p.count ? p.out_w + (size_t)item * p.out_words : nullptr, p.out_words, n,
-                                     p.ctx.n0inv, smem + ME_X0 * KS::KP, smem + ME_R2 * KS::KP, sm);
+                                     want < p.count ? p.out_w + (size_t)item * p.out_words : nullptr, p.out_words,
+                                     smem + ME_N * KS::KP, p.ctx.n0inv, smem + ME_X0 * KS::KP, smem + ME_R2 * KS::KP, sm);
   }
 }
 
@@ -241,54 +237,54 @@ struct CombArgs {
   const uint32_t* hs_w;   // hs canonical words
   int hs_words;
   int nwin;
-  uint32_t* comb;         // [nwin][256][KP]
+  double* comb;           // [nwin][256][KP]
   MontCtxArgs ctx;
 };
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT) k_comb_bases(CombArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_comb_bases(CombArgs p) {
   using Env = DevEnv<TPI>;
   using KS = KShape<L, TPI>;
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(16) double smem[];
   stage_entries<KS::KP>(smem, p.ctx.entries, ME_COUNT);
   GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
-  uint32_t n[L], x[L];
-  load_entry<L, TPI, Env>(n, smem + ME_N * KS::KP);
+  double x[L];
   // every group of the single CTA computes the same chain; only group 0 stores
   const bool writer = (threadIdx.x / TPI) == 0;
   limbs_from_words<L, TPI, Env>(x, p.hs_w, p.hs_words);
-  const uint32_t* bp = smem + ME_R2 * KS::KP;
+  const double* bp = smem + ME_R2 * KS::KP;
   const int total = 1 + (p.nwin - 1) * 8;
+#pragma unroll 1
   for (int s = 0; s < total; ++s) {
-    montmul<L, TPI, Env>(x, x, bp, n, p.ctx.n0inv);
-    if (s % 8 == 0 && writer) limbs_to_smem<L, TPI, Env>(p.comb + ((size_t)(s / 8) * 256 + 1) * KS::KP, x);
+    montmul<L, TPI, Env>(x, x, bp, smem + ME_N * KS::KP, p.ctx.n0inv);
+    if (s % 8 == 0 && writer) limbs_to_mem<L, TPI, Env>(p.comb + ((size_t)(s / 8) * 256 + 1) * KS::KP, x);
     Env::sync();
-    limbs_to_smem<L, TPI, Env>(sm.b0, x);
+    limbs_to_mem<L, TPI, Env>(sm.b0, x);
     Env::sync();
     bp = sm.b0;
   }
 }
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT) k_comb_fill(CombArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_comb_fill(CombArgs p) {
   using Env = DevEnv<TPI>;
   using KS = KShape<L, TPI>;
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(16) double smem[];
   stage_entries<KS::KP>(smem, p.ctx.entries, ME_COUNT);
   GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
-  uint32_t n[L], x[L];
-  load_entry<L, TPI, Env>(n, smem + ME_N * KS::KP);
+  double x[L];
   const int g = threadIdx.x / TPI;
   for (int base = blockIdx.x * KS::GPB; base < p.nwin; base += gridDim.x * KS::GPB) {
     const int want = base + g;
     const int j = want < p.nwin ? want : p.nwin - 1;
-    uint32_t* row = p.comb + (size_t)j * 256 * KS::KP;
+    double* row = p.comb + (size_t)j * 256 * KS::KP;
     Env::sync();
     copy_entry<L, TPI, Env>(sm.b0, row + KS::KP);          // T[j][1]
     copy_entry<L, TPI, Env>(row, smem + ME_ONEM * KS::KP);  // T[j][0]
     Env::sync();
     load_entry<L, TPI, Env>(x, sm.b0);
+#pragma unroll 1
     for (int d = 2; d < 256; ++d) {
-      montmul<L, TPI, Env>(x, x, sm.b0, n, p.ctx.n0inv);
-      limbs_to_smem<L, TPI, Env>(row + (size_t)d * KS::KP, x);
+      montmul<L, TPI, Env>(x, x, sm.b0, smem + ME_N * KS::KP, p.ctx.n0inv);
+      limbs_to_mem<L, TPI, Env>(row + (size_t)d * KS::KP, x);
     }
   }
 }

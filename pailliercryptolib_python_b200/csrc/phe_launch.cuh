@@ -59,9 +59,9 @@ template <int L, int TPI> struct Launch {
   template <int WIN> static size_t tbl_words_w(int ny, int count) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     const int grid = grid_for(k_powm<L, TPI, WIN>, smem, count, KS::GPB, ny);
-    return (size_t)grid * ny * KS::GPB * ((size_t)KS::KP << WIN);
+    return (size_t)grid * ny * KS::GPB * ((size_t)KS::KP << WIN) * 2;   // doubles -> u32 words
   }
-  static size_t powm_tbl_words(int win, int ny, int count) {
+  static size_t powm_tbl_words(int win, int ny, int count) {   // in u32 words (DevBuf unit)
     switch (win) {
       case 1: return tbl_words_w<1>(ny, count);
       case 3: return tbl_words_w<3>(ny, count);

@@ -17,13 +17,13 @@ struct EncFinishArgs;
 struct CombArgs;
 
 struct ShapeOps {
-  int L, TPI, KP, GPB;
-  int capacity_bits;  // 28 * L * TPI
+  int L, TPI, KP, GPB;   // KP: doubles per padded entry
+  int capacity_bits;     // 52 * L * TPI
   // every launcher returns the launch error (cudaGetLastError) and counts one kernel launch
   cudaError_t (*modmul)(const uint32_t* a, const uint32_t* b, size_t b_stride, uint32_t* out, int nwords, int count,
                         const MontCtxArgs& ctx, cudaStream_t s);
   cudaError_t (*powm)(int win, const PowmArgs& p, int ny, cudaStream_t s);
-  size_t (*powm_tbl_words)(int win, int ny, int count);   // scratch size for a powm launch
+  size_t (*powm_tbl_words)(int win, int ny, int count);   // scratch size (u32 words) for a powm launch
   cudaError_t (*dec_prep)(const DecPrepArgs& p, cudaStream_t s);
   cudaError_t (*dec_tail)(const DecTailArgs& p, cudaStream_t s);
   cudaError_t (*encrypt_comb)(const EncCombArgs& p, cudaStream_t s);

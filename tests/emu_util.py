@@ -6,7 +6,7 @@ import subprocess
 
 import numpy as np
 
-LW = 28
+LW = 52
 LMASK = (1 << LW) - 1
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -16,20 +16,20 @@ def shape_id(L, TPI):
 
 
 def lp(L):
-    return (L + 3) & ~3
+    return (L + 1) & ~1
 
 
 def to_entry(val, L, TPI):
-    """Python int -> padded limb entry [TPI][LP] (uint32)."""
-    out = np.zeros((TPI, lp(L)), dtype=np.uint32)
+    """Python int -> padded limb entry [TPI][LP]: float64 holding the exact integer value of each 52-bit limb."""
+    out = np.zeros((TPI, lp(L)), dtype=np.float64)
     for g in range(L * TPI):
-        out[g // L, g % L] = (val >> (LW * g)) & LMASK
+        out[g // L, g % L] = float((val >> (LW * g)) & LMASK)
     assert val >> (LW * L * TPI) == 0
     return out.reshape(-1)
 
 
 def from_entry(e, L, TPI):
-    e = np.asarray(e, dtype=np.uint32).reshape(TPI, lp(L))
+    e = np.asarray(e, dtype=np.float64).reshape(TPI, lp(L))
     v = 0
     for g in range(L * TPI):
         v += int(e[g // L, g % L]) << (LW * g)
@@ -70,9 +70,11 @@ def load_emu():
         return _emu
     src = os.path.join(HERE, "emu", "emu_driver.cpp")
     so = os.path.join(HERE, "emu", "libphe_emu.so")
-    deps = [src] + [os.path.join(HERE, "..", "pailliercryptolib_python_b200", "csrc", f) for f in ("mont28.cuh", "paillier_items.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "pailliercryptolib_python_b200", "csrc", f) for f in ("mont52.cuh", "paillier_items.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-o", so, src])
+        # -frounding-math: the emulator runs under FE_TOWARDZERO (fma.rz.f64); no constant folding across that
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-frounding-math", "-ffp-contract=off", "-pthread", "-shared",
+                               "-fPIC", "-o", so, src])
     _emu = ctypes.CDLL(so)
     return _emu
 
@@ -83,3 +85,16 @@ def P(a):
         return None
     assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+
+
+def PD(a):
+    """numpy float64 array (limb entries) -> ctypes pointer (None passes NULL)."""
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def P64(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))

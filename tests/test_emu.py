@@ -1,4 +1,4 @@
-"""CPU tests of the *device source* (csrc/mont28.cuh, csrc/paillier_items.cuh) compiled for the host and run
+"""CPU tests of the *device source* (csrc/mont52.cuh, csrc/paillier_items.cuh) compiled for the host and run
 under a lockstep lane emulator (tests/emu/emu_driver.cpp), checked bit-exactly against the Python-int oracle.
 These catch logic errors in the kernels before any GPU time is spent; the -m gpu tests repeat the checks on
 the real CUDA build through the C ABI."""
@@ -9,9 +9,9 @@ import numpy as np
 import pytest
 
 import paillier_oracle as O
-from emu_util import P, from_entry, from_words, load_emu, mont_consts, shape_id, to_entry, to_words
+from emu_util import P, P64, PD, from_entry, from_words, load_emu, mont_consts, shape_id, to_entry, to_words
 
-U32 = ctypes.c_uint32
+U64 = ctypes.c_uint64
 
 
 @pytest.fixture(scope="module")
@@ -19,7 +19,7 @@ def emu():
     return load_emu()
 
 
-SHAPES = [(37, 1, 1024), (37, 2, 2048), (37, 4, 4096), (19, 8, 4096), (28, 4, 3072), (28, 8, 6144)]
+SHAPES = [(20, 1, 1024), (20, 2, 2048), (20, 4, 4096), (15, 4, 3072), (15, 8, 6144), (20, 8, 8192), (7, 4, 1408)]
 
 
 @pytest.mark.parametrize("L,TPI,bits", SHAPES)
@@ -33,12 +33,12 @@ def test_modmul(emu, L, TPI, bits):
         b = [5, 1, N - 1, 1] + [rng.randrange(N) for _ in range(6)]
         aw, bw = to_words(a, nw), to_words(b, nw)
         out = np.zeros_like(aw)
-        assert emu.emu_modmul(shape_id(L, TPI), P(aw), P(bw), P(out), nw, len(a), P(mc["n"]), U32(mc["n0inv"]), P(mc["r2"])) == 0
+        assert emu.emu_modmul(shape_id(L, TPI), P(aw), P(bw), P(out), nw, len(a), PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"])) == 0
         assert from_words(out) == [x * y % N for x, y in zip(a, b)]
 
 
-@pytest.mark.parametrize("L,TPI,bits,win,ebits", [(37, 1, 1024, 5, 300), (37, 2, 2048, 5, 1024), (37, 4, 4096, 3, 53),
-                                                   (37, 4, 4096, 1, 7), (37, 2, 2048, 3, 1), (28, 4, 3072, 5, 100)])
+@pytest.mark.parametrize("L,TPI,bits,win,ebits", [(20, 1, 1024, 5, 300), (20, 2, 2048, 5, 1024), (20, 4, 4096, 3, 53),
+                                                   (20, 4, 4096, 1, 7), (20, 2, 2048, 3, 1), (15, 4, 3072, 5, 100)])
 def test_powm_per_item_exponent(emu, L, TPI, bits, win, ebits):
     rng = random.Random(bits * 7 + win)
     nw = bits // 32
@@ -51,22 +51,22 @@ def test_powm_per_item_exponent(emu, L, TPI, bits, win, ebits):
     bw, ewa = to_words(base, nw), to_words(exps, ew)
     out = np.zeros_like(bw)
     rc = emu.emu_powm(shape_id(L, TPI), win, P(bw), nw, None, P(ewa), ew, ew, ebits, P(out), nw, len(base),
-                      P(mc["n"]), U32(mc["n0inv"]), P(mc["r2"]), P(mc["oneM"]), P(mc["one"]))
+                      PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"]), PD(mc["oneM"]), PD(mc["one"]))
     assert rc == 0
     assert from_words(out) == [pow(b, e, N) for b, e in zip(base, exps)]
 
 
 def _dec_consts(sk, L, TPI):
     """Decrypt-tail constant block, computed with Python ints."""
-    R = 1 << (28 * L * TPI)
+    R = 1 << (52 * L * TPI)
     p, q, n = sk.p, sk.q, sk.pk.n
     ents = [p, q, n, sk.hp * R % p, sk.hq * R % q, sk.pinv * R % q, p * R % n, 1]
     cst = np.concatenate([to_entry(v, L, TPI) for v in ents])
-    n0 = np.array([(-pow(m, -1, 1 << 28)) % (1 << 28) for m in (p, q, n)], dtype=np.uint32)
+    n0 = np.array([(-pow(m, -1, 1 << 52)) % (1 << 52) for m in (p, q, n)], dtype=np.uint64)
     return cst, n0
 
 
-@pytest.mark.parametrize("bits,L,TPI", [(1024, 37, 1), (2048, 37, 2)])
+@pytest.mark.parametrize("bits,L,TPI", [(1024, 20, 1), (2048, 20, 2), (3072, 15, 4)])
 def test_decrypt_pipeline(emu, bits, L, TPI):
     """dec_prep -> powm(shared exponent x-1) -> dec_tail == oracle decrypt_crt."""
     if bits == 2048:
@@ -84,26 +84,26 @@ def test_decrypt_pipeline(emu, bits, L, TPI):
         mc = mont_consts(X2, L, TPI)
         k2 = to_entry((1 << (32 * hw)) * mc["R"] * mc["R"] % X2, L, TPI)
         KP = len(mc["n"])
-        ent = np.zeros((len(cs), KP), dtype=np.uint32)
-        assert emu.emu_dec_prep(shape_id(L, TPI), P(cw), hw, P(ent), len(cs), P(mc["n"]), U32(mc["n0inv"]), P(mc["r2"]), P(k2)) == 0
+        ent = np.zeros((len(cs), KP), dtype=np.float64)
+        assert emu.emu_dec_prep(shape_id(L, TPI), P(cw), hw, PD(ent), len(cs), PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"]), PD(k2)) == 0
         for i, c in enumerate(cs):
             assert from_entry(ent[i], L, TPI) % X2 == c * mc["R"] % X2
         e = to_words([x - 1], hw)
         out = np.zeros((len(cs), hw), dtype=np.uint32)
-        rc = emu.emu_powm(shape_id(L, TPI), 5, None, 0, P(ent), P(e), hw, 0, (x - 1).bit_length(), P(out), hw, len(cs),
-                          P(mc["n"]), U32(mc["n0inv"]), P(mc["r2"]), P(mc["oneM"]), P(mc["one"]))
+        rc = emu.emu_powm(shape_id(L, TPI), 5, None, 0, PD(ent), P(e), hw, 0, (x - 1).bit_length(), P(out), hw, len(cs),
+                          PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"]), PD(mc["oneM"]), PD(mc["one"]))
         assert rc == 0
         assert from_words(out) == [pow(c % X2, x - 1, X2) for c in cs]
         us.append(out)
     cst, n0 = _dec_consts(sk, L, TPI)
     mo = np.zeros((len(cs), hw), dtype=np.uint32)
-    assert emu.emu_dec_tail(shape_id(L, TPI), P(us[0]), P(us[1]), hw, P(mo), hw, len(cs), P(cst), P(n0)) == 0
+    assert emu.emu_dec_tail(shape_id(L, TPI), P(us[0]), P(us[1]), hw, P(mo), hw, len(cs), PD(cst), P64(n0)) == 0
     assert from_words(mo) == ms == O.decrypt_batch(sk, cs)
 
 
 def _comb_table(pk, L, TPI, WB=8):
     N = pk.nsquare
-    R = 1 << (28 * L * TPI)
+    R = 1 << (52 * L * TPI)
     nwin = (pk.randbits + WB - 1) // WB
     rows = []
     for j in range(nwin):
@@ -115,7 +115,7 @@ def _comb_table(pk, L, TPI, WB=8):
     return np.concatenate(rows), nwin
 
 
-@pytest.mark.parametrize("bits,L,TPI", [(1024, 37, 2)])
+@pytest.mark.parametrize("bits,L,TPI", [(1024, 20, 2)])
 def test_encrypt_comb(emu, bits, L, TPI):
     pk, sk = O.seeded_keypair(bits, 3)
     N = pk.nsquare
@@ -128,18 +128,18 @@ def test_encrypt_comb(emu, bits, L, TPI):
     mw, rw = to_words(ms, bits // 32), to_words(rs, pk.randbits // 32)
     out = np.zeros((len(ms), bits // 16), dtype=np.uint32)
     rc = emu.emu_encrypt_comb(shape_id(L, TPI), P(mw), bits // 32, P(rw), pk.randbits // 32, nwin, P(out), bits // 16,
-                              len(ms), P(mc["n"]), U32(mc["n0inv"]), P(nR), P(comb), ctypes.c_uint64(len(comb)))
+                              len(ms), PD(mc["n"]), U64(mc["n0inv"]), PD(nR), PD(comb), ctypes.c_uint64(len(comb)))
     assert rc == 0
     assert from_words(out) == O.encrypt_batch(pk, ms, rs)
     # make_secure = False
     rc = emu.emu_encrypt_comb(shape_id(L, TPI), P(mw), bits // 32, None, 0, nwin, P(out), bits // 16,
-                              len(ms), P(mc["n"]), U32(mc["n0inv"]), P(nR), P(comb), ctypes.c_uint64(len(comb)))
+                              len(ms), PD(mc["n"]), U64(mc["n0inv"]), PD(nR), PD(comb), ctypes.c_uint64(len(comb)))
     assert rc == 0
     assert from_words(out) == O.encrypt_batch(pk, ms, None)
 
 
 def test_encrypt_finish_classic(emu):
-    bits, L, TPI = 1024, 37, 2
+    bits, L, TPI = 1024, 20, 2
     pk, sk = O.seeded_keypair(bits, 3, djn=False)
     N = pk.nsquare
     mc = mont_consts(N, L, TPI)
@@ -150,7 +150,7 @@ def test_encrypt_finish_classic(emu):
     obf = [O.obfuscator(pk, r) for r in rs]
     mw, ow = to_words(ms, bits // 32), to_words(obf, bits // 16)
     out = np.zeros_like(ow)
-    rc = emu.emu_encrypt_finish(shape_id(L, TPI), P(mw), bits // 32, P(ow), P(out), bits // 16, len(ms), P(mc["n"]),
-                                U32(mc["n0inv"]), P(nR), P(mc["r2"]))
+    rc = emu.emu_encrypt_finish(shape_id(L, TPI), P(mw), bits // 32, P(ow), P(out), bits // 16, len(ms), PD(mc["n"]),
+                                U64(mc["n0inv"]), PD(nR), PD(mc["r2"]))
     assert rc == 0
     assert from_words(out) == O.encrypt_batch(pk, ms, rs)
