@@ -130,6 +130,11 @@ int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint
  * [TPI][LP] layout): N, R^2 mod N, R mod N, 1, extra (0 here), R = 2^(52 L TPI).  Returns KP (>0) or <0 on
  * error.  out may be NULL to query KP.  n0inv_out = -N^-1 mod 2^52. */
 int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, double* out, uint64_t* n0inv_out);
+/* Sliding-window program of a shared exponent as executed by k_powm_prog (decrypt: p-1, q-1; classic scheme: n):
+ * out[0] = table index of the leading window (0xffff: exponent is zero), out[k>=1] = (squarings << 8) | index into
+ * the table of odd powers x^(2 index + 1), index 0xff = no multiplication.  Returns the number of entries (or <0);
+ * out may be NULL to query. */
+int phe_host_powm_program(const uint32_t* e, int e_words, uint32_t* out, int out_cap);
 /* base^exp mod modulus on the host bignum (key-setup arithmetic), words words each. */
 int phe_host_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulus, int words, uint32_t* out);
 /* Shape selection: writes L, TPI for a modulus of `mod_bits` bits; returns 0 or error. */

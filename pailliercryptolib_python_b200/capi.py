@@ -21,7 +21,7 @@ SYMBOLS = [
     "phe_privkey_create", "phe_privkey_destroy", "phe_privkey_get_p", "phe_privkey_get_q", "phe_keygen",
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
-    "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits",
+    "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak",
 ]
 
@@ -261,6 +261,17 @@ def host_mont_block(modulus, mod_words, L, TPI):
     lib().phe_host_mont_block(_p(int_to_words(modulus, mod_words)), mod_words, L, TPI,
                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(n0))
     return out.reshape(5, kp), n0.value
+
+
+def host_powm_program(exponent, e_words):
+    """Sliding-window program the library builds for a shared exponent (list of ints)."""
+    e = int_to_words(exponent, e_words)
+    n = lib().phe_host_powm_program(_p(e), e_words, None, 0)
+    if n <= 0:
+        raise RuntimeError(lib().phe_last_error().decode())
+    out = np.zeros(n, dtype=np.uint32)
+    lib().phe_host_powm_program(_p(e), e_words, _p(out), n)
+    return [int(v) for v in out]
 
 
 def host_modexp(base, exp, modulus, words):

@@ -171,6 +171,99 @@ PHE_HD void item_powm(const uint32_t* base_w, int base_words, const double* base
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sliding-window exponentiation for an exponent SHARED by every item of the launch (decrypt: p-1 / q-1; classic
+// obfuscator: n): the host turns the exponent into a program (phe_api.cu: build_powm_program)
+//     prog[0]            table index of the leading window (PROG_ONE: exponent is zero)
+//     prog[1..nprog]     (squarings << 8) | table index, PROG_NOMUL as index = trailing squarings only
+// over the table of odd powers T[k] = x^(2k+1), k < TS = 2^(WS-1).  For a 1024-bit exponent and WS = 6 that is
+// 1 + 32 + 1023 + ~146 products instead of 30 + 1024 + 205 with fixed 5-bit windows.  One montmul call site.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t PROG_NOMUL = 0xffu;
+constexpr uint32_t PROG_ONE = 0xffffu;
+
+template <int L, int TPI, class Env, int WS>
+PHE_HD void item_powm_prog(const uint32_t* base_w, int base_words, const double* base_mont, const uint32_t* prog,
+                           int nprog, uint32_t* out_w, int out_words, const double* n_entry, uint64_t n0inv,
+                           const double* r2, const double* oneM, const double* one_plain, double* tbl, GroupSmem sm) {
+  constexpr int KP = Shape<L, TPI>::KP;
+  constexpr int TS = 1 << (WS - 1);
+  double x[L];
+  enum { P_TOMONT = 0, P_X2 = 1, P_TABLE = 2, P_SQR = 3, P_MUL = 4, P_FROMMONT = 5 };
+  int phase, ti = 1, sq = 0, pc = 1;
+  uint32_t op = 0;
+
+  if (base_mont) {
+    load_entry<L, TPI, Env>(x, base_mont);
+    phase = -1;
+  } else {
+    limbs_from_words<L, TPI, Env>(x, base_w, base_words);
+    phase = P_TOMONT;
+  }
+  const double* bp = r2;
+#pragma unroll 1
+  for (;;) {
+    if (phase == -1) {            // x holds xM: T[0] = xM, then x^2
+      Env::sync();
+      limbs_to_mem<L, TPI, Env>(tbl, x);
+      limbs_to_mem<L, TPI, Env>(sm.b0, x);
+      Env::sync();
+      if (TS > 1 && prog[0] != PROG_ONE) { phase = P_X2; bp = sm.b0; }
+      else phase = -2;
+    }
+    if (phase == -2) {            // table complete: load the leading window
+      const uint32_t i0 = prog[0];
+      load_entry<L, TPI, Env>(x, i0 == PROG_ONE ? oneM : tbl + (size_t)i0 * KP);
+      pc = 1;
+      phase = -3;
+    }
+    if (phase == -3) {            // fetch the next program entry
+      if (pc > nprog) { phase = P_FROMMONT; bp = one_plain; }
+      else {
+        op = prog[pc++];
+        sq = (int)(op >> 8);
+        phase = sq > 0 ? P_SQR : P_MUL;
+      }
+    }
+    if (phase == P_SQR) {
+      Env::sync();
+      limbs_to_mem<L, TPI, Env>(sm.b1, x);
+      Env::sync();
+      bp = sm.b1;
+    } else if (phase == P_MUL) {
+      Env::sync();
+      copy_entry<L, TPI, Env>(sm.b1, tbl + (size_t)(op & 0xffu) * KP);
+      Env::sync();
+      bp = sm.b1;
+    }
+
+    montmul<L, TPI, Env>(x, x, bp, n_entry, n0inv);
+
+    if (phase == P_TOMONT) {
+      phase = -1;
+    } else if (phase == P_X2) {   // x = xM^2: the table multiplier; restart the chain from T[0]
+      Env::sync();
+      limbs_to_mem<L, TPI, Env>(sm.b0, x);
+      Env::sync();
+      load_entry<L, TPI, Env>(x, tbl);
+      bp = sm.b0;
+      phase = P_TABLE;
+    } else if (phase == P_TABLE) {
+      limbs_to_mem<L, TPI, Env>(tbl + (size_t)ti * KP, x);
+      if (++ti == TS) phase = -2;
+    } else if (phase == P_SQR) {
+      if (--sq == 0) phase = ((op & 0xffu) == PROG_NOMUL) ? -3 : P_MUL;
+    } else if (phase == P_MUL) {
+      phase = -3;
+    } else {  // P_FROMMONT
+      break;
+    }
+  }
+  uint64_t xi[L];
+  canonical_ints<L, TPI, Env>(xi, x, n_entry);
+  store_words<L, TPI, Env>(out_w, out_words, xi, sm.b1);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Decrypt pre-reduction: xM = c * R mod x^2 from the double-width ciphertext c = c_lo + 2^(32*hw) c_hi:
 //   xM = montmul(c_lo, R^2) + montmul(c_hi, 2^(32 hw) R^2)   (both constants mod x^2).
 // Output: Montgomery-form entry (padded exact limbs, value < 4 x^2) in global memory.

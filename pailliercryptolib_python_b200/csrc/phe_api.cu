@@ -201,6 +201,33 @@ int max_bits_host(const uint32_t* e, int e_words, size_t n) {
   return best;
 }
 
+// Sliding-window program of a shared exponent (paillier_items.cuh: item_powm_prog), window width PROG_WS.
+std::vector<uint32_t> build_powm_program(const BN& e) {
+  std::vector<uint32_t> prog;
+  if (e.is_zero()) { prog.push_back(PROG_ONE); return prog; }
+  long i = (long)e.bits() - 1;
+  bool first = true;
+  uint32_t pending_sq = 0;
+  while (i >= 0) {
+    if (!e.bit((size_t)i)) { ++pending_sq; --i; continue; }
+    long j = std::max<long>(i - PROG_WS + 1, 0);
+    while (!e.bit((size_t)j)) ++j;
+    uint32_t digit = 0;
+    for (long k = i; k >= j; --k) digit = (digit << 1) | (e.bit((size_t)k) ? 1u : 0u);
+    const uint32_t idx = (digit - 1) >> 1;
+    if (first) { prog.push_back(idx); first = false; }
+    else {
+      uint32_t sq = pending_sq + (uint32_t)(i - j + 1);
+      while (sq > 0xffffffu) { prog.push_back((0xffffffu << 8) | PROG_NOMUL); sq -= 0xffffffu; }
+      prog.push_back((sq << 8) | idx);
+    }
+    pending_sq = 0;
+    i = j - 1;
+  }
+  if (pending_sq) prog.push_back((pending_sq << 8) | PROG_NOMUL);
+  return prog;
+}
+
 int window_for_bits(int ebits) { return ebits <= 8 ? 1 : (ebits <= 160 ? 3 : 5); }
 
 }  // namespace
@@ -214,6 +241,8 @@ struct phe_pubkey {
   std::vector<uint32_t> h_ctx;    // Montgomery block, uploaded lazily
   int nwin = 0;
   mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_tbl;  // op workspaces
+  mutable DevBuf d_prog_n;                         // classic scheme: sliding-window program of the exponent n
+  std::vector<uint32_t> h_prog_n;
   mutable std::mutex mu;
   mutable bool dev_ready = false;  // device state (Montgomery block, comb table) is built on first compute call
 };
@@ -222,7 +251,7 @@ struct phe_privkey {
   const phe_pubkey* pk = nullptr;
   BN p, q;
   const ShapeOps* ops = nullptr;  // shape of the x^2 contexts (also used for p, q, n in the tail)
-  mutable DevBuf d_ctx[2], d_exp[2], d_tail;
+  mutable DevBuf d_ctx[2], d_exp[2], d_prog[2], d_tail;
   mutable MontCtxArgs ctx[2]{};
   int ebits[2] = {0, 0};
   int hw = 0;  // words of x^2 (= n_words)
@@ -230,7 +259,7 @@ struct phe_privkey {
   mutable DevBuf ws_in, ws_out, ws_mont[2], ws_u[2], ws_tbl;
   mutable std::mutex mu;
   mutable bool dev_ready = false;
-  std::vector<uint32_t> h_ctx[2], h_exp[2], h_tail;   // host copies uploaded on first compute call
+  std::vector<uint32_t> h_ctx[2], h_exp[2], h_prog[2], h_tail;   // host copies uploaded on first compute call
 };
 
 namespace {
@@ -271,6 +300,7 @@ int sk_ensure_device(const phe_privkey* sk) {
     PHE_TRY(upload(sk->d_ctx[y], sk->h_ctx[y]));
     sk->ctx[y].entries = reinterpret_cast<const double*>(sk->d_ctx[y].p);
     PHE_TRY(upload(sk->d_exp[y], sk->h_exp[y]));
+    PHE_TRY(upload(sk->d_prog[y], sk->h_prog[y]));
   }
   PHE_TRY(upload(sk->d_tail, sk->h_tail));
   sk->dev_ready = true;
@@ -317,16 +347,18 @@ int obfuscators_dev(const phe_pubkey* pk, const uint32_t* d_r, int r_words, size
     }
     return 0;
   }
-  // classic: r^n mod n^2, shared exponent n
-  PHE_TRY(pk->ws_d.ensure((size_t)pk->n_words));
-  std::vector<uint32_t> nw(pk->n_words);
-  pk->n.to_words(nw.data(), nw.size());
-  CUDA_TRY(cudaMemcpyAsync(pk->ws_d.p, nw.data(), nw.size() * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaStreamSynchronize(s));  // nw is a stack-lifetime staging buffer
+  // classic: r^n mod n^2, shared exponent n -> sliding-window program
+  if (!pk->d_prog_n.p) PHE_TRY(upload(pk->d_prog_n, pk->h_prog_n));
   for (size_t off = 0; off < count; off += CHUNK) {
     const int c = (int)std::min(CHUNK, count - off);
-    PHE_TRY(launch_powm(pk->ops, pk->ctx, d_r + off * r_words, r_words, pk->ws_d.p, pk->n_words, 0,
-                        (int)pk->n.bits(), d_obf + off * cw, cw, c, pk->ws_tbl, s));
+    PHE_TRY(pk->ws_tbl.ensure(pk->ops->powm_prog_tbl_words(1, c)));
+    PowmArgs p{};
+    p.base_w = d_r + off * r_words; p.base_words = r_words;
+    p.out_w[0] = d_obf + off * cw; p.out_words = cw; p.count = c;
+    p.ctx[0] = pk->ctx; p.ctx[1] = pk->ctx;
+    p.tbl = reinterpret_cast<double*>(pk->ws_tbl.p);
+    p.prog[0] = pk->d_prog_n.p; p.nprog[0] = (int)pk->h_prog_n.size() - 1;
+    CUDA_TRY(pk->ops->powm_prog(p, 1, s));
   }
   return 0;
 }
@@ -419,7 +451,7 @@ int decrypt_dev_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, 
     PHE_TRY(sk->ws_mont[y].ensure(chunk * EW(o)));
     PHE_TRY(sk->ws_u[y].ensure(chunk * hw));
   }
-  PHE_TRY(sk->ws_tbl.ensure(o->powm_tbl_words(5, 2, (int)chunk)));
+  PHE_TRY(sk->ws_tbl.ensure(o->powm_prog_tbl_words(2, (int)chunk)));
   for (size_t off = 0; off < count; off += CHUNK) {
     const int c = (int)std::min(CHUNK, count - off);
     DecPrepArgs dp{};
@@ -431,9 +463,10 @@ int decrypt_dev_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, 
     for (int y = 0; y < 2; ++y) {
       p.base_mont[y] = reinterpret_cast<const double*>(sk->ws_mont[y].p); p.e_w[y] = sk->d_exp[y].p; p.ebits[y] = sk->ebits[y];
       p.out_w[y] = sk->ws_u[y].p; p.ctx[y] = sk->ctx[y];
+      p.prog[y] = sk->d_prog[y].p; p.nprog[y] = (int)sk->h_prog[y].size() - 1;
     }
     p.tbl = reinterpret_cast<double*>(sk->ws_tbl.p);
-    CUDA_TRY(o->powm(5, p, 2, s));
+    CUDA_TRY(o->powm_prog(p, 2, s));
     DecTailArgs t{};
     t.up_w = sk->ws_u[0].p; t.uq_w = sk->ws_u[1].p; t.u_words = hw; t.m_w = d_m + off * hw; t.m_words = hw;
     t.count = c; t.cst = reinterpret_cast<const double*>(sk->d_tail.p);
@@ -499,6 +532,8 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
         pk->hs = hbn::modexp(h, N, pk->nsq);
       }
       pk->nwin = (pk->randbits + 7) / 8;
+    } else {
+      pk->h_prog_n = build_powm_program(N);
     }
     *out = pk.release();
     return 0;
@@ -507,7 +542,7 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
 
 void phe_pubkey_destroy(phe_pubkey* pk) {
   if (!pk) return;
-  for (DevBuf* b : {&pk->d_ctx, &pk->d_comb, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
+  for (DevBuf* b : {&pk->d_ctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
   delete pk;
 }
 int phe_pubkey_bits(const phe_pubkey* pk) { return pk ? pk->bits : -1; }
@@ -544,6 +579,7 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
       sk->h_exp[y].assign(sk->hw, 0);
       e.to_words(sk->h_exp[y].data(), sk->h_exp[y].size());
       sk->ebits[y] = (int)e.bits();
+      sk->h_prog[y] = build_powm_program(e);
       // hx = (L_x(g^(x-1) mod x^2))^-1 mod x
       const BN u = hbn::modexp(hbn::mod(g, X2), e, X2);
       const BN Lx = hbn::div(hbn::sub(u, BN(1)), X[y]);
@@ -569,7 +605,7 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
 
 void phe_privkey_destroy(phe_privkey* sk) {
   if (!sk) return;
-  for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_tail, &sk->ws_in, &sk->ws_out,
+  for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->ws_in, &sk->ws_out,
                     &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl}) b->release();
   delete sk;
 }
@@ -851,6 +887,17 @@ int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, doub
     if (n0inv_out) *n0inv_out = n0;
     return o->KP;
   } catch (const std::exception& e) { fail(e.what()); return -1; }
+}
+
+int phe_host_powm_program(const uint32_t* e, int e_words, uint32_t* out, int out_cap) {
+  try {
+    const std::vector<uint32_t> prog = build_powm_program(BN::from_words(e, e_words));
+    if (out) {
+      if ((int)prog.size() > out_cap) { fail("phe_host_powm_program: buffer too small"); return -1; }
+      std::memcpy(out, prog.data(), prog.size() * 4);
+    }
+    return (int)prog.size();
+  } catch (const std::exception& ex) { fail(ex.what()); return -1; }
 }
 
 int phe_host_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulus, int words, uint32_t* out) {

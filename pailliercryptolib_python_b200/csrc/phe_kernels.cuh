@@ -7,10 +7,12 @@
 //
 // Shared memory (doubles): [CTA-shared constant entries][per group: b0, b1].  The modulus is read from its
 // shared-memory entry inside montmul, so no kernel keeps it in registers.
-// __launch_bounds__(NT, MinCtas<L>::V) for L = 20: 255 registers per thread, 2 CTAs (8 warps) per SM -- ptxas needs the
-// head-room to keep many independent product chains in flight.  For L = 15 ptxas always settles on a 168-register,
-// one-chain-at-a-time schedule, so those shapes run 3 CTAs (12 warps) per SM and hide the latency with warps
-// instead (tools/mont52_probe.cu: 8.8 vs 9.8 T MAC32-equivalents/s).
+// __launch_bounds__(NT, 3): a 168-register cap, 3 CTAs (12 warps) per SM.  Left to itself (cap 255) ptxas flips,
+// kernel by kernel, between a schedule that interleaves ~20 product chains (250 registers, ~7 stall cycles per
+// DFMA in the SASS control words) and one that runs a single chain at a time (180-200 registers, ~17 stall cycles
+// per DFMA: k_powm_prog<20,2> came out 47 % slower than k_powm<20,2,5> on the same arithmetic).  Under the explicit
+// cap every kernel gets the interleaved schedule in 160-168 registers without spills, and the third CTA adds the
+// warps that hide what latency is left (tools/mont52_probe.cu: 1.17 G vs 1.18 G 2048-bit products/s).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -19,7 +21,7 @@
 namespace phe {
 
 constexpr int NT = 128;  // threads per CTA
-template <int L> struct MinCtas { static constexpr int V = (L <= 15) ? 3 : 2; };
+template <int L> struct MinCtas { static constexpr int V = 3; };
 
 template <int L, int TPI> struct KShape {
   static constexpr int KP = Shape<L, TPI>::KP;
@@ -93,6 +95,8 @@ struct PowmArgs {
   int count;
   MontCtxArgs ctx[2];
   double* tbl;                 // [gridDim.y * gridDim.x * GPB][1<<WIN][KP] scratch
+  const uint32_t* prog[2];     // k_powm_prog only: sliding-window program of the shared exponent (paillier_items.cuh)
+  int nprog[2];
 };
 
 template <int L, int TPI, int WIN>
@@ -114,6 +118,30 @@ __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_powm(PowmArgs p) {
                                 want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words,
                                 smem + ME_N * KS::KP, p.ctx[y].n0inv, smem + ME_R2 * KS::KP, smem + ME_ONEM * KS::KP,
                                 smem + ME_ONE * KS::KP, tbl, sm);
+  }
+}
+
+// ---- shared-exponent sliding-window modexp (decrypt, classic obfuscator) ---------------------------------
+constexpr int PROG_WS = 6;   // window width of the programs built by the host: 32 odd powers per table
+template <int L, int TPI>
+__global__ void __launch_bounds__(NT, MinCtas<L>::V) k_powm_prog(PowmArgs p) {
+  using Env = DevEnv<TPI>;
+  using KS = KShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  const int y = blockIdx.y;
+  stage_entries<KS::KP>(smem, p.ctx[y].entries, ME_COUNT);
+  GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
+  const int g = threadIdx.x / TPI;
+  double* tbl = p.tbl + ((size_t)(y * gridDim.x + blockIdx.x) * KS::GPB + g) * ((size_t)KS::KP << (PROG_WS - 1));
+  for (int base = blockIdx.x * KS::GPB; base < p.count; base += gridDim.x * KS::GPB) {
+    const int want = base + g;
+    const int item = want < p.count ? want : p.count - 1;
+    item_powm_prog<L, TPI, Env, PROG_WS>(p.base_w ? p.base_w + (size_t)item * p.base_words : nullptr, p.base_words,
+                                         p.base_mont[y] ? p.base_mont[y] + (size_t)item * KS::KP : nullptr,
+                                         p.prog[y], p.nprog[y],
+                                         want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr,
+                                         p.out_words, smem + ME_N * KS::KP, p.ctx[y].n0inv, smem + ME_R2 * KS::KP,
+                                         smem + ME_ONEM * KS::KP, smem + ME_ONE * KS::KP, tbl, sm);
   }
 }
 

@@ -56,6 +56,20 @@ template <int L, int TPI> struct Launch {
       default: return cudaErrorInvalidValue;
     }
   }
+  // shared-exponent program path; scratch: same 32 entries per group as the 5-bit fixed window
+  static cudaError_t powm_prog(const PowmArgs& p, int ny, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int grid = grid_for(k_powm_prog<L, TPI>, smem, p.count, KS::GPB, ny);
+    { TimedLaunch tl_(KK_POWM, s);
+    k_powm_prog<L, TPI><<<dim3(grid, ny), NT, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+  }
+  static size_t powm_prog_tbl_words(int ny, int count) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int grid = grid_for(k_powm_prog<L, TPI>, smem, count, KS::GPB, ny);
+    return (size_t)grid * ny * KS::GPB * ((size_t)KS::KP << (PROG_WS - 1)) * 2;
+  }
   template <int WIN> static size_t tbl_words_w(int ny, int count) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     const int grid = grid_for(k_powm<L, TPI, WIN>, smem, count, KS::GPB, ny);
@@ -118,7 +132,7 @@ template <int L, int TPI> struct Launch {
   }
 
   static constexpr ShapeOps ops() {
-    return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &dec_prep, &dec_tail,
+    return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &powm_prog, &powm_prog_tbl_words, &dec_prep, &dec_tail,
                     &encrypt_comb, &encrypt_finish, &comb_build};
   }
 };

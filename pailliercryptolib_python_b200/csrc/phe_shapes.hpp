@@ -24,6 +24,8 @@ struct ShapeOps {
                         const MontCtxArgs& ctx, cudaStream_t s);
   cudaError_t (*powm)(int win, const PowmArgs& p, int ny, cudaStream_t s);
   size_t (*powm_tbl_words)(int win, int ny, int count);   // scratch size (u32 words) for a powm launch
+  cudaError_t (*powm_prog)(const PowmArgs& p, int ny, cudaStream_t s);   // shared-exponent sliding-window program
+  size_t (*powm_prog_tbl_words)(int ny, int count);
   cudaError_t (*dec_prep)(const DecPrepArgs& p, cudaStream_t s);
   cudaError_t (*dec_tail)(const DecTailArgs& p, cudaStream_t s);
   cudaError_t (*encrypt_comb)(const EncCombArgs& p, cudaStream_t s);

@@ -2,7 +2,7 @@
 // Each lane of a group is a std::thread; shuffles are barrier-synchronised exchanges.
 // Built by tests/emu_util.py: g++ -O2 -std=c++20 -frounding-math -pthread -shared -fPIC.  Every lane thread runs with
 // the rounding mode FE_TOWARDZERO so that std::fma reproduces the device's fma.rz.f64 bit for bit.
-#include <barrier>
+#include <atomic>
 #include <cfenv>
 #include <cstdint>
 #include <cstring>
@@ -14,9 +14,29 @@
 
 namespace {
 
+// Sense-reversing spin barrier: the lanes of a group exchange values thousands of times per Montgomery product and a
+// futex-based std::barrier costs microseconds per phase.
+struct SpinBarrier {
+  const int n;
+  std::atomic<int> waiting{0};
+  std::atomic<int> phase{0};
+  explicit SpinBarrier(int n_) : n(n_) {}
+  void arrive_and_wait() {
+    const int ph = phase.load(std::memory_order_acquire);
+    if (waiting.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+      waiting.store(0, std::memory_order_relaxed);
+      phase.store(ph + 1, std::memory_order_release);
+    } else {
+      int spins = 0;
+      while (phase.load(std::memory_order_acquire) == ph)
+        if (++spins > 2000) { std::this_thread::yield(); spins = 0; }
+    }
+  }
+};
+
 struct Exchange {
   uint32_t slot[32];
-  std::barrier<> bar;
+  SpinBarrier bar;
   explicit Exchange(int n) : bar(n) {}
 };
 
@@ -103,6 +123,31 @@ int do_powm(const uint32_t* base, int base_words, const double* base_mont, const
       phe::item_powm<L, TPI, Env, WIN>(base ? base + (size_t)i * base_words : nullptr, base_words, bmp,
                                        e + (size_t)i * e_stride, e_words, ebits, out + (size_t)i * out_words,
                                        out_words, ne.p, n0inv, r2.p, oneM.p, one.p, tp, bufs.sm);
+    });
+    delete bmc;
+  }
+  return 0;
+}
+
+template <int L, int TPI>
+int do_powm_prog(const uint32_t* base, int base_words, const double* base_mont, const uint32_t* prog, int nprog,
+                 uint32_t* out, int out_words, int count, const double* n_e, uint64_t n0inv, const double* r2_e,
+                 const double* oneM_e, const double* one_e) {
+  using Env = EmuEnv<TPI>;
+  constexpr int KP = phe::Shape<L, TPI>::KP;
+  constexpr int WS = 6;
+  AlignedCopy ne(n_e, KP), r2(r2_e, KP), oneM(oneM_e, KP), one(one_e, KP);
+  for (int i = 0; i < count; ++i) {
+    Bufs<L, TPI> bufs;
+    std::vector<double> tbl((size_t)(1 << (WS - 1)) * KP + 2);
+    double* tp = (double*)(((uintptr_t)tbl.data() + 15) & ~(uintptr_t)15);
+    const double* bmp = nullptr;
+    AlignedCopy* bmc = nullptr;
+    if (base_mont) { bmc = new AlignedCopy(base_mont + (size_t)i * KP, KP); bmp = bmc->p; }
+    run_group<TPI>([&] {
+      phe::item_powm_prog<L, TPI, Env, WS>(base ? base + (size_t)i * base_words : nullptr, base_words, bmp, prog, nprog,
+                                           out + (size_t)i * out_words, out_words, ne.p, n0inv, r2.p, oneM.p, one.p,
+                                           tp, bufs.sm);
     });
     delete bmc;
   }
@@ -204,6 +249,12 @@ int emu_powm(int shape, int win, const uint32_t* base, int base_words, const dou
   if (win == 3) { DISPATCH_SHAPE((POWM_CALL(3))); }
   if (win == 1) { DISPATCH_SHAPE((POWM_CALL(1))); }
   return -2;
+}
+
+int emu_powm_prog(int shape, const uint32_t* base, int base_words, const double* base_mont, const uint32_t* prog,
+                  int nprog, uint32_t* out, int out_words, int count, const double* n_e, uint64_t n0inv,
+                  const double* r2_e, const double* oneM_e, const double* one_e) {
+  DISPATCH_SHAPE((do_powm_prog<L, TPI>(base, base_words, base_mont, prog, nprog, out, out_words, count, n_e, n0inv, r2_e, oneM_e, one_e)));
 }
 
 int emu_dec_prep(int shape, const uint32_t* c, int hw, double* out_entries, int count, const double* n_e,

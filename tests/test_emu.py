@@ -56,6 +56,39 @@ def test_powm_per_item_exponent(emu, L, TPI, bits, win, ebits):
     assert from_words(out) == [pow(b, e, N) for b, e in zip(base, exps)]
 
 
+def run_program(prog, x, N):
+    """Reference interpreter of a sliding-window program (include/phe_b200.h: phe_host_powm_program)."""
+    if prog[0] == 0xFFFF:
+        return 1 % N
+    acc = pow(x, 2 * prog[0] + 1, N)
+    for op in prog[1:]:
+        acc = pow(acc, 1 << (op >> 8), N)
+        if op & 0xFF != 0xFF:
+            acc = acc * pow(x, 2 * (op & 0xFF) + 1, N) % N
+    return acc
+
+
+@pytest.mark.parametrize("L,TPI,bits,ebits", [(20, 1, 1024, 512), (20, 2, 2048, 1024), (15, 4, 3072, 200), (20, 1, 512, 9)])
+def test_powm_shared_exponent_program(emu, L, TPI, bits, ebits):
+    from pailliercryptolib_python_b200 import capi
+    rng = random.Random(bits + ebits)
+    nw = bits // 32
+    N = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+    mc = mont_consts(N, L, TPI)
+    base = [rng.randrange(N) for _ in range(3)] + [0, 1, N - 1]
+    bw = to_words(base, nw)
+    for e in (rng.getrandbits(ebits) | (1 << (ebits - 1)), (1 << ebits) - 1, 1 << (ebits - 1), 1, 0, 0b1000001000000):
+        prog = capi.host_powm_program(e, (ebits + 31) // 32 + 1)
+        assert [run_program(prog, b, N) for b in base] == [pow(b, e, N) for b in base]
+        assert sum(op >> 8 for op in prog[1:]) <= max(e.bit_length() - 1, 0)
+        pa = np.array(prog, dtype=np.uint32)
+        out = np.zeros_like(bw)
+        rc = emu.emu_powm_prog(shape_id(L, TPI), P(bw), nw, None, P(pa), len(prog) - 1, P(out), nw, len(base),
+                               PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"]), PD(mc["oneM"]), PD(mc["one"]))
+        assert rc == 0
+        assert from_words(out) == [pow(b, e, N) for b in base]
+
+
 def _dec_consts(sk, L, TPI):
     """Decrypt-tail constant block, computed with Python ints."""
     R = 1 << (52 * L * TPI)
@@ -94,6 +127,12 @@ def test_decrypt_pipeline(emu, bits, L, TPI):
                           PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"]), PD(mc["oneM"]), PD(mc["one"]))
         assert rc == 0
         assert from_words(out) == [pow(c % X2, x - 1, X2) for c in cs]
+        from pailliercryptolib_python_b200 import capi
+        pa = np.array(capi.host_powm_program(x - 1, hw), dtype=np.uint32)
+        out2 = np.zeros_like(out)
+        rc = emu.emu_powm_prog(shape_id(L, TPI), None, 0, PD(ent), P(pa), len(pa) - 1, P(out2), hw, len(cs),
+                               PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"]), PD(mc["oneM"]), PD(mc["one"]))
+        assert rc == 0 and np.array_equal(out, out2)
         us.append(out)
     cst, n0 = _dec_consts(sk, L, TPI)
     mo = np.zeros((len(cs), hw), dtype=np.uint32)
