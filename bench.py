@@ -160,7 +160,7 @@ def run_reference(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u64 (OpenSSL BIGNUM limbs)", "data": "synthetic",
         "config": {"workload": "2048-bit bench key (DJN), encrypt+decrypt, reference batch=100000 sampled at %d elements/step" % sample,
                    "key_bits": 2048, "batch": sample, "scheme": "DJN"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -263,33 +263,56 @@ def run_gpu(args):
     barrier()
     e2e_steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
+    e2e_each = []
     for _ in range(e2e_steps):
+        t1 = time.perf_counter()
         step_e2e()
+        e2e_each.append(round((time.perf_counter() - t1) * 1e3, 2))
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
     if not np.array_equal(out_hv, m_hv):
         raise RuntimeError("round trip D(E(m)) != m through the host C ABI")
     e2e = {"value": world * 2.0 * N / (e2e_ms * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(N * (64 + 32 + 128) * 4), "d2h_bytes_per_step": int(N * (128 + 64) * 4),
-           "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "phe_encrypt + phe_decrypt (host buffers, pinned)"}
+           "ms_per_step": e2e_ms, "ms_each_step": e2e_each, "steps": e2e_steps, "api": "phe_encrypt + phe_decrypt (host buffers, pinned)"}
 
     # ---- roofline of the dominant kernel (k_powm: the two CRT modexps of decrypt) -----------------------------
     peak = capi.int_pipe_peak(5)
+    fp64_peak = capi.fp64_pipe_peak(5)
+    mix_peak = capi.product_mix_peak(5)
     powm_ms, powm_n = ktimes["k_powm"]
     comb_ms, comb_n = ktimes["k_encrypt_comb"]
     roofline = None
     if powm_n:
         per_launch_ms = powm_ms / powm_n
-        achieved = W_DEC_2048 * (N * args.steps / powm_n) / (per_launch_ms * 1e-3)
+        ops_per_launch = N * args.steps / powm_n
+        achieved = W_DEC_2048 * ops_per_launch / (per_launch_ms * 1e-3)
+        # what the kernel really executes: Montgomery products of the two sliding-window programs (p-1, q-1),
+        # 2*K^2 limb products of 52 bits each (K = 40), 3 FP64 instructions per limb product
+        K52 = 40
+        progs = [capi.host_powm_program(x - 1, 64) for x in (p, q)]
+        mm_per_op = sum(sum(op >> 8 for op in pr[1:]) + sum(1 for op in pr[1:] if op & 0xFF != 0xFF) + 32 + 1 for pr in progs)
+        limb_products = mm_per_op * 2 * K52 * K52
+        prod_rate = limb_products * ops_per_launch / (per_launch_ms * 1e-3)
         roofline = {
-            "bound": "int_pipe", "kernel": "k_powm<20,2,5> (decrypt: c^(p-1) mod p^2, c^(q-1) mod q^2)",
+            "bound": "int_pipe", "kernel": "k_powm_prog<20,2> (decrypt: c^(p-1) mod p^2, c^(q-1) mod q^2)",
             "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s", "frac": achieved / peak,
             "traffic": None, "launch_ms": per_launch_ms, "launches": powm_n,
             "peak_source": "measured live: phe_int_pipe_peak (IMAD.WIDE.U32 issue rate, all SMs)",
             "algorithmic_mac32_per_op": W_DEC_2048,
+            "note": "algorithmic MAC32 of the reference algorithm (SURVEY 8d) against the integer-multiplier peak; the "
+                    "kernel itself runs 52-bit limb products on the FP64 pipe, hence frac > 1 -- see fp64_pipe / product_mix",
             "share_of_step": powm_ms / ms_total,
-            # HBM view of the same kernel (sanity counter: the path is integer-pipe bound)
-            "hbm": {"algorithmic_bytes_per_op": 2 * (148 * 4 + 256), "achieved_gbs": 2 * (148 * 4 + 256) * (N * args.steps / powm_n) / (per_launch_ms * 1e-3) / 1e9,
+            # the pipe the kernel executes on: DFMA/DADD lane operations per second against the measured DFMA rate
+            "fp64_pipe": {"executed_fp64_per_op": 3 * limb_products, "achieved": 3 * prod_rate / 1e12, "peak": fp64_peak / 1e12,
+                          "unit": "T FP64 lane-ops/s", "frac": 3 * prod_rate / fp64_peak,
+                          "peak_source": "measured live: phe_fp64_pipe_peak (DFMA.RZ issue rate, all SMs)"},
+            # the practical ceiling: the bare 2 DFMA + DADD + IADD3 + IADD3.X mix of one limb product
+            "product_mix": {"montmul_per_op": mm_per_op, "limb_products_per_op": limb_products, "achieved": prod_rate / 1e12,
+                            "peak": mix_peak / 1e12, "unit": "T limb-products/s", "frac": prod_rate / mix_peak,
+                            "peak_source": "measured live: phe_product_mix_peak (same instruction mix, nothing else)"},
+            # HBM view of the same kernel (sanity counter: the path is arithmetic bound)
+            "hbm": {"algorithmic_bytes_per_op": 2 * (80 * 8 + 256), "achieved_gbs": 2 * (80 * 8 + 256) * ops_per_launch / (per_launch_ms * 1e-3) / 1e9,
                     "peak_gbs": _measured_hbm()},
         }
     kernels = {k: {"ms_total": v[0], "launches": v[1]} for k, v in ktimes.items() if v[1]}
@@ -323,7 +346,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic",
+            "dtype": "f64 (exact 52-bit integer limbs, 64-bit integer accumulators)", "data": "synthetic",
             "config": {"workload": "2048-bit bench key (DJN), batch=%d encrypt+decrypt per GPU (BASELINE configs[1])" % N,
                        "key_bits": 2048, "batch_per_gpu": N, "scheme": "DJN", "ops_per_step": 2 * N * world,
                        "l2": "flushed between timed iterations (256 MiB memset inside the timed region)"},

@@ -48,6 +48,12 @@ const char* phe_timing_kind_name(int kind);
 /* Integer-pipe roofline denominator measured on the current device: sustained IMAD.WIDE.U32 issue rate in
  * multiply-accumulates per second (all SMs, independent chains), best of `reps` runs. */
 int phe_int_pipe_peak(int reps, double* mac_per_s);
+/* FP64-pipe denominator: sustained DFMA.RZ issue rate in lane operations per second (the Montgomery kernels run on
+ * this pipe: csrc/mont52.cuh). */
+int phe_fp64_pipe_peak(int reps, double* dfma_per_s);
+/* Rate of the bare instruction mix of one 52x52-bit limb product (2 DFMA + 1 DADD + IADD3 + IADD3.X, 20 independent
+ * products in flight, nothing else) in limb products per second: the practical ceiling of the Montgomery kernels. */
+int phe_product_mix_peak(int reps, double* products_per_s);
 
 /* ---- keys ---------------------------------------------------------------------------------------------- */
 

@@ -22,7 +22,8 @@ SYMBOLS = [
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
     "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program",
-    "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak",
+    "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
+    "phe_product_mix_peak",
 ]
 
 
@@ -110,6 +111,20 @@ def int_pipe_peak(reps=5):
     """Measured IMAD.WIDE.U32 issue rate of the current device in MAC/s (the roofline denominator)."""
     v = ctypes.c_double()
     _check(lib().phe_int_pipe_peak(int(reps), ctypes.byref(v)), "phe_int_pipe_peak")
+    return v.value
+
+
+def fp64_pipe_peak(reps=5):
+    """Measured DFMA.RZ issue rate of the current device in lane operations/s."""
+    v = ctypes.c_double()
+    _check(lib().phe_fp64_pipe_peak(int(reps), ctypes.byref(v)), "phe_fp64_pipe_peak")
+    return v.value
+
+
+def product_mix_peak(reps=5):
+    """Measured rate of the bare 52x52-bit limb-product instruction mix in products/s."""
+    v = ctypes.c_double()
+    _check(lib().phe_product_mix_peak(int(reps), ctypes.byref(v)), "phe_product_mix_peak")
     return v.value
 
 

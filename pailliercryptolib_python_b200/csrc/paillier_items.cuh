@@ -56,10 +56,10 @@ PHE_HD uint32_t get_bits(const uint32_t* w, int nwords, int pos, int width) {
   return (uint32_t)(two >> sh) & ((1u << width) - 1u);
 }
 
-// x (montmul result) -> canonical, + 1, exact limbs again (1 + m n < n^2 always)
-template <int L, int TPI, class Env> PHE_HD void canonical_plus_one(double (&x)[L], const double* n_entry) {
+// x (montmul result, < 2N) += 1, exact limbs again: still a valid montmul operand (no reduction needed here)
+template <int L, int TPI, class Env> PHE_HD void plus_one_exact(double (&x)[L]) {
   uint64_t xi[L];
-  canonical_ints<L, TPI, Env>(xi, x, n_entry);
+  ints_of<L>(xi, x);
   if (Env::lane() == 0) xi[0] += 1ull;
   normalize_exact<L, TPI, Env>(xi);
   limbs_of<L>(x, xi);
@@ -304,7 +304,6 @@ PHE_HD void item_encrypt_comb(const uint32_t* m_w, int m_words, const uint32_t* 
                               const double* nR, const double* comb, GroupSmem sm) {
   constexpr int KP = Shape<L, TPI>::KP;
   double x[L];
-  uint64_t xi[L];
   int j = 1;
   // step kinds: 0 comb multiply, 1 raw (m * nR), 2 final (raw * obf)
   int kind;
@@ -341,19 +340,19 @@ PHE_HD void item_encrypt_comb(const uint32_t* m_w, int m_words, const uint32_t* 
     if (kind == 0) {
       if (++j == nwin) kind = 1;
     } else if (kind == 1) {
-      // x == m*n (mod n^2), < 2 n^2: make it canonical and add 1
-      if (!r_w) {
-        canonical_ints<L, TPI, Env>(xi, x, n_entry);
-        if (Env::lane() == 0) xi[0] += 1ull;
-        normalize_exact<L, TPI, Env>(xi);
-        break;
-      }
-      canonical_plus_one<L, TPI, Env>(x, n_entry);
+      // x == m*n (mod n^2), < 2 n^2
+      if (!r_w) break;
+      plus_one_exact<L, TPI, Env>(x);   // == 1 + m n (mod n^2), < 2 n^2 + 1: fine as the next multiplicand
       kind = 2;
     } else {
-      canonical_ints<L, TPI, Env>(xi, x, n_entry);
       break;
     }
+  }
+  uint64_t xi[L];
+  canonical_ints<L, TPI, Env>(xi, x, n_entry);
+  if (!r_w) {   // make_secure = false: ct = 1 + m n, and m n mod n^2 <= n^2 - n
+    if (Env::lane() == 0) xi[0] += 1ull;
+    normalize_exact<L, TPI, Env>(xi);
   }
   store_words<L, TPI, Env>(out_w, out_words, xi, sm.b0);
 }
@@ -382,7 +381,7 @@ PHE_HD void item_encrypt_finish(const uint32_t* m_w, int m_words, const uint32_t
       bp = nR;
       kind = 1;
     } else if (kind == 1) {
-      canonical_plus_one<L, TPI, Env>(x, n_entry);
+      plus_one_exact<L, TPI, Env>(x);
       bp = sm.b1;
       kind = 2;
     } else {

@@ -240,7 +240,7 @@ struct phe_pubkey {
   mutable DevBuf d_ctx, d_comb;
   std::vector<uint32_t> h_ctx;    // Montgomery block, uploaded lazily
   int nwin = 0;
-  mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_tbl;  // op workspaces
+  mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_r, ws_tbl;  // op workspaces
   mutable DevBuf d_prog_n;                         // classic scheme: sliding-window program of the exponent n
   std::vector<uint32_t> h_prog_n;
   mutable std::mutex mu;
@@ -542,7 +542,7 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
 
 void phe_pubkey_destroy(phe_pubkey* pk) {
   if (!pk) return;
-  for (DevBuf* b : {&pk->d_ctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
+  for (DevBuf* b : {&pk->d_ctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
   delete pk;
 }
 int phe_pubkey_bits(const phe_pubkey* pk) { return pk ? pk->bits : -1; }
@@ -723,19 +723,16 @@ int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uin
     PHE_TRY(pk->ws_b.ensure(count * cw));
     CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, m, count * pk->n_words * 4, cudaMemcpyHostToDevice, 0));
     const uint32_t* d_r = nullptr;
-    DevBuf rbuf;
-    if (r) {
-      PHE_TRY(rbuf.ensure(count * (size_t)r_words));
-      cudaError_t e = cudaMemcpyAsync(rbuf.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice, 0);
-      if (e != cudaSuccess) { rbuf.release(); return fail(std::string("H2D r: ") + cudaGetErrorString(e)); }
-      d_r = rbuf.p;
+    if (r) {   // workspace kept with the key: a cudaMalloc/cudaFree pair per call costs milliseconds and a device sync
+      PHE_TRY(pk->ws_r.ensure(count * (size_t)r_words));
+      CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice, 0));
+      d_r = pk->ws_r.p;
     }
     int rc = encrypt_dev_impl(pk, pk->ws_a.p, count, d_r, r_words, pk->ws_b.p, 0);
     if (!rc) {
       cudaError_t e = cudaMemcpy(ct_out, pk->ws_b.p, count * cw * 4, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) rc = fail(std::string("phe_encrypt D2H: ") + cudaGetErrorString(e));
     }
-    rbuf.release();
     return rc;
   } catch (const std::exception& e) { return fail(std::string("phe_encrypt: ") + e.what()); }
 }
