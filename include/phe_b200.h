@@ -66,6 +66,13 @@ int phe_product_mix_peak(int reps, double* products_per_s);
 int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const uint32_t* hs, int randbits,
                       phe_pubkey** out);
 void phe_pubkey_destroy(phe_pubkey* pk);
+/* Digit width (1..16 bits, 0 = automatic from the free device memory) of the DJN fixed-base comb table
+ * T[j][d] = hs^(d 2^(bits j)): an obfuscated encrypt costs randbits / bits + 2 Montgomery products and the table
+ * nwin * 2^bits entries of HBM (2.7 GB at 16 bits for a 2048-bit key).  Takes effect at the next table build
+ * (the first obfuscated encrypt, or immediately if the width changes).  The environment variable PHE_COMB_BITS
+ * sets the default.  phe_pubkey_comb_bits returns the width in use (0 before the table exists). */
+int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits);
+int phe_pubkey_comb_bits(const phe_pubkey* pk);
 int phe_pubkey_bits(const phe_pubkey* pk);
 int phe_pubkey_n_words(const phe_pubkey* pk);
 int phe_pubkey_is_djn(const phe_pubkey* pk);

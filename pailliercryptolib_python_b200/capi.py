@@ -21,7 +21,7 @@ SYMBOLS = [
     "phe_privkey_create", "phe_privkey_destroy", "phe_privkey_get_p", "phe_privkey_get_q", "phe_keygen",
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
-    "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program",
+    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
     "phe_product_mix_peak",
 ]
@@ -150,6 +150,14 @@ class PubKey:
                 self.h = None
         except Exception:
             pass
+
+    def set_comb_bits(self, bits):
+        """Digit width of the DJN comb table (0 = automatic); see include/phe_b200.h."""
+        _check(lib().phe_pubkey_set_comb_bits(self.h, int(bits)), "phe_pubkey_set_comb_bits")
+
+    @property
+    def comb_bits(self):
+        return lib().phe_pubkey_comb_bits(self.h)
 
     @property
     def hs(self):

@@ -103,6 +103,13 @@ template <int TPI> struct DevEnv {
     return __any_sync(0xffffffffu, p) != 0;
   }
   static PHE_D void sync() { __syncwarp(); }
+  // 16-byte asynchronous global -> shared copy (LDGSTS) and the matching wait; used to prefetch the next comb-table
+  // entry of the DJN encrypt under the current Montgomery product
+  static PHE_D void cp_async16(void* dst_shared, const void* src_global) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_shared);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_global) : "memory");
+  }
+  static PHE_D void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 };
 #endif
 

@@ -293,13 +293,22 @@ PHE_HD void item_dec_prep(const uint32_t* c_w, int hw, double* out_entry, const 
 
 // ------------------------------------------------------------------------------------------------
 // DJN encrypt with a fixed-base comb table (no squarings):
-//   obf = prod_j T[j][digit_j(r)],  T[j][d] = hs^(d * 2^(WB j)) * R mod n^2
+//   obf = prod_j T[j][digit_j(r)],  T[j][d] = hs^(d * 2^(wb j)) * R mod n^2,  digits of wb bits (wb <= 16)
 //   ct  = (1 + m n) * obf mod n^2
 // ipcl::PublicKey::encrypt + applyObfuscator (DJN) (ipcl_bindings_classes.cpp:53-60, 71-83).
 // r_w == nullptr -> make_secure = false (ct = 1 + m n).
+// The table lives in HBM (2.7 GB at wb = 16 for a 2048-bit key: 64 windows x 65536 entries x 640 B); the entry of
+// window j+1 is fetched with cp.async into the idle operand buffer while window j is being multiplied.
 // ------------------------------------------------------------------------------------------------
-template <int L, int TPI, class Env, int WB>
-PHE_HD void item_encrypt_comb(const uint32_t* m_w, int m_words, const uint32_t* r_w, int r_words, int nwin,
+template <int L, int TPI, class Env> PHE_HD void copy_entry_async(double* dst, const double* src) {
+  constexpr int LP = Pad<L>::LP;
+  const int lane = Env::lane();
+#pragma unroll
+  for (int j = 0; j < LP / 2; ++j) Env::cp_async16(dst + lane * LP + 2 * j, src + lane * LP + 2 * j);
+}
+
+template <int L, int TPI, class Env>
+PHE_HD void item_encrypt_comb(const uint32_t* m_w, int m_words, const uint32_t* r_w, int r_words, int nwin, int wb,
                               uint32_t* out_w, int out_words, const double* n_entry, uint64_t n0inv,
                               const double* nR, const double* comb, GroupSmem sm) {
   constexpr int KP = Shape<L, TPI>::KP;
@@ -308,21 +317,31 @@ PHE_HD void item_encrypt_comb(const uint32_t* m_w, int m_words, const uint32_t* 
   // step kinds: 0 comb multiply, 1 raw (m * nR), 2 final (raw * obf)
   int kind;
   const double* bp;
+  double* cur = sm.b0;      // buffer the pending prefetch was issued into
+  double* other = sm.b1;
   if (r_w) {
-    const uint32_t d0 = get_bits(r_w, r_words, 0, WB);
+    const uint32_t d0 = get_bits(r_w, r_words, 0, wb);
     load_entry<L, TPI, Env>(x, comb + (size_t)d0 * KP);
     kind = (nwin > 1) ? 0 : 1;
+    if (nwin > 1) {
+      const uint32_t d1 = get_bits(r_w, r_words, wb, wb);
+      Env::sync();
+      copy_entry_async<L, TPI, Env>(cur, comb + (((size_t)1 << wb) + d1) * KP);
+    }
   } else {
     kind = 1;
   }
 #pragma unroll 1
   for (;;) {
     if (kind == 0) {
-      const uint32_t d = get_bits(r_w, r_words, j * WB, WB);
-      Env::sync();
-      copy_entry<L, TPI, Env>(sm.b0, comb + ((size_t)j * (1u << WB) + d) * KP);
-      Env::sync();
-      bp = sm.b0;
+      Env::cp_async_wait();
+      Env::sync();                       // entry j is in `cur`; every lane is done reading `other`
+      if (j + 1 < nwin) {
+        const uint32_t d = get_bits(r_w, r_words, (j + 1) * wb, wb);
+        copy_entry_async<L, TPI, Env>(other, comb + ((((size_t)j + 1) << wb) + d) * KP);
+      }
+      bp = cur;
+      double* t = cur; cur = other; other = t;
     } else if (kind == 1) {
       if (r_w) {   // park obf*R in b1
         Env::sync();

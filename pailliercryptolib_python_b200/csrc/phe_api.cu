@@ -240,6 +240,9 @@ struct phe_pubkey {
   mutable DevBuf d_ctx, d_comb;
   std::vector<uint32_t> h_ctx;    // Montgomery block, uploaded lazily
   int nwin = 0;
+  mutable int comb_bits = 0;      // digit width of the comb table once built (0: not built yet)
+  int comb_bits_wanted = 0;       // 0: choose from the free device memory
+  mutable bool comb_ready = false;
   mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_r, ws_tbl;  // op workspaces
   mutable DevBuf d_prog_n;                         // classic scheme: sliding-window program of the exponent n
   std::vector<uint32_t> h_prog_n;
@@ -272,21 +275,43 @@ int pk_ensure_device(const phe_pubkey* pk) {
   CUDA_TRY(cudaGetDevice(const_cast<int*>(&pk->device)));
   PHE_TRY(upload(pk->d_ctx, pk->h_ctx));
   pk->ctx.entries = reinterpret_cast<const double*>(pk->d_ctx.p);
-  if (pk->djn) {
-    // fixed-base comb table T[j][d] = hs^(d 2^(8j)) R mod n^2
-    PHE_TRY(pk->d_comb.ensure((size_t)pk->nwin * 256 * EW(pk->ops)));
-    std::vector<uint32_t> hsw(2 * (size_t)pk->n_words);
-    pk->hs.to_words(hsw.data(), hsw.size());
-    DevBuf dhs;
-    PHE_TRY(upload(dhs, hsw));
-    CombArgs ca{};
-    ca.hs_w = dhs.p; ca.hs_words = 2 * pk->n_words; ca.nwin = pk->nwin; ca.comb = reinterpret_cast<double*>(pk->d_comb.p); ca.ctx = pk->ctx;
-    cudaError_t e = pk->ops->comb_build(ca, 0);
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    dhs.release();
-    if (e != cudaSuccess) return fail(std::string("comb table build: ") + cudaGetErrorString(e));
-  }
   pk->dev_ready = true;
+  return 0;
+}
+
+// Comb table of the DJN obfuscator, built on the first obfuscated encrypt.  Digit width: as wide as the device memory
+// comfortably allows (the table is nwin * 2^wb entries: 2.7 GB at wb = 16 for a 2048-bit key, 15 ms to build), because
+// the number of Montgomery products per encrypt is randbits / wb + 2.  PHE_COMB_BITS or phe_pubkey_set_comb_bits override.
+int pk_ensure_comb(const phe_pubkey* pk) {
+  if (pk->comb_ready) return 0;
+  if (!pk->djn) return fail("comb table requested for a non-DJN key");
+  int wb = pk->comb_bits_wanted;
+  if (wb <= 0) { const char* e = getenv("PHE_COMB_BITS"); if (e) wb = atoi(e); }
+  const size_t entry_bytes = EW(pk->ops) * 4;
+  auto table_bytes = [&](int w) { return (size_t)((pk->randbits + w - 1) / w) * ((size_t)1 << w) * entry_bytes; };
+  if (wb <= 0) {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    wb = 16;
+    while (wb > 8 && (table_bytes(wb) > free_b / 8 || table_bytes(wb) > ((size_t)6 << 30))) wb -= 2;
+  }
+  if (wb < 1) wb = 1;
+  if (wb > 16) wb = 16;
+  pk->comb_bits = wb;
+  const_cast<phe_pubkey*>(pk)->nwin = (pk->randbits + wb - 1) / wb;
+  PHE_TRY(pk->d_comb.ensure(table_bytes(wb) / 4));
+  std::vector<uint32_t> hsw(2 * (size_t)pk->n_words);
+  pk->hs.to_words(hsw.data(), hsw.size());
+  DevBuf dhs;
+  PHE_TRY(upload(dhs, hsw));
+  CombArgs ca{};
+  ca.hs_w = dhs.p; ca.hs_words = 2 * pk->n_words; ca.nwin = pk->nwin; ca.wb = wb;
+  ca.comb = reinterpret_cast<double*>(pk->d_comb.p); ca.ctx = pk->ctx;
+  cudaError_t e = pk->ops->comb_build(ca, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  dhs.release();
+  if (e != cudaSuccess) return fail(std::string("comb table build: ") + cudaGetErrorString(e));
+  pk->comb_ready = true;
   return 0;
 }
 
@@ -335,13 +360,14 @@ int obfuscators_dev(const phe_pubkey* pk, const uint32_t* d_r, int r_words, size
   const int cw = 2 * pk->n_words;
   if (pk->djn) {
     // comb kernel with m = 0 gives (1 + 0) * obf
+    PHE_TRY(pk_ensure_comb(pk));
     PHE_TRY(pk->ws_d.ensure((size_t)pk->n_words));
     CUDA_TRY(cudaMemsetAsync(pk->ws_d.p, 0, (size_t)pk->n_words * 4, s));
     for (size_t off = 0; off < count; off += CHUNK) {
       const int c = (int)std::min(CHUNK, count - off);
       EncCombArgs a{};
       a.m_w = pk->ws_d.p; a.m_words = 0;   // zero words: m = 0 for every item
-      a.r_w = d_r + off * r_words; a.r_words = r_words; a.nwin = pk->nwin;
+      a.r_w = d_r + off * r_words; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
       a.out_w = d_obf + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
       CUDA_TRY(pk->ops->encrypt_comb(a, s));
     }
@@ -390,13 +416,16 @@ int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, co
   const int cw = 2 * pk->n_words;
   if (count == 0) return 0;
   if (!d_r || pk->djn) {
+    if (d_r) {
+      PHE_TRY(pk_ensure_comb(pk));
+      if ((size_t)r_words * 32 < (size_t)pk->randbits) return fail("phe_encrypt: r_words too small for randbits");
+    }
     for (size_t off = 0; off < count; off += CHUNK) {
       const int c = (int)std::min(CHUNK, count - off);
       EncCombArgs a{};
       a.m_w = d_m + off * pk->n_words; a.m_words = pk->n_words;
-      a.r_w = d_r ? d_r + off * r_words : nullptr; a.r_words = r_words; a.nwin = pk->nwin;
+      a.r_w = d_r ? d_r + off * r_words : nullptr; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
       a.out_w = d_ct + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
-      if (d_r && (size_t)r_words * 32 < (size_t)pk->nwin * 8) return fail("phe_encrypt: r_words too small for randbits");
       CUDA_TRY(pk->ops->encrypt_comb(a, s));
     }
     return 0;
@@ -531,7 +560,6 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
         const BN h = hbn::sub(N, hbn::mulmod(xm, xm, N));
         pk->hs = hbn::modexp(h, N, pk->nsq);
       }
-      pk->nwin = (pk->randbits + 7) / 8;
     } else {
       pk->h_prog_n = build_powm_program(N);
     }
@@ -545,6 +573,15 @@ void phe_pubkey_destroy(phe_pubkey* pk) {
   for (DevBuf* b : {&pk->d_ctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
   delete pk;
 }
+int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits) {
+  if (!pk) return fail("null");
+  if (bits < 0 || bits > 16) return fail("phe_pubkey_set_comb_bits: bits must be in [0, 16] (0 = automatic)");
+  std::lock_guard<std::mutex> lk(pk->mu);
+  if (pk->comb_ready && bits != pk->comb_bits) { pk->d_comb.release(); pk->comb_ready = false; }
+  pk->comb_bits_wanted = bits;
+  return 0;
+}
+int phe_pubkey_comb_bits(const phe_pubkey* pk) { return pk ? pk->comb_bits : -1; }
 int phe_pubkey_bits(const phe_pubkey* pk) { return pk ? pk->bits : -1; }
 int phe_pubkey_n_words(const phe_pubkey* pk) { return pk ? pk->n_words : -1; }
 int phe_pubkey_is_djn(const phe_pubkey* pk) { return pk ? pk->djn : -1; }

@@ -206,11 +206,12 @@ struct EncCombArgs {
   const uint32_t* r_w;   // [count][r_words] or null (make_secure = false)
   int r_words;
   int nwin;
+  int wb;                // comb digit width in bits (<= 16)
   uint32_t* out_w;       // [count][out_words]
   int out_words;
   int count;
   MontCtxArgs ctx;       // n^2 context; ME_X0 = n*R mod n^2
-  const double* comb;    // [nwin][256][KP]
+  const double* comb;    // [nwin][1 << wb][KP]
 };
 
 template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_encrypt_comb(EncCombArgs p) {
@@ -223,8 +224,8 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
   for (int base = blockIdx.x * KS::GPB; base < p.count; base += gridDim.x * KS::GPB) {
     const int want = base + g;
     const int item = want < p.count ? want : p.count - 1;
-    item_encrypt_comb<L, TPI, Env, 8>(p.m_w + (size_t)item * p.m_words, p.m_words,
-                                      p.r_w ? p.r_w + (size_t)item * p.r_words : nullptr, p.r_words, p.nwin,
+    item_encrypt_comb<L, TPI, Env>(p.m_w + (size_t)item * p.m_words, p.m_words,
+                                      p.r_w ? p.r_w + (size_t)item * p.r_words : nullptr, p.r_words, p.nwin, p.wb,
                                       want < p.count ? p.out_w + (size_t)item * p.out_words : nullptr, p.out_words,
                                       smem + ME_N * KS::KP, p.ctx.n0inv, smem + ME_X0 * KS::KP, p.comb, sm);
   }
@@ -258,14 +259,19 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
   }
 }
 
-// ---- comb table construction (key setup, once per DJN key) ---------------------------------------------
-// Phase A (one group): T[j][1] = hs^(2^(8j)) * R for j = 0..nwin-1 by repeated squaring.
-// Phase B (one group per window j): T[j][0] = R mod N, T[j][d] = T[j][d-1] * T[j][1].
+// ---- comb table construction (once per DJN key, on the first obfuscated encrypt) ------------------------------
+// T[j][d] = hs^(d 2^(wb j)) R mod n^2, j < nwin, d < 2^wb.
+// Phase A (k_comb_bases, one group): the chain hs^(2^i) R, i = 0 .. wb*nwin - 1, by repeated squaring;
+//   element i = wb j + k is T[j][2^k].  T[j][0] = R mod N is written alongside.
+// Phase B (k_comb_level, one launch per k = 1 .. wb-1): T[j][2^k + e] = T[j][e] * T[j][2^k] for 0 < e < 2^k --
+//   nwin (2^k - 1) independent products per level, 4.2 M in total at wb = 16 (~15 ms).
 struct CombArgs {
   const uint32_t* hs_w;   // hs canonical words
   int hs_words;
   int nwin;
-  double* comb;           // [nwin][256][KP]
+  int wb;
+  int level;              // k_comb_level: k
+  double* comb;           // [nwin][1 << wb][KP]
   MontCtxArgs ctx;
 };
 
@@ -280,11 +286,16 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
   const bool writer = (threadIdx.x / TPI) == 0;
   limbs_from_words<L, TPI, Env>(x, p.hs_w, p.hs_words);
   const double* bp = smem + ME_R2 * KS::KP;
-  const int total = 1 + (p.nwin - 1) * 8;
+  const int total = p.wb * p.nwin;
 #pragma unroll 1
-  for (int s = 0; s < total; ++s) {
+  for (int i = 0; i < total; ++i) {   // product i yields hs^(2^i) R
     montmul<L, TPI, Env>(x, x, bp, smem + ME_N * KS::KP, p.ctx.n0inv);
-    if (s % 8 == 0 && writer) limbs_to_mem<L, TPI, Env>(p.comb + ((size_t)(s / 8) * 256 + 1) * KS::KP, x);
+    const int j = i / p.wb, k = i - j * p.wb;
+    double* row = p.comb + ((size_t)j << p.wb) * KS::KP;
+    if (writer) {
+      limbs_to_mem<L, TPI, Env>(row + ((size_t)1 << k) * KS::KP, x);
+      if (k == 0) copy_entry<L, TPI, Env>(row, smem + ME_ONEM * KS::KP);
+    }
     Env::sync();
     limbs_to_mem<L, TPI, Env>(sm.b0, x);
     Env::sync();
@@ -292,7 +303,7 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
   }
 }
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_comb_fill(CombArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_comb_level(CombArgs p) {
   using Env = DevEnv<TPI>;
   using KS = KShape<L, TPI>;
   extern __shared__ __align__(16) double smem[];
@@ -300,20 +311,19 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
   GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
   double x[L];
   const int g = threadIdx.x / TPI;
-  for (int base = blockIdx.x * KS::GPB; base < p.nwin; base += gridDim.x * KS::GPB) {
+  const int per_win = (1 << p.level) - 1;
+  const int count = p.nwin * per_win;
+  for (int base = blockIdx.x * KS::GPB; base < count; base += gridDim.x * KS::GPB) {
     const int want = base + g;
-    const int j = want < p.nwin ? want : p.nwin - 1;
-    double* row = p.comb + (size_t)j * 256 * KS::KP;
+    const int item = want < count ? want : count - 1;   // past the end: redo the last product (same value stored)
+    const int j = item / per_win, e = 1 + item % per_win;
+    double* row = p.comb + ((size_t)j << p.wb) * KS::KP;
     Env::sync();
-    copy_entry<L, TPI, Env>(sm.b0, row + KS::KP);          // T[j][1]
-    copy_entry<L, TPI, Env>(row, smem + ME_ONEM * KS::KP);  // T[j][0]
+    copy_entry<L, TPI, Env>(sm.b0, row + ((size_t)1 << p.level) * KS::KP);
     Env::sync();
-    load_entry<L, TPI, Env>(x, sm.b0);
-#pragma unroll 1
-    for (int d = 2; d < 256; ++d) {
-      montmul<L, TPI, Env>(x, x, sm.b0, smem + ME_N * KS::KP, p.ctx.n0inv);
-      limbs_to_mem<L, TPI, Env>(row + (size_t)d * KS::KP, x);
-    }
+    load_entry<L, TPI, Env>(x, row + (size_t)e * KS::KP);
+    montmul<L, TPI, Env>(x, x, sm.b0, smem + ME_N * KS::KP, p.ctx.n0inv);
+    limbs_to_mem<L, TPI, Env>(row + (((size_t)1 << p.level) + e) * KS::KP, x);
   }
 }
 

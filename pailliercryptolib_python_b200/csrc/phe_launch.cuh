@@ -116,19 +116,24 @@ template <int L, int TPI> struct Launch {
     }
     return cudaGetLastError();
   }
-  static cudaError_t comb_build(const CombArgs& p, cudaStream_t s) {
+  static cudaError_t comb_build(const CombArgs& p0, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     cudaFuncSetAttribute(k_comb_bases<L, TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     { TimedLaunch tl_(KK_COMB_BUILD, s);
-    k_comb_bases<L, TPI><<<1, NT, smem, s>>>(p);
+    k_comb_bases<L, TPI><<<1, NT, smem, s>>>(p0);
     }
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    const int grid = grid_for(k_comb_fill<L, TPI>, smem, p.nwin, KS::GPB, 1);
-    { TimedLaunch tl_(KK_COMB_BUILD, s);
-    k_comb_fill<L, TPI><<<grid, NT, smem, s>>>(p);
+    for (int k = 1; k < p0.wb && e == cudaSuccess; ++k) {
+      CombArgs p = p0;
+      p.level = k;
+      const int count = p.nwin * ((1 << k) - 1);
+      const int grid = grid_for(k_comb_level<L, TPI>, smem, count, KS::GPB, 1);
+      { TimedLaunch tl_(KK_COMB_BUILD, s);
+      k_comb_level<L, TPI><<<grid, NT, smem, s>>>(p);
+      }
+      e = cudaGetLastError();
     }
-    return cudaGetLastError();
+    return e;
   }
 
   static constexpr ShapeOps ops() {

@@ -62,6 +62,8 @@ template <int TPI> struct EmuEnv {
     return r;
   }
   static void sync() { if (TPI > 1) t_ex->bar.arrive_and_wait(); }
+  static void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+  static void cp_async_wait() {}
 };
 
 template <int TPI> void run_group(const std::function<void()>& body) {
@@ -170,8 +172,8 @@ int do_dec_prep(const uint32_t* c, int hw, double* out_entries, int count, const
   return 0;
 }
 
-template <int L, int TPI, int WB>
-int do_encrypt_comb(const uint32_t* m, int m_words, const uint32_t* r, int r_words, int nwin, uint32_t* out,
+template <int L, int TPI>
+int do_encrypt_comb(const uint32_t* m, int m_words, const uint32_t* r, int r_words, int nwin, int wb, uint32_t* out,
                     int out_words, int count, const double* n_e, uint64_t n0inv, const double* nR_e,
                     const double* comb, size_t comb_doubles) {
   using Env = EmuEnv<TPI>;
@@ -180,8 +182,8 @@ int do_encrypt_comb(const uint32_t* m, int m_words, const uint32_t* r, int r_wor
   for (int i = 0; i < count; ++i) {
     Bufs<L, TPI> bufs;
     run_group<TPI>([&] {
-      phe::item_encrypt_comb<L, TPI, Env, WB>(m + (size_t)i * m_words, m_words, r ? r + (size_t)i * r_words : nullptr,
-                                              r_words, nwin, out + (size_t)i * out_words, out_words, ne.p, n0inv, nR.p,
+      phe::item_encrypt_comb<L, TPI, Env>(m + (size_t)i * m_words, m_words, r ? r + (size_t)i * r_words : nullptr,
+                                              r_words, nwin, wb, out + (size_t)i * out_words, out_words, ne.p, n0inv, nR.p,
                                               cb.p, bufs.sm);
     });
   }
@@ -262,10 +264,10 @@ int emu_dec_prep(int shape, const uint32_t* c, int hw, double* out_entries, int 
   DISPATCH_SHAPE((do_dec_prep<L, TPI>(c, hw, out_entries, count, n_e, n0inv, r2_e, k2_e)));
 }
 
-int emu_encrypt_comb(int shape, const uint32_t* m, int m_words, const uint32_t* r, int r_words, int nwin,
+int emu_encrypt_comb(int shape, const uint32_t* m, int m_words, const uint32_t* r, int r_words, int nwin, int wb,
                      uint32_t* out, int out_words, int count, const double* n_e, uint64_t n0inv,
                      const double* nR_e, const double* comb, uint64_t comb_doubles) {
-  DISPATCH_SHAPE((do_encrypt_comb<L, TPI, 8>(m, m_words, r, r_words, nwin, out, out_words, count, n_e, n0inv, nR_e, comb, comb_doubles)));
+  DISPATCH_SHAPE((do_encrypt_comb<L, TPI>(m, m_words, r, r_words, nwin, wb, out, out_words, count, n_e, n0inv, nR_e, comb, comb_doubles)));
 }
 
 int emu_encrypt_finish(int shape, const uint32_t* m, int m_words, const uint32_t* obf, uint32_t* out, int out_words,

@@ -154,24 +154,24 @@ def _comb_table(pk, L, TPI, WB=8):
     return np.concatenate(rows), nwin
 
 
-@pytest.mark.parametrize("bits,L,TPI", [(1024, 20, 2)])
-def test_encrypt_comb(emu, bits, L, TPI):
+@pytest.mark.parametrize("bits,L,TPI,WB", [(1024, 20, 2, 8), (1024, 20, 2, 5), (1024, 20, 2, 11)])
+def test_encrypt_comb(emu, bits, L, TPI, WB):
     pk, sk = O.seeded_keypair(bits, 3)
     N = pk.nsquare
     mc = mont_consts(N, L, TPI)
     nR = to_entry(pk.n * mc["R"] % N, L, TPI)
-    comb, nwin = _comb_table(pk, L, TPI)
+    comb, nwin = _comb_table(pk, L, TPI, WB)
     rng = random.Random(9)
     ms = [0, 1, pk.n - 1, rng.randrange(pk.n), rng.getrandbits(53)]
     rs = [0, 1, (1 << pk.randbits) - 1, rng.getrandbits(pk.randbits), rng.getrandbits(pk.randbits)]
     mw, rw = to_words(ms, bits // 32), to_words(rs, pk.randbits // 32)
     out = np.zeros((len(ms), bits // 16), dtype=np.uint32)
-    rc = emu.emu_encrypt_comb(shape_id(L, TPI), P(mw), bits // 32, P(rw), pk.randbits // 32, nwin, P(out), bits // 16,
+    rc = emu.emu_encrypt_comb(shape_id(L, TPI), P(mw), bits // 32, P(rw), pk.randbits // 32, nwin, WB, P(out), bits // 16,
                               len(ms), PD(mc["n"]), U64(mc["n0inv"]), PD(nR), PD(comb), ctypes.c_uint64(len(comb)))
     assert rc == 0
     assert from_words(out) == O.encrypt_batch(pk, ms, rs)
     # make_secure = False
-    rc = emu.emu_encrypt_comb(shape_id(L, TPI), P(mw), bits // 32, None, 0, nwin, P(out), bits // 16,
+    rc = emu.emu_encrypt_comb(shape_id(L, TPI), P(mw), bits // 32, None, 0, nwin, WB, P(out), bits // 16,
                               len(ms), PD(mc["n"]), U64(mc["n0inv"]), PD(nR), PD(comb), ctypes.c_uint64(len(comb)))
     assert rc == 0
     assert from_words(out) == O.encrypt_batch(pk, ms, None)

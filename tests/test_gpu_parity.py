@@ -42,6 +42,20 @@ def test_encrypt_djn_pinned_r(key2048):
     assert got == O.encrypt_batch(pk_o, ms, None)
 
 
+@pytest.mark.parametrize("comb_bits", [1, 7, 8, 13, 16])
+def test_encrypt_comb_widths(comb_bits):
+    """Every digit width of the fixed-base comb table gives the same ciphertexts (table rebuilt on the device)."""
+    pk_o, sk_o = O.seeded_keypair(1024, 21)
+    pk = capi.PubKey(pk_o.n, 1024, djn=True, hs=pk_o.hs)
+    pk.set_comb_bits(comb_bits)
+    rng = random.Random(SEED + comb_bits)
+    ms = [0, pk_o.n - 1] + [rng.randrange(pk_o.n) for _ in range(30)]
+    rs = [0, (1 << 512) - 1, 1, 1 << 511] + [rng.getrandbits(512) for _ in range(len(ms) - 4)]
+    got = capi.array_to_ints(pk.encrypt(capi.ints_to_array(ms, 32), capi.ints_to_array(rs, 16)))
+    assert pk.comb_bits == comb_bits
+    assert got == O.encrypt_batch(pk_o, ms, rs)
+
+
 def test_decrypt_crt(key2048):
     pk_o, sk_o, pk, sk = key2048
     rng = random.Random(SEED + 1)
