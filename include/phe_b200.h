@@ -143,6 +143,13 @@ int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint
  * [TPI][LP] layout): N, R^2 mod N, R mod N, 1, extra (0 here), R = 2^(52 L TPI).  Returns KP (>0) or <0 on
  * error.  out may be NULL to query KP.  n0inv_out = -N^-1 mod 2^52. */
 int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, double* out, uint64_t* n0inv_out);
+/* Decrypt runs its two CRT halves on the p-adic pair engine when p and q both have exactly bits/2 bits (every key
+ * made by a keygen).  This dumps what the engine is given for x = p (y = 0) or q (y = 1): L (limbs per number),
+ * n0inv = -x^-1 mod 2^52, mod_out = [L] limbs of x then [L + 1] limbs of D = ceil(R / x) x (doubles), cst_out =
+ * [6][2][L] constant pairs (W_0..W_3, (1, 0), (h_x R mod x, 0)) and the program (csrc/paillier_items.cuh: PairOp).
+ * Returns the program length, 0 if the key does not use the engine, < 0 on error.  Buffers may be NULL. */
+int phe_privkey_pair_block(const phe_privkey* sk, int y, int* L_out, uint64_t* n0inv_out, double* mod_out,
+                           double* cst_out, uint32_t* prog_out, int prog_cap);
 /* Sliding-window program of a shared exponent as executed by k_powm_prog (decrypt: p-1, q-1; classic scheme: n):
  * out[0] = table index of the leading window (0xffff: exponent is zero), out[k>=1] = (squarings << 8) | index into
  * the table of odd powers x^(2 index + 1), index 0xff = no multiplication.  Returns the number of entries (or <0);

@@ -113,6 +113,21 @@ template <int TPI> struct DevEnv {
 };
 #endif
 
+#if defined(__CUDACC__)
+// One bignum per lane (the p-adic pair engine): a "group" is a single lane, per-lane operands sit in shared memory as
+// columns of a [limb][32] matrix.
+struct DevPairEnv {
+  static constexpr int STRIDE = 32;
+  static PHE_D int lane() { return 0; }
+  static PHE_D int column() { return (int)(threadIdx.x & 31); }
+  static PHE_D uint32_t bcast(uint32_t v, int) { return v; }
+  static PHE_D uint32_t from_above(uint32_t) { return 0u; }
+  static PHE_D uint32_t from_below(uint32_t) { return 0u; }
+  static PHE_D bool any(bool p) { return p; }
+  static PHE_D void sync() { __syncwarp(); }
+};
+#endif
+
 template <class Env> PHE_HD uint64_t bcast64(uint64_t v, int src) {
   const uint32_t lo = Env::bcast((uint32_t)v, src), hi = Env::bcast((uint32_t)(v >> 32), src);
   return ((uint64_t)hi << 32) | lo;
@@ -282,6 +297,110 @@ PHE_HD void montmul(double (&r)[L], const double (&a)[L], const double* b, const
   normalize_exact<L, TPI, Env>(acc);
 #pragma unroll
   for (int j = 0; j < L; ++j) r[j] = limb_of(acc[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// p-adic pair arithmetic for the CRT half of decrypt:  numbers mod x^2 (x = p or q) are kept as pairs (X0, X1),
+// X0, X1 < 2x, meaning (X0 + X1 x) R^-1 mod x^2 with R = 2^(52 L) >= 2^8 x.  With  X0 Y0 = u R - m x  (u, m the
+// result and the quotient of an ordinary Montgomery reduction mod x) one gets
+//     (X0 + X1 x)(Y0 + Y1 x) R^-1  =  u + (X0 Y1 + X1 Y0 - m) R^-1 x   (mod x^2)
+// so a product mod x^2 costs 5 L^2 limb products (3 multiplications + 2 reductions of L limbs) and a square 4 L^2,
+// against 8 L^2 for one Montgomery product of 2L limbs -- and everything fits ONE lane (L = 20 at 2048-bit keys):
+// no shuffles, 32 ciphertexts per warp.  The L function comes for free: c^(x-1) = 1 + L x.
+//
+// pair_pass is one reduction:  r = (a b [+ a2 b2] + E + m x) / R  with E = sum_i e_in[i] 2^(52 i) a (signed) column
+// addend.  Pass 1 of a product (b = Y0) records e_out[i] = D_i - q_i, D = k x >= R, which pass 2 (b = Y1, a2 = X1,
+// b2 = Y0) takes as e_in: that is the "- m" term made non-negative.  Operands other than `a` are read from, and the
+// result written to, (shared) memory with a stride of PE::STRIDE doubles between limbs (one column per lane); n and
+// dcon (L + 1 limbs of D) are shared by all lanes.  Result: exact limbs, value < 2x.  r_out may alias b.
+// ------------------------------------------------------------------------------------------------
+template <class PE> struct Strided {
+  const double* p;
+  PHE_HD double operator[](int i) const { return p[i * PE::STRIDE]; }
+};
+
+template <int L, class PE>
+PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, const double* a2, const double* b2,
+                      const int64_t* e_in, int64_t* e_out, const double* n, const double* dcon, uint64_t n0inv) {
+  constexpr int U = Unroll<L>::U;
+  constexpr int ST = PE::STRIDE;
+  const uint32_t S = a2 ? 3u : 2u;   // product sets per row: A-part(s) + N-part
+  // bias bookkeeping as in montmul, scaled by the run-time number of sets (all biases are multiples of 2^52)
+  const uint64_t INIT = 0ull - (uint64_t)S * bias_of(L, L);
+  uint64_t acc[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) acc[j] = 0ull - (uint64_t)S * bias_of(j + 1, j);
+  const Strided<PE> a2s{a2};
+
+  uint64_t topA, q;
+  double qd;
+  {  // prologue: A-part(s) of row 0 and the quotient digit
+    const double b0 = b[0];
+    uint64_t h, h2 = 0;
+    double b20 = 0.0;
+    mac_first(acc[0], a[0], b0, h);
+    if (a2) { b20 = b2[0]; mac_first(acc[0], a2[0], b20, h2); }
+    if (e_in) acc[0] += (uint64_t)e_in[0];
+    q = (acc[0] * n0inv) & M52;
+    mac_span<L, 1, L>(acc, a, b0, h, 0);
+    topA = h;
+    if (a2) { mac_span<L, 1, L>(acc, a2s, b20, h2, 0); topA += h2; }
+    qd = limb_of(q);
+  }
+#pragma unroll 1
+  for (int row0 = 0; row0 < L; row0 += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {   // row i = row0 + u; column c of row i lives in acc[(c + u) % L]
+      const int row = row0 + u;
+      const bool last = (u == U - 1) && (row == L - 1);
+      if (e_out) e_out[row * ST] = (int64_t)int_of(dcon[row]) - (int64_t)q;   // D_i - q_i
+      uint64_t hN, hA = 0, hA2 = 0;
+      const double n0 = n[0], n1 = n[1];
+      mac_first(acc[u % L], n0, qd, hN);
+      {
+        const double ph = fma_rz(n1, qd, TWO104);
+        const double pl = fma_rz(n1, qd, TWO104P52 - ph);
+        const int64_t low = (int64_t)acc[u % L];         // column 0 is complete (a multiple of 2^52, maybe negative)
+        acc[(u + 1) % L] += d2u(pl) + hN + (uint64_t)(low >> LW);
+        hN = d2u(ph);
+        acc[u % L] = 0;                                    // becomes the new top column (column L of row i)
+      }
+      double bn = 0.0, b2n = 0.0;
+      if (!last) {
+        bn = b[(row + 1) * ST];
+        mac_first(acc[(u + 1) % L], a[0], bn, hA);
+        if (a2) { b2n = b2[(row + 1) * ST]; mac_first(acc[(u + 1) % L], a2[0], b2n, hA2); }
+        if (e_in) acc[(u + 1) % L] += (uint64_t)e_in[(row + 1) * ST];
+        q = (acc[(u + 1) % L] * n0inv) & M52;
+      }
+      mac_span<L, 2, L>(acc, n, qd, hN, u);
+      acc[u % L] += topA + hN + INIT;
+      if (!last) {
+        mac_span<L, 1, L>(acc, a, bn, hA, u + 1);
+        topA = hA;
+        if (a2) { mac_span<L, 1, L>(acc, a2s, b2n, hA2, u + 1); topA += hA2; }
+        qd = limb_of(q);
+      }
+    }
+    if (U != L) {   // rotate back: column c returns to acc[c]
+      uint64_t t[L];
+#pragma unroll
+      for (int j = 0; j < L; ++j) t[j] = acc[(j + U) % L];
+#pragma unroll
+      for (int j = 0; j < L; ++j) acc[j] = t[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < L; ++j) acc[j] += (uint64_t)S * bias_of(j + 1, j);
+  if (e_out) e_out[L * ST] = (int64_t)int_of(dcon[L]);
+  if (e_in) acc[0] += (uint64_t)e_in[L * ST];            // top limb of D
+  int64_t c = 0;                                            // signed ripple: single columns may be negative, the
+#pragma unroll
+  for (int j = 0; j < L; ++j) {                             // value is in [0, 2x): no carry out of the top
+    const int64_t v = (int64_t)acc[j] + c;
+    r_out[j * ST] = limb_of((uint64_t)v & M52);
+    c = v >> LW;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

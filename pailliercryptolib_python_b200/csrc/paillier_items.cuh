@@ -501,4 +501,222 @@ PHE_HD void item_dec_tail(const uint32_t* up_w, const uint32_t* uq_w, int u_word
   store_words<L, TPI, Env>(m_w, m_words, xi, sm.b0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// CRT recombination (ipcl computeCRT): m = m_p + ((m_q - m_p) * p^-1 mod q) * p from the two halves produced by
+// item_dec_pair; same constants (DecTailConst) and shape as item_dec_tail, of which this is the last two steps.
+// ------------------------------------------------------------------------------------------------
+template <int L, int TPI, class Env>
+PHE_HD void item_dec_crt(const uint32_t* mp_w, const uint32_t* mq_w, int half_words, uint32_t* m_w, int m_words,
+                         const double* cst, const uint64_t* n0invs /* [p, q, n] */, GroupSmem sm) {
+  constexpr int KP = Shape<L, TPI>::KP;
+  double x[L];
+  uint64_t xi[L], mp[L];
+  ints_from_words<L, TPI, Env>(mp, mp_w, half_words);
+  ints_from_words<L, TPI, Env>(xi, mq_w, half_words);
+  {
+    const uint32_t neg = sub_exact<L, TPI, Env>(xi, mp);   // m_q - m_p
+    uint64_t addend[L], qi[L];
+    ints_from_entry<L, TPI, Env>(qi, cst + DT_Q * KP);
+#pragma unroll
+    for (int j = 0; j < L; ++j) addend[j] = neg ? qi[j] : 0ull;
+    add_exact<L, TPI, Env>(xi, addend);                    // + q if negative: wraps back into [0, q)
+    limbs_of<L>(x, xi);
+  }
+#pragma unroll 1
+  for (int step = 0; step < 2; ++step) {
+    const double* mod_e = cst + (step == 0 ? DT_Q : DT_N) * KP;
+    montmul<L, TPI, Env>(x, x, cst + (step == 0 ? DT_PINVM : DT_PMN) * KP, mod_e, n0invs[step == 0 ? 1 : 2]);
+    canonical_ints<L, TPI, Env>(xi, x, mod_e);             // step 0: h in [0, q); step 1: h * p (< n)
+    limbs_of<L>(x, xi);
+  }
+  add_exact<L, TPI, Env>(xi, mp);                          // m
+  store_words<L, TPI, Env>(m_w, m_words, xi, sm.b0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CRT half of decrypt on the p-adic pair engine (mont52.cuh: pair_pass), one (ciphertext, x) per lane, x = p or q:
+//     m_x = L_x(c^(x-1) mod x^2) * h_x mod x          (ipcl::PrivateKey::decryptCRT)
+// driven by a host-built program (phe_api.cu: build_decpair_program) that is the same for every lane:
+//     load the four (bits/2)-bit chunks C_k of c, multiply each by the constant pair W_k ~ 2^(k bits/2) R^2, sum
+//     -> c in pair form; table of odd powers; sliding-window squarings / multiplications (exponent x - 1);
+//     multiply by (1, 0) to leave the Montgomery domain: c^(x-1) = v0 + v1 x with v0 = 1, so L_x = v1 - [v0 = 0];
+//     multiply by (h_x R, 0); write the canonical result.
+// State per lane: X0 in registers; XS0 (copy of X0), X1, Y0, Y1, E in shared memory (columns, stride PE::STRIDE);
+// table slots in global memory (same column layout).  A product is two pair_pass calls through ONE call site.
+// ------------------------------------------------------------------------------------------------
+enum PairOp : uint32_t {
+  PO_END = 0, PO_LOADC, PO_YCONST, PO_YT, PO_YX, PO_XT, PO_TX, PO_MUL, PO_SQR, PO_SUM4, PO_FINISH, PO_OUT
+};
+enum PairConst { PC_W0 = 0, PC_W1, PC_W2, PC_W3, PC_ONE, PC_HR, PC_COUNT };   // constant pairs, [PC_COUNT][2][L] doubles
+
+template <class PE> struct PairSmem {   // all pointers already offset to this lane's column
+  double *xs0, *x1, *y0, *y1;
+  int64_t* e;                           // L + 1 entries
+};
+
+template <int L, class PE> PHE_HD void col_store(double* dst, const double (&x)[L]) {
+#pragma unroll
+  for (int j = 0; j < L; ++j) dst[j * PE::STRIDE] = x[j];
+}
+template <int L, class PE> PHE_HD void col_load(double (&x)[L], const double* src) {
+#pragma unroll
+  for (int j = 0; j < L; ++j) x[j] = src[j * PE::STRIDE];
+}
+template <int L, class PE> PHE_HD void col_copy(double* dst, const double* src) {
+#pragma unroll
+  for (int j = 0; j < L; ++j) dst[j * PE::STRIDE] = src[j * PE::STRIDE];
+}
+
+template <int L, class PE>
+PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* prog, uint32_t* out_w, int out_words,
+                          const double* n, const double* dcon, uint64_t n0inv, const double* cst, double* tbl,
+                          PairSmem<PE> sm) {
+  constexpr int ST = PE::STRIDE;
+  double x[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) x[j] = 0.0;
+  int pc = 0, sub = 0, sqleft = 0;
+  bool square = false;
+
+#pragma unroll 1
+  for (;;) {
+    if (sub == 0 && sqleft == 0) {
+      bool done = false;
+#pragma unroll 1
+      for (;;) {   // data-movement instructions up to the next product
+        const uint32_t ins = prog[pc++];
+        const uint32_t op = ins & 0xffu, arg = ins >> 8;
+        if (op == PO_MUL) { square = false; break; }
+        if (op == PO_SQR) { square = true; sqleft = (int)arg; break; }
+        if (op == PO_END) { done = true; break; }
+        if (op == PO_LOADC) {
+          limbs_from_words<L, 1, PE>(x, c_w + arg * chunk_words, chunk_words);
+          col_store<L, PE>(sm.xs0, x);
+#pragma unroll
+          for (int j = 0; j < L; ++j) sm.x1[j * ST] = 0.0;
+        } else if (op == PO_YCONST) {
+          const double* src = cst + (size_t)arg * 2 * L;
+#pragma unroll
+          for (int j = 0; j < L; ++j) { sm.y0[j * ST] = src[j]; sm.y1[j * ST] = src[L + j]; }
+        } else if (op == PO_YT) {
+          const double* src = tbl + (size_t)arg * 2 * L * ST;
+          col_copy<L, PE>(sm.y0, src);
+          col_copy<L, PE>(sm.y1, src + L * ST);
+        } else if (op == PO_YX) {
+          col_copy<L, PE>(sm.y0, sm.xs0);
+          col_copy<L, PE>(sm.y1, sm.x1);
+        } else if (op == PO_XT) {
+          const double* src = tbl + (size_t)arg * 2 * L * ST;
+          col_load<L, PE>(x, src);
+          col_store<L, PE>(sm.xs0, x);
+          col_copy<L, PE>(sm.x1, src + L * ST);
+        } else if (op == PO_TX) {
+          double* dst = tbl + (size_t)arg * 2 * L * ST;
+          col_store<L, PE>(dst, x);
+          col_copy<L, PE>(dst + L * ST, sm.x1);
+        } else if (op == PO_SUM4) {   // X = slot 0 + slot 1 + slot 2 + slot 3 (each part < 2x: sums < 8x < R)
+#pragma unroll 1
+          for (int part = 0; part < 2; ++part) {
+            uint64_t t[L];
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+              uint64_t v = 0;
+#pragma unroll
+              for (int sidx = 0; sidx < 4; ++sidx) v += int_of(tbl[((size_t)(sidx * 2 + part) * L + j) * ST]);
+              t[j] = v;
+            }
+            ripple<L>(t, 0u);
+            if (part == 0) { limbs_of<L>(x, t); col_store<L, PE>(sm.xs0, x); }
+            else {
+#pragma unroll
+              for (int j = 0; j < L; ++j) sm.x1[j * ST] = limb_of(t[j]);
+            }
+          }
+        } else if (op == PO_FINISH) {
+          // X = (w, z1) = c^(x-1) itself (out of the Montgomery domain), parts < 2x.  Canonical digits v0, v1;
+          // L = (c^(x-1) - 1) div x = v1 - [v0 == 0]   (v0 == 1 for every unit c; floor semantics otherwise)
+          uint64_t v0[L], v1[L], xi[L], one[L];
+          ints_of<L>(v0, x);
+#pragma unroll
+          for (int j = 0; j < L; ++j) { v1[j] = int_of(sm.x1[j * ST]); xi[j] = int_of(n[j]); one[j] = (j == 0) ? 1ull : 0ull; }
+          {
+            uint64_t d[L];
+#pragma unroll
+            for (int j = 0; j < L; ++j) d[j] = v0[j];
+            if (!sub_exact<L, 1, PE>(d, xi)) {   // w >= x: v0 = w - x, carry one x into the second digit
+#pragma unroll
+              for (int j = 0; j < L; ++j) v0[j] = d[j];
+              add_exact<L, 1, PE>(v1, one);
+            }
+          }
+          cond_sub<L, 1, PE>(v1, xi);
+          cond_sub<L, 1, PE>(v1, xi);
+          uint64_t nz = 0;
+#pragma unroll
+          for (int j = 0; j < L; ++j) nz |= v0[j];
+          if (nz == 0) {                         // v1 - 1 mod x
+            if (sub_exact<L, 1, PE>(v1, one)) add_exact<L, 1, PE>(v1, xi);
+          }
+          limbs_of<L>(x, v1);
+          col_store<L, PE>(sm.xs0, x);
+#pragma unroll
+          for (int j = 0; j < L; ++j) sm.x1[j * ST] = 0.0;
+        } else if (op == PO_OUT) {
+          uint64_t v[L], xi[L];
+          ints_of<L>(v, x);
+#pragma unroll
+          for (int j = 0; j < L; ++j) xi[j] = int_of(n[j]);
+          cond_sub<L, 1, PE>(v, xi);
+          uint64_t* st = reinterpret_cast<uint64_t*>(sm.e);
+#pragma unroll
+          for (int j = 0; j < L; ++j) st[j * ST] = v[j];
+          if (out_w) {
+            for (int w = 0; w < out_words; ++w) {
+              const int bit = w * 32, g = bit / LW, o = bit - g * LW;
+              uint64_t u = (g < L) ? st[g * ST] >> o : 0ull;
+              if (o > LW - 32 && g + 1 < L) u |= st[(g + 1) * ST] << (LW - o);
+              out_w[w] = (uint32_t)u;
+            }
+          }
+        }
+      }
+      if (done) break;
+    }
+
+    const double *b, *a2 = nullptr, *b2 = nullptr;
+    const int64_t* ein = nullptr;
+    int64_t* eout = nullptr;
+    double* rout;
+    if (sub == 0) {
+      b = square ? sm.xs0 : sm.y0;
+      eout = sm.e;
+      rout = sm.xs0;
+    } else {
+      ein = sm.e;
+      rout = sm.x1;
+      if (square) {                    // a = 2 X0 (exact limbs again), b = X1
+        uint64_t t[L];
+        ints_of<L>(t, x);
+#pragma unroll
+        for (int j = 0; j < L; ++j) t[j] <<= 1;
+        ripple<L>(t, 0u);
+        limbs_of<L>(x, t);
+        b = sm.x1;
+      } else {
+        b = sm.y1; a2 = sm.x1; b2 = sm.y0;
+      }
+    }
+
+    pair_pass<L, PE>(rout, x, b, a2, b2, ein, eout, n, dcon, n0inv);
+
+    if (sub == 0) {
+      sub = 1;
+    } else {
+      sub = 0;
+      col_load<L, PE>(x, sm.xs0);      // X0 = Z0
+      if (square) --sqleft;
+    }
+  }
+}
+
 }  // namespace phe

@@ -19,6 +19,7 @@
 using hbn::BN;
 
 namespace phe {
+extern const PairOps g_pair_10, g_pair_20, g_pair_30;
 extern const ShapeOps g_ops_20_1, g_ops_20_2, g_ops_20_4, g_ops_20_8, g_ops_15_4, g_ops_15_8;
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -84,6 +85,11 @@ static bool timing_read(int kind, double* ms, unsigned long long* n) {
 const ShapeOps* shape_ops(int L, int TPI) {
   const ShapeOps* all[] = {&g_ops_20_1, &g_ops_20_2, &g_ops_20_4, &g_ops_20_8, &g_ops_15_4, &g_ops_15_8};
   for (auto* o : all) if (o->L == L && o->TPI == TPI) return o;
+  return nullptr;
+}
+const PairOps* pair_ops(int L) {
+  const PairOps* all[] = {&g_pair_10, &g_pair_20, &g_pair_30};
+  for (auto* o : all) if (o->L == L) return o;
   return nullptr;
 }
 }  // namespace phe
@@ -228,6 +234,77 @@ std::vector<uint32_t> build_powm_program(const BN& e) {
   return prog;
 }
 
+// ---- p-adic pair engine (decrypt halves): constants and program -------------------------------------------------
+// L limbs of 52 bits as doubles
+void to_limbs52(const BN& v, int L, double* out) {
+  for (int g = 0; g < L; ++g) {
+    const size_t bit = (size_t)g * 52, wi = bit >> 5, sh = bit & 31;
+    unsigned __int128 three = 0;
+    for (int k = 0; k < 3; ++k)
+      if (wi + k < v.w.size()) three |= (unsigned __int128)v.w[wi + k] << (32 * k);
+    out[g] = (double)((uint64_t)(three >> sh) & M52);
+  }
+  if (v.bits() > (size_t)L * 52) throw std::runtime_error("to_limbs52: value exceeds L limbs");
+}
+
+struct PairBlock {
+  int L = 0;
+  uint64_t n0inv = 0;
+  std::vector<double> mod;       // [L] x, [L + 1] D
+  std::vector<double> cst;       // [PC_COUNT][2][L]
+  std::vector<uint32_t> prog;
+};
+
+// x: p or q (bits == chunk_bits), hx = h_x, chunk_bits = key bits / 2.  Returns false if no pair shape fits.
+bool build_pair_block(const BN& x, const BN& hx, int chunk_bits, PairBlock* out) {
+  int L = 0;
+  for (int cand : {10, 20, 30}) if ((size_t)cand * 52 >= x.bits() + 8 && pair_ops(cand)) { L = cand; break; }
+  if (!L || (int)x.bits() != chunk_bits) return false;
+  out->L = L;
+  out->n0inv = neg_inv52(x);
+  const BN R = hbn::shl(BN(1), 52 * (size_t)L);
+  const BN x2 = hbn::mul(x, x);
+  // D = ceil(R / x) * x: a multiple of x that is >= R > every Montgomery quotient
+  BN k = hbn::div(hbn::add(R, hbn::sub(x, BN(1))), x);
+  const BN D = hbn::mul(k, x);
+  out->mod.assign(2 * (size_t)L + 1, 0.0);
+  to_limbs52(x, L, out->mod.data());
+  to_limbs52(D, L + 1, out->mod.data() + L);
+  out->cst.assign((size_t)PC_COUNT * 2 * L, 0.0);
+  auto put_pair = [&](int idx, const BN& v0, const BN& v1) {
+    to_limbs52(v0, L, &out->cst[((size_t)idx * 2 + 0) * L]);
+    to_limbs52(v1, L, &out->cst[((size_t)idx * 2 + 1) * L]);
+  };
+  const BN R2 = hbn::mod(hbn::mul(R, R), x2);
+  for (int c = 0; c < 4; ++c) {   // W_c ~ 2^(c chunk_bits) R^2 mod x^2 as p-adic digits
+    const BN w = hbn::mulmod(hbn::mod(hbn::shl(BN(1), (size_t)c * chunk_bits), x2), R2, x2);
+    BN q, r;
+    hbn::divmod(w, x, &q, &r);
+    put_pair(PC_W0 + c, r, q);
+  }
+  put_pair(PC_ONE, BN(1), BN());
+  put_pair(PC_HR, hbn::mulmod(hx, hbn::mod(R, x), x), BN());
+  // program
+  auto ins = [](uint32_t op, uint32_t arg) { return op | (arg << 8); };
+  std::vector<uint32_t>& P = out->prog;
+  P.clear();
+  for (int c = 3; c >= 0; --c) { P.push_back(ins(PO_LOADC, c)); P.push_back(ins(PO_YCONST, PC_W0 + c)); P.push_back(ins(PO_MUL, 0)); P.push_back(ins(PO_TX, c)); }
+  P.push_back(ins(PO_SUM4, 0));
+  const std::vector<uint32_t> sw = build_powm_program(hbn::sub(x, BN(1)));
+  constexpr int TS = 1 << (PROG_WS - 1);
+  P.push_back(ins(PO_TX, 0)); P.push_back(ins(PO_YX, 0)); P.push_back(ins(PO_SQR, 1)); P.push_back(ins(PO_YX, 0)); P.push_back(ins(PO_XT, 0));
+  for (int t = 1; t < TS; ++t) { P.push_back(ins(PO_MUL, 0)); P.push_back(ins(PO_TX, t)); }
+  P.push_back(ins(PO_XT, sw[0]));
+  for (size_t i = 1; i < sw.size(); ++i) {
+    const uint32_t sq = sw[i] >> 8, idx = sw[i] & 0xffu;
+    if (sq) P.push_back(ins(PO_SQR, sq));
+    if (idx != PROG_NOMUL) { P.push_back(ins(PO_YT, idx)); P.push_back(ins(PO_MUL, 0)); }
+  }
+  P.push_back(ins(PO_YCONST, PC_ONE)); P.push_back(ins(PO_MUL, 0)); P.push_back(ins(PO_FINISH, 0));
+  P.push_back(ins(PO_YCONST, PC_HR)); P.push_back(ins(PO_MUL, 0)); P.push_back(ins(PO_OUT, 0)); P.push_back(ins(PO_END, 0));
+  return true;
+}
+
 int window_for_bits(int ebits) { return ebits <= 8 ? 1 : (ebits <= 160 ? 3 : 5); }
 
 }  // namespace
@@ -255,6 +332,10 @@ struct phe_privkey {
   BN p, q;
   const ShapeOps* ops = nullptr;  // shape of the x^2 contexts (also used for p, q, n in the tail)
   mutable DevBuf d_ctx[2], d_exp[2], d_prog[2], d_tail;
+  // p-adic pair engine (balanced keys): per x = p, q
+  bool use_pair = false;
+  PairBlock pairb[2];
+  mutable DevBuf d_pair_mod[2], d_pair_cst[2], d_pair_prog[2];
   mutable MontCtxArgs ctx[2]{};
   int ebits[2] = {0, 0};
   int hw = 0;  // words of x^2 (= n_words)
@@ -328,6 +409,18 @@ int sk_ensure_device(const phe_privkey* sk) {
     PHE_TRY(upload(sk->d_prog[y], sk->h_prog[y]));
   }
   PHE_TRY(upload(sk->d_tail, sk->h_tail));
+  if (sk->use_pair) {
+    for (int y = 0; y < 2; ++y) {
+      const PairBlock& b = sk->pairb[y];
+      std::vector<uint32_t> tmp(b.mod.size() * 2);
+      std::memcpy(tmp.data(), b.mod.data(), b.mod.size() * 8);
+      PHE_TRY(upload(sk->d_pair_mod[y], tmp));
+      tmp.assign(b.cst.size() * 2, 0);
+      std::memcpy(tmp.data(), b.cst.data(), b.cst.size() * 8);
+      PHE_TRY(upload(sk->d_pair_cst[y], tmp));
+      PHE_TRY(upload(sk->d_pair_prog[y], b.prog));
+    }
+  }
   sk->dev_ready = true;
   return 0;
 }
@@ -472,7 +565,38 @@ int mul_dev_impl(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uin
   return 0;
 }
 
+// decrypt = two CRT halves m_p, m_q on the pair engine (one lane each) + recombination
+int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m, cudaStream_t s) {
+  const ShapeOps* o = sk->ops;
+  const PairOps* po = pair_ops(sk->pairb[0].L);
+  const int hw = sk->hw, cw = 2 * hw, half = hw / 2;
+  const size_t chunk = std::min(count, CHUNK);
+  constexpr int slots = 1 << (PROG_WS - 1);
+  for (int y = 0; y < 2; ++y) PHE_TRY(sk->ws_u[y].ensure(chunk * half));
+  PHE_TRY(sk->ws_tbl.ensure(po->tbl_words((int)chunk, slots)));
+  for (size_t off = 0; off < count; off += CHUNK) {
+    const int c = (int)std::min(CHUNK, count - off);
+    DecPairArgs a{};
+    a.c_w = d_ct + off * cw; a.c_words = cw; a.chunk_words = half; a.out_words = half; a.count = c; a.slots = slots;
+    for (int y = 0; y < 2; ++y) {
+      a.prog[y] = sk->d_pair_prog[y].p; a.out_w[y] = sk->ws_u[y].p;
+      a.mod[y] = reinterpret_cast<const double*>(sk->d_pair_mod[y].p);
+      a.cst[y] = reinterpret_cast<const double*>(sk->d_pair_cst[y].p);
+      a.n0inv[y] = sk->pairb[y].n0inv;
+    }
+    a.tbl = reinterpret_cast<double*>(sk->ws_tbl.p);
+    CUDA_TRY(po->dec_pair(a, s));
+    DecCrtArgs t{};
+    t.mp_w = sk->ws_u[0].p; t.mq_w = sk->ws_u[1].p; t.half_words = half; t.m_w = d_m + off * hw; t.m_words = hw;
+    t.count = c; t.cst = reinterpret_cast<const double*>(sk->d_tail.p);
+    for (int i = 0; i < 3; ++i) t.n0invs[i] = sk->n0invs[i];
+    CUDA_TRY(o->dec_crt(t, s));
+  }
+  return 0;
+}
+
 int decrypt_dev_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m, cudaStream_t s) {
+  if (sk->use_pair) return decrypt_pair_impl(sk, d_ct, count, d_m, s);
   const ShapeOps* o = sk->ops;
   const int hw = sk->hw, cw = 2 * hw;
   const size_t chunk = std::min(count, CHUNK);
@@ -635,6 +759,12 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
     sk->n0invs[0] = neg_inv52(P);
     sk->n0invs[1] = neg_inv52(Q);
     sk->n0invs[2] = neg_inv52(pk->n);
+    {   // balanced keys run the CRT halves on the p-adic pair engine
+      const int chunk_bits = 16 * sk->hw;
+      const char* off = getenv("PHE_NO_PAIR_ENGINE");
+      sk->use_pair = !(off && off[0] == '1') && build_pair_block(P, hx[0], chunk_bits, &sk->pairb[0]) &&
+                     build_pair_block(Q, hx[1], chunk_bits, &sk->pairb[1]) && sk->pairb[0].L == sk->pairb[1].L;
+    }
     *out = sk.release();
     return 0;
   } catch (const std::exception& e) { return fail(std::string("phe_privkey_create: ") + e.what()); }
@@ -642,7 +772,7 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
 
 void phe_privkey_destroy(phe_privkey* sk) {
   if (!sk) return;
-  for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->ws_in, &sk->ws_out,
+  for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->d_pair_mod[0], &sk->d_pair_mod[1], &sk->d_pair_cst[0], &sk->d_pair_cst[1], &sk->d_pair_prog[0], &sk->d_pair_prog[1], &sk->ws_in, &sk->ws_out,
                     &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl}) b->release();
   delete sk;
 }
@@ -921,6 +1051,22 @@ int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, doub
     if (n0inv_out) *n0inv_out = n0;
     return o->KP;
   } catch (const std::exception& e) { fail(e.what()); return -1; }
+}
+
+int phe_privkey_pair_block(const phe_privkey* sk, int y, int* L_out, uint64_t* n0inv_out, double* mod_out,
+                           double* cst_out, uint32_t* prog_out, int prog_cap) {
+  if (!sk || y < 0 || y > 1) { fail("phe_privkey_pair_block: bad arguments"); return -1; }
+  if (!sk->use_pair) return 0;
+  const PairBlock& b = sk->pairb[y];
+  if (L_out) *L_out = b.L;
+  if (n0inv_out) *n0inv_out = b.n0inv;
+  if (mod_out) std::memcpy(mod_out, b.mod.data(), b.mod.size() * 8);
+  if (cst_out) std::memcpy(cst_out, b.cst.data(), b.cst.size() * 8);
+  if (prog_out) {
+    if ((int)b.prog.size() > prog_cap) { fail("phe_privkey_pair_block: program buffer too small"); return -1; }
+    std::memcpy(prog_out, b.prog.data(), b.prog.size() * 4);
+  }
+  return (int)b.prog.size();
 }
 
 int phe_host_powm_program(const uint32_t* e, int e_words, uint32_t* out, int out_cap) {

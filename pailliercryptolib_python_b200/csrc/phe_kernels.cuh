@@ -199,6 +199,78 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
   }
 }
 
+// ---- decrypt on the p-adic pair engine: one (ciphertext, modulus) per lane ---------------------------------------
+struct DecPairArgs {
+  const uint32_t* c_w;       // [count][c_words]
+  int c_words, chunk_words;
+  const uint32_t* prog[2];   // pair-engine programs for x = p, q (paillier_items.cuh: PairOp)
+  uint32_t* out_w[2];        // m_p, m_q: [count][out_words]
+  int out_words;
+  int count;
+  const double* mod[2];      // [L] limbs of x followed by [L + 1] limbs of D = k x >= R
+  uint64_t n0inv[2];
+  const double* cst[2];      // [PC_COUNT][2][L] constant pairs
+  double* tbl;               // [gridDim.y * gridDim.x * NT / 32][slots][2][L][32]
+  int slots;
+};
+
+template <int L> struct PairShape {
+  static constexpr int LE = (L + 2) & ~1;                       // L + 1 entries of E, padded to even
+  static constexpr int PER_LANE = 4 * L + LE;                   // doubles of shared memory per lane
+  static constexpr size_t smem_bytes() { return (size_t)(2 * LE + PER_LANE * NT) * sizeof(double); }
+};
+
+template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(DecPairArgs p) {
+  using PE = DevPairEnv;
+  using PS = PairShape<L>;
+  extern __shared__ __align__(16) double smem[];
+  const int y = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * L + 1; i += NT) smem[i < L ? i : PS::LE + (i - L)] = p.mod[y][i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, col = threadIdx.x & 31;
+  double* wbase = smem + 2 * PS::LE + (size_t)warp * PS::PER_LANE * 32 + col;
+  PairSmem<PE> sm;
+  sm.xs0 = wbase;
+  sm.x1 = wbase + L * 32;
+  sm.y0 = wbase + 2 * L * 32;
+  sm.y1 = wbase + 3 * L * 32;
+  sm.e = reinterpret_cast<int64_t*>(wbase + 4 * L * 32);
+  double* tbl = p.tbl + ((size_t)(y * gridDim.x + blockIdx.x) * (NT / 32) + warp) * ((size_t)p.slots * 2 * L * 32) + col;
+  for (int base = blockIdx.x * NT; base < p.count; base += gridDim.x * NT) {
+    const int want = base + (int)threadIdx.x;
+    const int item = want < p.count ? want : p.count - 1;
+    item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog[y],
+                         want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, smem,
+                         smem + PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+  }
+}
+
+struct DecCrtArgs {
+  const uint32_t* mp_w;
+  const uint32_t* mq_w;
+  int half_words;
+  uint32_t* m_w;
+  int m_words;
+  int count;
+  const double* cst;       // DT_COUNT entries
+  uint64_t n0invs[3];
+};
+
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_dec_crt(DecCrtArgs p) {
+  using Env = DevEnv<TPI>;
+  using KS = KShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<KS::KP>(smem, p.cst, DT_COUNT);
+  GroupSmem sm = group_smem<L, TPI>(smem, DT_COUNT);
+  const int g = threadIdx.x / TPI;
+  for (int base = blockIdx.x * KS::GPB; base < p.count; base += gridDim.x * KS::GPB) {
+    const int want = base + g;
+    const int item = want < p.count ? want : p.count - 1;
+    item_dec_crt<L, TPI, Env>(p.mp_w + (size_t)item * p.half_words, p.mq_w + (size_t)item * p.half_words, p.half_words,
+                              want < p.count ? p.m_w + (size_t)item * p.m_words : nullptr, p.m_words, smem, p.n0invs, sm);
+  }
+}
+
 // ---- DJN encrypt (fixed-base comb) -----------------------------------------------------------------
 struct EncCombArgs {
   const uint32_t* m_w;   // [count][m_words]

@@ -100,6 +100,14 @@ template <int L, int TPI> struct Launch {
     }
     return cudaGetLastError();
   }
+  static cudaError_t dec_crt(const DecCrtArgs& p, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(DT_COUNT);
+    const int grid = grid_for(k_dec_crt<L, TPI>, smem, p.count, KS::GPB, 1);
+    { TimedLaunch tl_(KK_DEC_TAIL, s);
+    k_dec_crt<L, TPI><<<grid, NT, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+  }
   static cudaError_t encrypt_comb(const EncCombArgs& p, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(ME_COUNT);
     const int grid = grid_for(k_encrypt_comb<L, TPI>, smem, p.count, KS::GPB, 1);
@@ -137,9 +145,28 @@ template <int L, int TPI> struct Launch {
   }
 
   static constexpr ShapeOps ops() {
-    return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &powm_prog, &powm_prog_tbl_words, &dec_prep, &dec_tail,
+    return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &powm_prog, &powm_prog_tbl_words, &dec_prep, &dec_tail, &dec_crt,
                     &encrypt_comb, &encrypt_finish, &comb_build};
   }
+};
+
+// Launcher of the one-bignum-per-lane pair engine (L = limbs of p, q).
+template <int L> struct PairLaunch {
+  static int grid(int count) {
+    return grid_for(k_dec_pair<L>, PairShape<L>::smem_bytes(), count, NT, 2);
+  }
+  static cudaError_t dec_pair(const DecPairArgs& p, cudaStream_t s) {
+    const size_t smem = PairShape<L>::smem_bytes();
+    const int g = grid(p.count);
+    { TimedLaunch tl_(KK_POWM, s);
+    k_dec_pair<L><<<dim3(g, 2), NT, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+  }
+  static size_t tbl_words(int count, int slots) {   // u32 words
+    return (size_t)grid(count) * 2 * (NT / 32) * slots * 2 * L * 32 * 2;
+  }
+  static constexpr PairOps ops() { return PairOps{L, &dec_pair, &tbl_words}; }
 };
 
 }  // namespace phe

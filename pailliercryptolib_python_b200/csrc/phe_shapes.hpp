@@ -15,6 +15,8 @@ struct DecTailArgs;
 struct EncCombArgs;
 struct EncFinishArgs;
 struct CombArgs;
+struct DecPairArgs;
+struct DecCrtArgs;
 
 struct ShapeOps {
   int L, TPI, KP, GPB;   // KP: doubles per padded entry
@@ -28,12 +30,21 @@ struct ShapeOps {
   size_t (*powm_prog_tbl_words)(int ny, int count);
   cudaError_t (*dec_prep)(const DecPrepArgs& p, cudaStream_t s);
   cudaError_t (*dec_tail)(const DecTailArgs& p, cudaStream_t s);
+  cudaError_t (*dec_crt)(const DecCrtArgs& p, cudaStream_t s);
   cudaError_t (*encrypt_comb)(const EncCombArgs& p, cudaStream_t s);
   cudaError_t (*encrypt_finish)(const EncFinishArgs& p, cudaStream_t s);
   cudaError_t (*comb_build)(const CombArgs& p, cudaStream_t s);
 };
 
 const ShapeOps* shape_ops(int L, int TPI);   // nullptr if not built
+
+// p-adic pair engine (decrypt halves, one bignum of L limbs per lane)
+struct PairOps {
+  int L;
+  cudaError_t (*dec_pair)(const DecPairArgs& p, cudaStream_t s);
+  size_t (*tbl_words)(int count, int slots);   // table scratch (u32 words) for a launch
+};
+const PairOps* pair_ops(int L);   // nullptr if not built
 unsigned long long launch_counter();          // kernels launched by this library so far
 void count_launch();
 

@@ -222,6 +222,49 @@ int do_dec_tail(const uint32_t* up, const uint32_t* uq, int u_words, uint32_t* m
   return 0;
 }
 
+// one-bignum-per-lane environment of the p-adic pair engine: a single column (stride 1)
+struct EmuPairEnv {
+  static constexpr int STRIDE = 1;
+  static int lane() { return 0; }
+  static int column() { return 0; }
+  static uint32_t bcast(uint32_t v, int) { return v; }
+  static uint32_t from_above(uint32_t) { return 0u; }
+  static uint32_t from_below(uint32_t) { return 0u; }
+  static bool any(bool p) { return p; }
+  static void sync() {}
+};
+
+template <int L>
+int do_dec_pair(const uint32_t* c, int c_words, int chunk_words, const uint32_t* prog, uint32_t* out, int out_words,
+                int count, const double* mod, uint64_t n0inv, const double* cst, int slots) {
+  std::fesetround(FE_TOWARDZERO);
+  for (int i = 0; i < count; ++i) {
+    std::vector<double> xs0(L), x1(L), y0(L), y1(L), tbl((size_t)slots * 2 * L);
+    std::vector<int64_t> e(L + 1);
+    phe::PairSmem<EmuPairEnv> sm{xs0.data(), x1.data(), y0.data(), y1.data(), e.data()};
+    phe::item_dec_pair<L, EmuPairEnv>(c + (size_t)i * c_words, chunk_words, prog, out + (size_t)i * out_words, out_words,
+                                      mod, mod + L, n0inv, cst, tbl.data(), sm);
+  }
+  std::fesetround(FE_TONEAREST);
+  return 0;
+}
+
+template <int L, int TPI>
+int do_dec_crt(const uint32_t* mp, const uint32_t* mq, int half_words, uint32_t* m, int m_words, int count,
+               const double* cst, const uint64_t* n0invs) {
+  using Env = EmuEnv<TPI>;
+  constexpr int KP = phe::Shape<L, TPI>::KP;
+  AlignedCopy c(cst, (size_t)phe::DT_COUNT * KP);
+  for (int i = 0; i < count; ++i) {
+    Bufs<L, TPI> bufs;
+    run_group<TPI>([&] {
+      phe::item_dec_crt<L, TPI, Env>(mp + (size_t)i * half_words, mq + (size_t)i * half_words, half_words,
+                                     m + (size_t)i * m_words, m_words, c.p, n0invs, bufs.sm);
+    });
+  }
+  return 0;
+}
+
 }  // namespace
 
 #define DISPATCH_SHAPE(CALL)                       \
@@ -273,6 +316,19 @@ int emu_encrypt_comb(int shape, const uint32_t* m, int m_words, const uint32_t* 
 int emu_encrypt_finish(int shape, const uint32_t* m, int m_words, const uint32_t* obf, uint32_t* out, int out_words,
                        int count, const double* n_e, uint64_t n0inv, const double* nR_e, const double* r2_e) {
   DISPATCH_SHAPE((do_encrypt_finish<L, TPI>(m, m_words, obf, out, out_words, count, n_e, n0inv, nR_e, r2_e)));
+}
+
+int emu_dec_pair(int L, const uint32_t* c, int c_words, int chunk_words, const uint32_t* prog, uint32_t* out,
+                 int out_words, int count, const double* mod, uint64_t n0inv, const double* cst, int slots) {
+  if (L == 10) return do_dec_pair<10>(c, c_words, chunk_words, prog, out, out_words, count, mod, n0inv, cst, slots);
+  if (L == 20) return do_dec_pair<20>(c, c_words, chunk_words, prog, out, out_words, count, mod, n0inv, cst, slots);
+  if (L == 30) return do_dec_pair<30>(c, c_words, chunk_words, prog, out, out_words, count, mod, n0inv, cst, slots);
+  return -1;
+}
+
+int emu_dec_crt(int shape, const uint32_t* mp, const uint32_t* mq, int half_words, uint32_t* m, int m_words, int count,
+                const double* cst, const uint64_t* n0invs) {
+  DISPATCH_SHAPE((do_dec_crt<L, TPI>(mp, mq, half_words, m, m_words, count, cst, n0invs)));
 }
 
 int emu_dec_tail(int shape, const uint32_t* up, const uint32_t* uq, int u_words, uint32_t* m, int m_words, int count,

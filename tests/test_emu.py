@@ -193,3 +193,49 @@ def test_encrypt_finish_classic(emu):
                                 U64(mc["n0inv"]), PD(nR), PD(mc["r2"]))
     assert rc == 0
     assert from_words(out) == O.encrypt_batch(pk, ms, rs)
+
+
+@pytest.mark.parametrize("bits,L,shape", [(1024, 10, (20, 1)), (2048, 20, (20, 2)), (3072, 30, (15, 4))])
+def test_decrypt_pair_engine(emu, bits, L, shape):
+    """p-adic pair engine: item_dec_pair (m_p, m_q) + item_dec_crt == oracle decrypt, with the constants and the
+    program exactly as the C ABI builds them for the private key (host code, no GPU)."""
+    from pailliercryptolib_python_b200 import capi
+    pk, sk = O.bench_keypair() if bits == 2048 else O.seeded_keypair(bits, 11)
+    cpk = capi.PubKey(pk.n, bits, djn=True, hs=pk.hs)
+    csk = capi.PrivKey(cpk, sk.p, sk.q)
+    rng = random.Random(bits + 5)
+    ms = [0, 1, pk.n - 1] + [rng.randrange(pk.n) for _ in range(3)]
+    cs = [O.encrypt(pk, m, rng.getrandbits(bits // 2)) for m in ms]
+    cs += [rng.randrange(1, pk.nsquare) for _ in range(2)] + [0, sk.p, sk.p * sk.q, pk.nsquare - 1]   # units and non-units
+    cw = to_words(cs, bits // 16)
+    hw, half = bits // 32, bits // 64
+    halves = []
+    for y, x in enumerate((sk.p, sk.q)):
+        Lc, n0 = ctypes.c_int(), ctypes.c_uint64()
+        mod = np.zeros(2 * L + 1, dtype=np.float64)
+        cst = np.zeros(6 * 2 * L, dtype=np.float64)
+        prog = np.zeros(4096, dtype=np.uint32)
+        n = capi.lib().phe_privkey_pair_block(csk.h, y, ctypes.byref(Lc), ctypes.byref(n0), PD(mod), PD(cst), P(prog), len(prog))
+        assert n > 0 and Lc.value == L
+        # the constants are what the header says they are
+        R = 1 << (52 * L)
+        limbs = lambda a: sum(int(v) << (52 * i) for i, v in enumerate(a))
+        assert limbs(mod[:L]) == x and limbs(mod[L:]) == -(-R // x) * x and n0.value == (-pow(x, -1, 1 << 52)) % (1 << 52)
+        for k in range(4):
+            w = (1 << (k * bits // 2)) * R * R % (x * x)
+            assert (limbs(cst[(2 * k) * L:(2 * k + 1) * L]), limbs(cst[(2 * k + 1) * L:(2 * k + 2) * L])) == (w % x, w // x)
+        out = np.zeros((len(cs), half), dtype=np.uint32)
+        rc = emu.emu_dec_pair(L, P(cw), bits // 16, half, P(prog), P(out), half, len(cs), PD(mod), U64(n0.value), PD(cst), 32)
+        assert rc == 0
+        hx = sk.hp if y == 0 else sk.hq
+        want = []
+        for c in cs:
+            u = pow(c % (x * x), x - 1, x * x)
+            want.append(((u - 1) // x) * hx % x)
+        assert from_words(out) == want
+        halves.append(out)
+    cst, n0 = _dec_consts(sk, *shape)
+    mo = np.zeros((len(cs), hw), dtype=np.uint32)
+    assert emu.emu_dec_crt(shape_id(*shape), P(halves[0]), P(halves[1]), half, P(mo), hw, len(cs), PD(cst), P64(n0)) == 0
+    assert from_words(mo) == O.decrypt_batch(sk, cs)
+    assert from_words(mo)[:len(ms)] == ms
