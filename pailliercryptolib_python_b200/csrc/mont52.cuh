@@ -304,47 +304,39 @@ PHE_HD void montmul(double (&r)[L], const double (&a)[L], const double* b, const
 // X0, X1 < 2x, meaning (X0 + X1 x) R^-1 mod x^2 with R = 2^(52 L) >= 2^8 x.  With  X0 Y0 = u R - m x  (u, m the
 // result and the quotient of an ordinary Montgomery reduction mod x) one gets
 //     (X0 + X1 x)(Y0 + Y1 x) R^-1  =  u + (X0 Y1 + X1 Y0 - m) R^-1 x   (mod x^2)
-// so a product mod x^2 costs 5 L^2 limb products (3 multiplications + 2 reductions of L limbs) and a square 4 L^2,
+// so a product mod x^2 costs 6 L^2 limb products (3 multiplications + 3 reductions of L limbs) and a square 4 L^2,
 // against 8 L^2 for one Montgomery product of 2L limbs -- and everything fits ONE lane (L = 20 at 2048-bit keys):
 // no shuffles, 32 ciphertexts per warp.  The L function comes for free: c^(x-1) = 1 + L x.
 //
-// pair_pass is one reduction:  r = (a b [+ a2 b2] + E + m x) / R  with E = sum_i e_in[i] 2^(52 i) a (signed) column
-// addend.  Pass 1 of a product (b = Y0) records e_out[i] = D_i - q_i, D = k x >= R, which pass 2 (b = Y1, a2 = X1,
-// b2 = Y0) takes as e_in: that is the "- m" term made non-negative.  Operands other than `a` are read from, and the
-// result written to, (shared) memory with a stride of PE::STRIDE doubles between limbs (one column per lane); n and
-// dcon (L + 1 limbs of D) are shared by all lanes.  Result: exact limbs, value < 2x.  r_out may alias b.
+// pair_pass is one reduction:  r = (a b + E + m x) / R  with E = sum_i e_in[i] 2^(52 i) a (signed) column addend.
+// Pass 1 of a product (a = X0, b = Y0) records e_out[i] = D_i - q_i, D = k x >= R; pass 2 (a = X0, b = Y1) takes it as
+// e_in: that is the "- m" term made non-negative; a third pass (a = X1, b = Y0) gives the other cross term and the two
+// are added (a square needs only pass 2 with a = 2 X0, b = X1).  One code body serves every pass: a fused
+// two-multiplicand pass saves one reduction per multiplication but needs a second, 26 KB loop body that evicts the hot
+// one from the 32 KB instruction cache (measured: no_instruction 0.64 stalled warps per issue).  b is read from, and
+// the result written to, (shared) memory with a stride of PE::STRIDE doubles between limbs (one column per lane); n
+// and dcon (L + 1 limbs of D) are shared by all lanes.  Result: exact limbs, value < 2x.  r_out may alias b.
 // ------------------------------------------------------------------------------------------------
-template <class PE> struct Strided {
-  const double* p;
-  PHE_HD double operator[](int i) const { return p[i * PE::STRIDE]; }
-};
-
 template <int L, class PE>
-PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, const double* a2, const double* b2,
-                      const int64_t* e_in, int64_t* e_out, const double* n, const double* dcon, uint64_t n0inv) {
+PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, const int64_t* e_in, int64_t* e_out,
+                      const double* n, const double* dcon, uint64_t n0inv) {
   constexpr int U = Unroll<L>::U;
   constexpr int ST = PE::STRIDE;
-  const uint32_t S = a2 ? 3u : 2u;   // product sets per row: A-part(s) + N-part
-  // bias bookkeeping as in montmul, scaled by the run-time number of sets (all biases are multiples of 2^52)
-  const uint64_t INIT = 0ull - (uint64_t)S * bias_of(L, L);
+  constexpr uint64_t INIT = 0ull - bias_of(2 * L, 2 * L);
   uint64_t acc[L];
 #pragma unroll
-  for (int j = 0; j < L; ++j) acc[j] = 0ull - (uint64_t)S * bias_of(j + 1, j);
-  const Strided<PE> a2s{a2};
+  for (int j = 0; j < L; ++j) acc[j] = 0ull - bias_of(2 * (j + 1), 2 * j);
 
   uint64_t topA, q;
   double qd;
-  {  // prologue: A-part(s) of row 0 and the quotient digit
+  {  // prologue: A-part of row 0 and the quotient digit
     const double b0 = b[0];
-    uint64_t h, h2 = 0;
-    double b20 = 0.0;
+    uint64_t h;
     mac_first(acc[0], a[0], b0, h);
-    if (a2) { b20 = b2[0]; mac_first(acc[0], a2[0], b20, h2); }
     if (e_in) acc[0] += (uint64_t)e_in[0];
     q = (acc[0] * n0inv) & M52;
     mac_span<L, 1, L>(acc, a, b0, h, 0);
     topA = h;
-    if (a2) { mac_span<L, 1, L>(acc, a2s, b20, h2, 0); topA += h2; }
     qd = limb_of(q);
   }
 #pragma unroll 1
@@ -354,7 +346,7 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
       const int row = row0 + u;
       const bool last = (u == U - 1) && (row == L - 1);
       if (e_out) e_out[row * ST] = (int64_t)int_of(dcon[row]) - (int64_t)q;   // D_i - q_i
-      uint64_t hN, hA = 0, hA2 = 0;
+      uint64_t hN, hA = 0;
       const double n0 = n[0], n1 = n[1];
       mac_first(acc[u % L], n0, qd, hN);
       {
@@ -365,11 +357,10 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
         hN = d2u(ph);
         acc[u % L] = 0;                                    // becomes the new top column (column L of row i)
       }
-      double bn = 0.0, b2n = 0.0;
+      double bn = 0.0;
       if (!last) {
         bn = b[(row + 1) * ST];
         mac_first(acc[(u + 1) % L], a[0], bn, hA);
-        if (a2) { b2n = b2[(row + 1) * ST]; mac_first(acc[(u + 1) % L], a2[0], b2n, hA2); }
         if (e_in) acc[(u + 1) % L] += (uint64_t)e_in[(row + 1) * ST];
         q = (acc[(u + 1) % L] * n0inv) & M52;
       }
@@ -378,7 +369,6 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
       if (!last) {
         mac_span<L, 1, L>(acc, a, bn, hA, u + 1);
         topA = hA;
-        if (a2) { mac_span<L, 1, L>(acc, a2s, b2n, hA2, u + 1); topA += hA2; }
         qd = limb_of(q);
       }
     }
@@ -391,7 +381,7 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
     }
   }
 #pragma unroll
-  for (int j = 0; j < L; ++j) acc[j] += (uint64_t)S * bias_of(j + 1, j);
+  for (int j = 0; j < L; ++j) acc[j] += bias_of(2 * (j + 1), 2 * j);
   if (e_out) e_out[L * ST] = (int64_t)int_of(dcon[L]);
   if (e_in) acc[0] += (uint64_t)e_in[L * ST];            // top limb of D
   int64_t c = 0;                                            // signed ripple: single columns may be negative, the

@@ -542,7 +542,7 @@ PHE_HD void item_dec_crt(const uint32_t* mp_w, const uint32_t* mq_w, int half_wo
 //     multiply by (1, 0) to leave the Montgomery domain: c^(x-1) = v0 + v1 x with v0 = 1, so L_x = v1 - [v0 = 0];
 //     multiply by (h_x R, 0); write the canonical result.
 // State per lane: X0 in registers; XS0 (copy of X0), X1, Y0, Y1, E in shared memory (columns, stride PE::STRIDE);
-// table slots in global memory (same column layout).  A product is two pair_pass calls through ONE call site.
+// table slots in global memory (same column layout).  A product is two or three pair_pass calls through ONE call site.
 // ------------------------------------------------------------------------------------------------
 enum PairOp : uint32_t {
   PO_END = 0, PO_LOADC, PO_YCONST, PO_YT, PO_YX, PO_XT, PO_TX, PO_MUL, PO_SQR, PO_SUM4, PO_FINISH, PO_OUT
@@ -633,7 +633,7 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
             }
           }
         } else if (op == PO_FINISH) {
-          // X = (w, z1) = c^(x-1) itself (out of the Montgomery domain), parts < 2x.  Canonical digits v0, v1;
+          // X = (w, z1) = c^(x-1) itself (out of the Montgomery domain), w < 2x, z1 < 4x.  Canonical digits v0, v1;
           // L = (c^(x-1) - 1) div x = v1 - [v0 == 0]   (v0 == 1 for every unit c; floor semantics otherwise)
           uint64_t v0[L], v1[L], xi[L], one[L];
           ints_of<L>(v0, x);
@@ -649,8 +649,8 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
               add_exact<L, 1, PE>(v1, one);
             }
           }
-          cond_sub<L, 1, PE>(v1, xi);
-          cond_sub<L, 1, PE>(v1, xi);
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) cond_sub<L, 1, PE>(v1, xi);   // second digit < 4x + 1
           uint64_t nz = 0;
 #pragma unroll
           for (int j = 0; j < L; ++j) nz |= v0[j];
@@ -683,7 +683,11 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
       if (done) break;
     }
 
-    const double *b, *a2 = nullptr, *b2 = nullptr;
+    // a product is two (square) or three (multiplication) passes through the one pair_pass call site:
+    //   sub 0: a = X0, b = X0 | Y0        -> Z0 (to XS0), E
+    //   sub 1: a = 2 X0 | X0, b = X1 | Y1, E -> Z1 (square: to X1; multiplication: first cross term, parked in E)
+    //   sub 2 (multiplication): a = X1, b = Y0 -> second cross term (to X1); Z1 = sum of the two (Y is left intact)
+    const double* b;
     const int64_t* ein = nullptr;
     int64_t* eout = nullptr;
     double* rout;
@@ -691,9 +695,8 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
       b = square ? sm.xs0 : sm.y0;
       eout = sm.e;
       rout = sm.xs0;
-    } else {
+    } else if (sub == 1) {
       ein = sm.e;
-      rout = sm.x1;
       if (square) {                    // a = 2 X0 (exact limbs again), b = X1
         uint64_t t[L];
         ints_of<L>(t, x);
@@ -702,16 +705,32 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
         ripple<L>(t, 0u);
         limbs_of<L>(x, t);
         b = sm.x1;
+        rout = sm.x1;
       } else {
-        b = sm.y1; a2 = sm.x1; b2 = sm.y0;
+        b = sm.y1;
+        rout = reinterpret_cast<double*>(sm.e);   // E is consumed by this very pass: park the first cross term there
       }
+    } else {
+      col_load<L, PE>(x, sm.x1);
+      b = sm.y0;
+      rout = sm.x1;
     }
 
-    pair_pass<L, PE>(rout, x, b, a2, b2, ein, eout, n, dcon, n0inv);
+    pair_pass<L, PE>(rout, x, b, ein, eout, n, dcon, n0inv);
 
     if (sub == 0) {
       sub = 1;
+    } else if (sub == 1 && !square) {
+      sub = 2;
     } else {
+      if (!square) {                   // Z1 = (X0 Y1 - m) R^-1 + X1 Y0 R^-1, < 4x, exact limbs
+        uint64_t t[L];
+#pragma unroll
+        for (int j = 0; j < L; ++j) t[j] = int_of(sm.x1[j * ST]) + int_of(reinterpret_cast<const double*>(sm.e)[j * ST]);
+        ripple<L>(t, 0u);
+#pragma unroll
+        for (int j = 0; j < L; ++j) sm.x1[j * ST] = limb_of(t[j]);
+      }
       sub = 0;
       col_load<L, PE>(x, sm.xs0);      // X0 = Z0
       if (square) --sqleft;
