@@ -41,7 +41,7 @@ unsigned long long phe_kernel_launches(void);
 /* Measurement hooks (bench.py): with timing enabled every kernel launch is bracketed by a cudaEvent pair on
  * the stream it is launched on; phe_timing_read waits for the recorded events and returns the summed device
  * time and launch count of one kernel kind since the last phe_timing_enable.  Kinds: 0 k_modmul, 1 k_powm,
- * 2 k_dec_prep, 3 k_dec_tail, 4 k_encrypt_comb, 5 k_encrypt_finish, 6 k_comb_build. */
+ * 2 k_dec_prep, 3 k_dec_tail, 4 k_encrypt_comb, 5 k_encrypt_finish, 6 k_comb_build, 7 k_dec_pair, 8 k_dec_crt. */
 int phe_timing_enable(int on);
 int phe_timing_read(int kind, double* ms_total, unsigned long long* launches);
 const char* phe_timing_kind_name(int kind);
@@ -86,8 +86,8 @@ int phe_pubkey_get_hs(const phe_pubkey* pk, uint32_t* hs_out);          /* 2*n_w
 int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, const uint32_t* q, int q_words,
                        phe_privkey** out);
 void phe_privkey_destroy(phe_privkey* sk);
-int phe_privkey_get_p(const phe_privkey* sk, uint32_t* p_out);  /* n_words/2 words (PrivateKey::getP) */
-int phe_privkey_get_q(const phe_privkey* sk, uint32_t* q_out);  /* n_words/2 words (PrivateKey::getQ) */
+int phe_privkey_get_p(const phe_privkey* sk, uint32_t* p_out);  /* n_words words, zero padded (PrivateKey::getP; p <= q) */
+int phe_privkey_get_q(const phe_privkey* sk, uint32_t* q_out);  /* n_words words, zero padded (PrivateKey::getQ) */
 
 /* ipcl::generateKeypair(n_length, enable_DJN) (ipcl_bindings.cpp:12-15): host prime search.
  * p, q = 3 (mod 4), top two bits set, gcd(p-1, q-1) = 2.  Outputs: n (bits/32 words), p, q (bits/64 words). */

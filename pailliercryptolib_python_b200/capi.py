@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libphe_b200.so")
+LIB_PATH = os.environ.get("PHE_B200_LIB") or os.path.join(_HERE, "lib", "libphe_b200.so")   # override: A/B builds of the kernels
 
 _u32p = ctypes.POINTER(ctypes.c_uint32)
 _lib = None
@@ -88,7 +88,8 @@ def kernel_launches():
     return int(lib().phe_kernel_launches())
 
 
-KERNEL_KINDS = ["k_modmul", "k_powm", "k_dec_prep", "k_dec_tail", "k_encrypt_comb", "k_encrypt_finish", "k_comb_build"]
+KERNEL_KINDS = ["k_modmul", "k_powm", "k_dec_prep", "k_dec_tail", "k_encrypt_comb", "k_encrypt_finish", "k_comb_build",
+                "k_dec_pair", "k_dec_crt"]
 
 
 def timing_enable(on=True):
@@ -230,9 +231,9 @@ class PubKey:
 class PrivKey:
     def __init__(self, pk, p, q):
         self.pk = pk
-        hw = pk.n_words // 2
+        pw, qw = (max(1, (int(v).bit_length() + 31) // 32) for v in (p, q))   # unbalanced primes are allowed
         h = ctypes.c_void_p()
-        _check(lib().phe_privkey_create(pk.h, _p(int_to_words(p, hw)), hw, _p(int_to_words(q, hw)), hw,
+        _check(lib().phe_privkey_create(pk.h, _p(int_to_words(p, pw)), pw, _p(int_to_words(q, qw)), qw,
                                         ctypes.byref(h)), "phe_privkey_create")
         self.h = h
 
@@ -284,6 +285,24 @@ def host_mont_block(modulus, mod_words, L, TPI):
     lib().phe_host_mont_block(_p(int_to_words(modulus, mod_words)), mod_words, L, TPI,
                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(n0))
     return out.reshape(5, kp), n0.value
+
+
+def pair_block(sk, y):
+    """What the p-adic pair engine is given for x = p (y = 0) or q (y = 1): dict(L, n0inv, mod, cst, prog), or None if
+    the key does not use the engine (include/phe_b200.h: phe_privkey_pair_block)."""
+    n = lib().phe_privkey_pair_block(sk.h, int(y), None, None, None, None, None, 0)
+    if n < 0:
+        raise RuntimeError(lib().phe_last_error().decode())
+    if n == 0:
+        return None
+    L, n0 = ctypes.c_int(), ctypes.c_uint64()
+    lib().phe_privkey_pair_block(sk.h, int(y), ctypes.byref(L), ctypes.byref(n0), None, None, None, 0)
+    mod = np.zeros(2 * L.value + 1, dtype=np.float64)
+    cst = np.zeros(6 * 2 * L.value, dtype=np.float64)
+    prog = np.zeros(n, dtype=np.uint32)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib().phe_privkey_pair_block(sk.h, int(y), None, None, mod.ctypes.data_as(dp), cst.ctypes.data_as(dp), _p(prog), n)
+    return {"L": L.value, "n0inv": n0.value, "mod": mod, "cst": cst, "prog": [int(v) for v in prog]}
 
 
 def host_powm_program(exponent, e_words):

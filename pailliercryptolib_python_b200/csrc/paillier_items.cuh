@@ -444,6 +444,7 @@ PHE_HD void item_dec_tail(const uint32_t* up_w, const uint32_t* uq_w, int u_word
   double x[L];
   uint64_t xi[L], mp[L], one[L];
   uint64_t* qbuf = reinterpret_cast<uint64_t*>(sm.b1);
+  uint32_t u_zero = 0;
   ints_from_entry<L, TPI, Env>(one, cst + DT_ONE * KP);
 #pragma unroll
   for (int j = 0; j < L; ++j) mp[j] = 0;
@@ -456,7 +457,7 @@ PHE_HD void item_dec_tail(const uint32_t* up_w, const uint32_t* uq_w, int u_word
     const double* bp;
     if (step == 0 || step == 2) {
       ints_from_words<L, TPI, Env>(xi, idx ? uq_w : up_w, u_words);
-      sub_exact<L, TPI, Env>(xi, one);                      // u - 1  (u >= 1)
+      u_zero = sub_exact<L, TPI, Env>(xi, one);             // u - 1; u = 0 only for a non-unit c: then L = floor(-1/x) = -1
       limbs_of<L>(x, xi);
       bp = cst + DT_ONE * KP;
       Env::sync();
@@ -478,6 +479,14 @@ PHE_HD void item_dec_tail(const uint32_t* up_w, const uint32_t* uq_w, int u_word
       for (int j = 0; j < L; ++j) xi[j] = (~qbuf[lane * LP + j]) & M52;
       if (lane == 0) xi[0] += 1ull;
       normalize_exact<L, TPI, Env>(xi);
+      {   // u = 0: L = -1 = x - 1 (mod x), as the oracle's floor division.  Branch-free: the shuffles inside sub_exact
+          // must stay warp-convergent and u_zero is only uniform within a lane group.
+        uint64_t xm1[L];
+        ints_from_entry<L, TPI, Env>(xm1, mod_e);
+        sub_exact<L, TPI, Env>(xm1, one);
+#pragma unroll
+        for (int j = 0; j < L; ++j) xi[j] = u_zero ? xm1[j] : xi[j];
+      }
       limbs_of<L>(x, xi);
     } else if (step == 1) {
       canonical_ints<L, TPI, Env>(mp, x, mod_e);            // m_p in [0, p)

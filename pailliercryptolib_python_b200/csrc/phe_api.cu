@@ -653,7 +653,7 @@ int phe_timing_read(int kind, double* ms_total, unsigned long long* launches) {
 }
 const char* phe_timing_kind_name(int kind) {
   static const char* names[KK_COUNT] = {"k_modmul", "k_powm", "k_dec_prep", "k_dec_tail", "k_encrypt_comb",
-                                        "k_encrypt_finish", "k_comb_build"};
+                                        "k_encrypt_finish", "k_comb_build", "k_dec_pair", "k_dec_crt"};
   return (kind >= 0 && kind < KK_COUNT) ? names[kind] : nullptr;
 }
 
@@ -725,6 +725,8 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
     sk->pk = pk; sk->p = P; sk->q = Q; sk->hw = pk->n_words;
     sk->ops = shape_for_bits(pk->n_words * 32);
     if (!sk->ops) return fail("phe_privkey_create: unsupported key size");
+    if (2 * Q.bits() > (size_t)pk->n_words * 32)
+      return fail("phe_privkey_create: primes too unbalanced (q^2 must fit the n_words words of n)");
     const ShapeOps* o = sk->ops;
     const BN R = hbn::shl(BN(1), o->capacity_bits);
     const BN g = hbn::add(pk->n, BN(1));
@@ -776,8 +778,8 @@ void phe_privkey_destroy(phe_privkey* sk) {
                     &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl}) b->release();
   delete sk;
 }
-int phe_privkey_get_p(const phe_privkey* sk, uint32_t* o) { if (!sk || !o) return fail("null"); sk->p.to_words(o, sk->hw / 2); return 0; }
-int phe_privkey_get_q(const phe_privkey* sk, uint32_t* o) { if (!sk || !o) return fail("null"); sk->q.to_words(o, sk->hw / 2); return 0; }
+int phe_privkey_get_p(const phe_privkey* sk, uint32_t* o) { if (!sk || !o) return fail("null"); sk->p.to_words(o, sk->hw); return 0; }
+int phe_privkey_get_q(const phe_privkey* sk, uint32_t* o) { if (!sk || !o) return fail("null"); sk->q.to_words(o, sk->hw); return 0; }
 
 // ---- key generation (host) ---------------------------------------------------------------------------
 static bool probably_prime(const BN& c) {

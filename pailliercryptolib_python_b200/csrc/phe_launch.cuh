@@ -103,7 +103,7 @@ template <int L, int TPI> struct Launch {
   static cudaError_t dec_crt(const DecCrtArgs& p, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(DT_COUNT);
     const int grid = grid_for(k_dec_crt<L, TPI>, smem, p.count, KS::GPB, 1);
-    { TimedLaunch tl_(KK_DEC_TAIL, s);
+    { TimedLaunch tl_(KK_DEC_CRT, s);
     k_dec_crt<L, TPI><<<grid, NT, smem, s>>>(p);
     }
     return cudaGetLastError();
@@ -158,7 +158,7 @@ template <int L> struct PairLaunch {
   static cudaError_t dec_pair(const DecPairArgs& p, cudaStream_t s) {
     const size_t smem = PairShape<L>::smem_bytes();
     const int g = grid(p.count);
-    { TimedLaunch tl_(KK_POWM, s);
+    { TimedLaunch tl_(KK_DEC_PAIR, s);
     k_dec_pair<L><<<dim3(g, 2), NT, smem, s>>>(p);
     }
     return cudaGetLastError();

@@ -50,7 +50,7 @@ void count_launch();
 
 // Per-kernel-kind device timing (phe_timing_* in the C ABI): when enabled every launch is bracketed by a
 // cudaEvent pair on its own stream.  Off by default (no events recorded).
-enum KernelKind { KK_MODMUL = 0, KK_POWM, KK_DEC_PREP, KK_DEC_TAIL, KK_ENC_COMB, KK_ENC_FINISH, KK_COMB_BUILD, KK_COUNT };
+enum KernelKind { KK_MODMUL = 0, KK_POWM, KK_DEC_PREP, KK_DEC_TAIL, KK_ENC_COMB, KK_ENC_FINISH, KK_COMB_BUILD, KK_DEC_PAIR, KK_DEC_CRT, KK_COUNT };
 void timing_begin(int kind, cudaStream_t s);
 void timing_end(int kind, cudaStream_t s);
 struct TimedLaunch {   // RAII: brackets one kernel launch, counts it

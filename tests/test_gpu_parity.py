@@ -253,6 +253,50 @@ def test_timing_hooks_and_pipe_peak(key2048):
     sk.decrypt(ct)
     t = capi.timing_read()
     capi.timing_enable(False)
-    assert t["k_encrypt_comb"][1] == 1 and t["k_powm"][1] == 1 and t["k_powm"][0] > 0
+    assert t["k_encrypt_comb"][1] == 1 and t["k_dec_pair"][1] == 1 and t["k_dec_pair"][0] > 0 and t["k_dec_crt"][1] == 1
     peak = capi.int_pipe_peak(2)
     assert 4e12 < peak < 12e12   # IMAD.WIDE.U32: one warp instruction per 4 cycles per SM sub-partition
+    assert 10e12 < capi.fp64_pipe_peak(2) < 20e12      # DFMA: one warp instruction per 2 cycles per sub-partition
+    assert 2e12 < capi.product_mix_peak(2) < 7e12      # 2 DFMA + DADD + IADD3 + IADD3.X per limb product
+
+
+def test_decrypt_generic_path_and_unbalanced_key(monkeypatch):
+    """Keys whose primes are not both exactly bits/2 long cannot use the p-adic pair engine and take the generic
+    k_dec_prep / k_powm_prog / k_dec_tail path; PHE_NO_PAIR_ENGINE=1 forces that path for any key.  Same results."""
+    rng = random.Random(SEED + 99)
+    pk_o, sk_o = O.bench_keypair()
+    monkeypatch.setenv("PHE_NO_PAIR_ENGINE", "1")
+    pk = capi.PubKey(pk_o.n, 2048, djn=True, hs=pk_o.hs)
+    sk = capi.PrivKey(pk, sk_o.p, sk_o.q)
+    assert capi.pair_block(sk, 0) is None
+    monkeypatch.delenv("PHE_NO_PAIR_ENGINE")
+    sk2 = capi.PrivKey(pk, sk_o.p, sk_o.q)
+    assert capi.pair_block(sk2, 0)["L"] == 20
+    ms = [0, 1, pk_o.n - 1] + [rng.randrange(pk_o.n) for _ in range(29)]
+    cs = O.encrypt_batch(pk_o, ms, [rng.getrandbits(1024) for _ in ms]) + _rand_cts(pk_o, rng, 32) + [0, sk_o.p, pk_o.n]
+    want = O.decrypt_batch(sk_o, cs)
+    capi.timing_enable(True)
+    got = capi.array_to_ints(sk.decrypt(capi.ints_to_array(cs, 128)))
+    t = capi.timing_read()
+    capi.timing_enable(False)
+    assert got == want and t["k_powm"][1] == 1 and t["k_dec_pair"][1] == 0
+    assert capi.array_to_ints(sk2.decrypt(capi.ints_to_array(cs, 128))) == want
+    # unbalanced primes: 1020-bit p, 1024-bit q (grossly unbalanced ones, q^2 > 2^2048, are rejected)
+    import sympy
+    with pytest.raises(RuntimeError):
+        capi.PrivKey(capi.PubKey((2 ** 1000 - 1) * (2 ** 1048 - 1), 2048, djn=False), 2 ** 1000 - 1, 2 ** 1048 - 1)
+    p = sympy.nextprime(rng.getrandbits(1020) | (1 << 1019))
+    q = sympy.nextprime(rng.getrandbits(1024) | (1 << 1023))
+    n = p * q
+    x = rng.getrandbits(2200) % n
+    hs = pow((-x * x) % n, n, n * n)
+    pk_u = O.PubKey(n, 2048, True, hs, 1024)
+    sk_u = O.PrivKey(pk_u, p, q)
+    cpk = capi.PubKey(n, 2048, djn=True, hs=hs)
+    csk = capi.PrivKey(cpk, p, q)
+    assert capi.pair_block(csk, 0) is None
+    ms = [0, n - 1] + [rng.randrange(n) for _ in range(14)]
+    rs = [rng.getrandbits(1024) for _ in ms]
+    ct = cpk.encrypt(capi.ints_to_array(ms, 64), capi.ints_to_array(rs, 32))
+    assert capi.array_to_ints(ct) == O.encrypt_batch(pk_u, ms, rs)
+    assert capi.array_to_ints(csk.decrypt(ct)) == ms == O.decrypt_batch(sk_u, capi.array_to_ints(ct))

@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""BASELINE config 5: 3072-bit key (6144-bit n^2), batch-N encrypt + decrypt on one B200.
+
+  python tools/config5_3072.py --count 100000
+
+The reference stops at 2048-bit keys (ipcl_python.py:29-30), so parity here is against the oracle only: a spot-check of
+rows against the Python-int formulas plus the full-batch round trip D(E(m)) == m.  Prints one JSON line.
+"""
+import argparse
+import json
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import paillier_oracle as O  # noqa: E402  (checker only)
+from pailliercryptolib_python_b200 import capi  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--count", type=int, default=100000)
+    ap.add_argument("--bits", type=int, default=3072)
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    bits, N = args.bits, args.count
+    nw = bits // 32
+    pk_o, sk_o = O.seeded_keypair(bits, 77)
+    pk = capi.PubKey(pk_o.n, bits, djn=True, hs=pk_o.hs)
+    sk = capi.PrivKey(pk, sk_o.p, sk_o.q)
+    rng = np.random.Generator(np.random.PCG64(20240611))
+    m_np = np.zeros((N, nw), dtype=np.uint32)
+    m_np[:, :2] = rng.integers(0, 1 << 32, size=(N, 2), dtype=np.uint64).astype(np.uint32)
+    m_np[:, 1] &= (1 << 21) - 1                      # 53-bit plaintexts (float64 mantissas), as configs[1]
+    r_np = rng.integers(0, 1 << 32, size=(N, nw // 2), dtype=np.uint64).astype(np.uint32)
+    dev = torch.device("cuda", 0)
+    m = torch.from_numpy(m_np.view(np.int32)).to(dev)
+    r = torch.from_numpy(r_np.view(np.int32)).to(dev)
+    ct = torch.empty((N, 2 * nw), dtype=torch.int32, device=dev)
+    out = torch.empty((N, nw), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    best = None
+    for _ in range(args.reps + 1):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        torch.cuda.synchronize()
+        e0.record()
+        pk.encrypt_dev(m.data_ptr(), N, r.data_ptr(), nw // 2, ct.data_ptr(), stream)
+        e1.record()
+        sk.decrypt_dev(ct.data_ptr(), N, out.data_ptr(), stream)
+        e2.record()
+        torch.cuda.synchronize()
+        t = (e0.elapsed_time(e1), e1.elapsed_time(e2))
+        if best is None or sum(t) < sum(best):
+            best = t
+    assert torch.equal(out, m), "round trip D(E(m)) != m"
+    idx = [0, 1, N // 2, N - 1] + random.Random(5).sample(range(N), 4)
+    ct_h = ct[idx].cpu().numpy().view(np.uint32)
+    ms = capi.array_to_ints(m_np[idx])
+    rs = capi.array_to_ints(r_np[idx])
+    ok = capi.array_to_ints(ct_h) == O.encrypt_batch(pk_o, ms, rs)
+    print(json.dumps({
+        "workload": "%d-bit DJN key, batch=%d encrypt + decrypt on 1 GPU (BASELINE configs[4])" % (bits, N),
+        "encrypt_ops_s": N / (best[0] * 1e-3), "decrypt_ops_s": N / (best[1] * 1e-3),
+        "ops_s": 2 * N / (sum(best) * 1e-3), "ms_encrypt": best[0], "ms_decrypt": best[1],
+        "comb_bits": pk.comb_bits, "round_trip": True, "parity_spot_check": bool(ok)}))
+    if not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
