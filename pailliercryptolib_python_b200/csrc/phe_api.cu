@@ -576,16 +576,17 @@ int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count,
   PHE_TRY(sk->ws_tbl.ensure(po->tbl_words((int)chunk, slots)));
   for (size_t off = 0; off < count; off += CHUNK) {
     const int c = (int)std::min(CHUNK, count - off);
-    DecPairArgs a{};
-    a.c_w = d_ct + off * cw; a.c_words = cw; a.chunk_words = half; a.out_words = half; a.count = c; a.slots = slots;
     for (int y = 0; y < 2; ++y) {
-      a.prog[y] = sk->d_pair_prog[y].p; a.out_w[y] = sk->ws_u[y].p;
-      a.mod[y] = reinterpret_cast<const double*>(sk->d_pair_mod[y].p);
-      a.cst[y] = reinterpret_cast<const double*>(sk->d_pair_cst[y].p);
-      a.n0inv[y] = sk->pairb[y].n0inv;
+      const int L = sk->pairb[y].L;
+      DecPairArgs a{};
+      a.c_w = d_ct + off * cw; a.c_words = cw; a.chunk_words = half; a.out_words = half; a.count = c; a.slots = slots;
+      a.prog = sk->d_pair_prog[y].p; a.out_w = sk->ws_u[y].p;
+      a.dcon = reinterpret_cast<const double*>(sk->d_pair_mod[y].p) + L;
+      a.cst = reinterpret_cast<const double*>(sk->d_pair_cst[y].p);
+      a.n0inv = sk->pairb[y].n0inv;
+      a.tbl = reinterpret_cast<double*>(sk->ws_tbl.p);   // the two launches run back to back on the stream
+      CUDA_TRY(po->dec_pair(a, sk->pairb[y].mod.data(), s));
     }
-    a.tbl = reinterpret_cast<double*>(sk->ws_tbl.p);
-    CUDA_TRY(po->dec_pair(a, s));
     DecCrtArgs t{};
     t.mp_w = sk->ws_u[0].p; t.mq_w = sk->ws_u[1].p; t.half_words = half; t.m_w = d_m + off * hw; t.m_words = hw;
     t.count = c; t.cst = reinterpret_cast<const double*>(sk->d_tail.p);

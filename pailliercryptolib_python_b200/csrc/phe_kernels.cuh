@@ -200,48 +200,51 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
 }
 
 // ---- decrypt on the p-adic pair engine: one (ciphertext, modulus) per lane ---------------------------------------
+// One launch per modulus (x = p, then x = q).  The limbs of x travel inside the kernel parameters: after unrolling
+// every use has a compile-time offset, so the N-part products read them as constant-bank operands of the DFMA
+// itself (c[0x0][..]) -- no load instructions and no registers for the modulus.
 struct DecPairArgs {
   const uint32_t* c_w;       // [count][c_words]
   int c_words, chunk_words;
-  const uint32_t* prog[2];   // pair-engine programs for x = p, q (paillier_items.cuh: PairOp)
-  uint32_t* out_w[2];        // m_p, m_q: [count][out_words]
+  const uint32_t* prog;      // pair-engine program for x (paillier_items.cuh: PairOp)
+  uint32_t* out_w;           // m_x: [count][out_words]
   int out_words;
   int count;
-  const double* mod[2];      // [L] limbs of x followed by [L + 1] limbs of D = k x >= R
-  uint64_t n0inv[2];
-  const double* cst[2];      // [PC_COUNT][2][L] constant pairs
-  double* tbl;               // [gridDim.y * gridDim.x * NT / 32][slots][2][L][32]
+  const double* dcon;        // [L + 1] limbs of D = ceil(R / x) x  (global; staged to shared memory: indexed by row)
+  uint64_t n0inv;
+  const double* cst;         // [PC_COUNT][2][L] constant pairs
+  double* tbl;               // [gridDim.x * NT / 32][slots][2][L][32]
   int slots;
 };
+template <int L> struct ModLimbs { double v[L]; };
 
 template <int L> struct PairShape {
   static constexpr int LE = (L + 2) & ~1;                       // L + 1 entries of E, padded to even
   static constexpr int PER_LANE = 4 * L + LE;                   // doubles of shared memory per lane
-  static constexpr size_t smem_bytes() { return (size_t)(2 * LE + PER_LANE * NT) * sizeof(double); }
+  static constexpr size_t smem_bytes() { return (size_t)(LE + PER_LANE * NT) * sizeof(double); }
 };
 
-template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(DecPairArgs p) {
+template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(const DecPairArgs p, const ModLimbs<L> mod) {
   using PE = DevPairEnv;
   using PS = PairShape<L>;
   extern __shared__ __align__(16) double smem[];
-  const int y = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * L + 1; i += NT) smem[i < L ? i : PS::LE + (i - L)] = p.mod[y][i];
+  for (int i = threadIdx.x; i < L + 1; i += NT) smem[i] = p.dcon[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, col = threadIdx.x & 31;
-  double* wbase = smem + 2 * PS::LE + (size_t)warp * PS::PER_LANE * 32 + col;
+  double* wbase = smem + PS::LE + (size_t)warp * PS::PER_LANE * 32 + col;
   PairSmem<PE> sm;
   sm.xs0 = wbase;
   sm.x1 = wbase + L * 32;
   sm.y0 = wbase + 2 * L * 32;
   sm.y1 = wbase + 3 * L * 32;
   sm.e = reinterpret_cast<int64_t*>(wbase + 4 * L * 32);
-  double* tbl = p.tbl + ((size_t)(y * gridDim.x + blockIdx.x) * (NT / 32) + warp) * ((size_t)p.slots * 2 * L * 32) + col;
+  double* tbl = p.tbl + ((size_t)blockIdx.x * (NT / 32) + warp) * ((size_t)p.slots * 2 * L * 32) + col;
   for (int base = blockIdx.x * NT; base < p.count; base += gridDim.x * NT) {
     const int want = base + (int)threadIdx.x;
     const int item = want < p.count ? want : p.count - 1;
-    item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog[y],
-                         want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, smem,
-                         smem + PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+    item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog,
+                         want < p.count ? p.out_w + (size_t)item * p.out_words : nullptr, p.out_words, mod.v,
+                         smem, p.n0inv, p.cst, tbl, sm);
   }
 }
 

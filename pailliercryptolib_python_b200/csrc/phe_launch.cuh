@@ -153,18 +153,21 @@ template <int L, int TPI> struct Launch {
 // Launcher of the one-bignum-per-lane pair engine (L = limbs of p, q).
 template <int L> struct PairLaunch {
   static int grid(int count) {
-    return grid_for(k_dec_pair<L>, PairShape<L>::smem_bytes(), count, NT, 2);
+    return grid_for(k_dec_pair<L>, PairShape<L>::smem_bytes(), count, NT, 1);
   }
-  static cudaError_t dec_pair(const DecPairArgs& p, cudaStream_t s) {
+  // mod: L limbs of x (doubles)
+  static cudaError_t dec_pair(const DecPairArgs& p, const double* mod, cudaStream_t s) {
     const size_t smem = PairShape<L>::smem_bytes();
     const int g = grid(p.count);
+    ModLimbs<L> m;
+    for (int i = 0; i < L; ++i) m.v[i] = mod[i];
     { TimedLaunch tl_(KK_DEC_PAIR, s);
-    k_dec_pair<L><<<dim3(g, 2), NT, smem, s>>>(p);
+    k_dec_pair<L><<<g, NT, smem, s>>>(p, m);
     }
     return cudaGetLastError();
   }
   static size_t tbl_words(int count, int slots) {   // u32 words
-    return (size_t)grid(count) * 2 * (NT / 32) * slots * 2 * L * 32 * 2;
+    return (size_t)grid(count) * (NT / 32) * slots * 2 * L * 32 * 2;
   }
   static constexpr PairOps ops() { return PairOps{L, &dec_pair, &tbl_words}; }
 };
