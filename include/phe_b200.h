@@ -136,6 +136,11 @@ int phe_add_dev(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint
 int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
                 int exp_bits, uint32_t* d_out, void* stream);
 
+/* The obfuscator exponents r of a DJN key, when the caller passes r = NULL, are drawn on the device from a ChaCha20
+ * keystream (RFC 8439 block function) keyed with 256 + 96 fresh bits of getrandom(2) per call.  This exposes the
+ * keystream generator for known-answer tests: `words` 32-bit words of keystream starting at block counter0. */
+int phe_chacha20_keystream(const uint32_t key[8], const uint32_t nonce[3], uint32_t counter0, uint32_t* out, size_t words);
+
 /* ---- host-only helpers exposed for the CPU test-suite (no GPU needed) --------------------------------------- */
 
 /* Montgomery context block exactly as uploaded to the device for modulus `mod` (mod_words words) in the

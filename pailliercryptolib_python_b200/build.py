@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--cudart", "static",
 ]
-CU_SOURCES = ["phe_api.cu", "pipe_peak.cu", "pair_shapes.cu"] + ["shape_%d_%d.cu" % s for s in ((20, 1), (20, 2), (20, 4), (20, 8), (15, 4), (15, 8))]
+CU_SOURCES = ["phe_api.cu", "pipe_peak.cu", "pair_shapes.cu", "chacha20.cu"] + ["shape_%d_%d.cu" % s for s in ((20, 1), (20, 2), (20, 4), (20, 8), (15, 4), (15, 8))]
 HEADERS = ["mont52.cuh", "paillier_items.cuh", "phe_kernels.cuh", "phe_launch.cuh", "phe_shapes.hpp", "hostbn.hpp",
            os.path.join("..", "..", "include", "phe_b200.h")]
 

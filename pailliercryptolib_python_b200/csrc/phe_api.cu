@@ -19,6 +19,8 @@
 using hbn::BN;
 
 namespace phe {
+cudaError_t chacha20_fill(uint32_t* d_out, size_t words, const uint32_t key[8], const uint32_t nonce[3], uint32_t counter0,
+                          int mask_every, uint32_t top_mask, cudaStream_t s);
 extern const PairOps g_pair_10, g_pair_20, g_pair_30;
 extern const ShapeOps g_ops_20_1, g_ops_20_2, g_ops_20_4, g_ops_20_8, g_ops_15_4, g_ops_15_8;
 static std::atomic<unsigned long long> g_launches{0};
@@ -504,6 +506,19 @@ int make_r_host(const phe_pubkey* pk, size_t count, std::vector<uint32_t>& r, in
   return 0;
 }
 
+// DJN obfuscator exponents drawn on the device: ChaCha20 keystream under a key and nonce fresh from getrandom(2) for
+// every call (csrc/chacha20.cu), top word of every r masked to randbits.  Result in pk->ws_r.
+int random_r_dev(const phe_pubkey* pk, size_t count, int* r_words, cudaStream_t s) {
+  *r_words = (pk->randbits + 31) / 32;
+  const size_t words = count * (size_t)*r_words;
+  PHE_TRY(pk->ws_r.ensure(words));
+  uint32_t seed[11];
+  PHE_TRY(random_words(seed, 11));
+  const uint32_t mask = (pk->randbits & 31) ? ((1u << (pk->randbits & 31)) - 1u) : 0xffffffffu;
+  CUDA_TRY(chacha20_fill(pk->ws_r.p, words, seed, seed + 8, 0u, *r_words, mask, s));
+  return 0;
+}
+
 int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
                      uint32_t* d_ct, cudaStream_t s) {
   const int cw = 2 * pk->n_words;
@@ -887,13 +902,17 @@ int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uin
     CUDA_TRY(cudaSetDevice(pk->device));
     const int cw = 2 * pk->n_words;
     std::vector<uint32_t> rgen;
-    if (make_secure && !r) { PHE_TRY(make_r_host(pk, count, rgen, &r_words)); r = rgen.data(); }
+    const bool device_r = make_secure && !r && pk->djn;   // DJN: r uniform in [0, 2^randbits), drawn on the device
+    if (make_secure && !r && !device_r) { PHE_TRY(make_r_host(pk, count, rgen, &r_words)); r = rgen.data(); }
     if (!make_secure) r = nullptr;
     PHE_TRY(pk->ws_a.ensure(count * pk->n_words));
     PHE_TRY(pk->ws_b.ensure(count * cw));
     CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, m, count * pk->n_words * 4, cudaMemcpyHostToDevice, 0));
     const uint32_t* d_r = nullptr;
-    if (r) {   // workspace kept with the key: a cudaMalloc/cudaFree pair per call costs milliseconds and a device sync
+    if (device_r) {
+      PHE_TRY(random_r_dev(pk, count, &r_words, 0));
+      d_r = pk->ws_r.p;
+    } else if (r) {   // workspace kept with the key: a cudaMalloc/cudaFree pair per call costs milliseconds and a device sync
       PHE_TRY(pk->ws_r.ensure(count * (size_t)r_words));
       CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice, 0));
       d_r = pk->ws_r.p;
@@ -916,19 +935,20 @@ int phe_obfuscate(const phe_pubkey* pk, uint32_t* ct, size_t count, const uint32
     CUDA_TRY(cudaSetDevice(pk->device));
     const int cw = 2 * pk->n_words;
     std::vector<uint32_t> rgen;
-    if (!r) { PHE_TRY(make_r_host(pk, count, rgen, &r_words)); r = rgen.data(); }
-    DevBuf rbuf, obuf;
-    PHE_TRY(rbuf.ensure(count * (size_t)r_words));
-    PHE_TRY(obuf.ensure(count * cw));
+    if (!r && pk->djn) {
+      PHE_TRY(random_r_dev(pk, count, &r_words, 0));
+    } else {
+      if (!r) { PHE_TRY(make_r_host(pk, count, rgen, &r_words)); r = rgen.data(); }
+      PHE_TRY(pk->ws_r.ensure(count * (size_t)r_words));
+      CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice, 0));
+    }
+    PHE_TRY(pk->ws_a.ensure(count * cw));   // obfuscators
     PHE_TRY(pk->ws_b.ensure(count * cw));
-    int rc = 0;
-    if (cudaMemcpy(rbuf.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(pk->ws_b.p, ct, count * cw * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("phe_obfuscate: H2D failed");
-    if (!rc) rc = obfuscators_dev(pk, rbuf.p, r_words, count, obuf.p, 0);
-    if (!rc) rc = add_dev_impl(pk, pk->ws_b.p, count, obuf.p, count, pk->ws_b.p, 0);
-    if (!rc && cudaMemcpy(ct, pk->ws_b.p, count * cw * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("phe_obfuscate: D2H failed");
-    rbuf.release(); obuf.release();
-    return rc;
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, ct, count * cw * 4, cudaMemcpyHostToDevice, 0));
+    PHE_TRY(obfuscators_dev(pk, pk->ws_r.p, r_words, count, pk->ws_a.p, 0));
+    PHE_TRY(add_dev_impl(pk, pk->ws_b.p, count, pk->ws_a.p, count, pk->ws_b.p, 0));
+    CUDA_TRY(cudaMemcpy(ct, pk->ws_b.p, count * cw * 4, cudaMemcpyDeviceToHost));
+    return 0;
   } catch (const std::exception& e) { return fail(std::string("phe_obfuscate: ") + e.what()); }
 }
 
@@ -1070,6 +1090,18 @@ int phe_privkey_pair_block(const phe_privkey* sk, int y, int* L_out, uint64_t* n
     std::memcpy(prog_out, b.prog.data(), b.prog.size() * 4);
   }
   return (int)b.prog.size();
+}
+
+int phe_chacha20_keystream(const uint32_t key[8], const uint32_t nonce[3], uint32_t counter0, uint32_t* out, size_t words) {
+  if (!key || !nonce || !out) return fail("phe_chacha20_keystream: null argument");
+  if (phe_device_count() <= 0) return fail("phe_chacha20_keystream: no CUDA device");
+  DevBuf b;
+  PHE_TRY(b.ensure(words ? words : 1));
+  int rc = 0;
+  if (chacha20_fill(b.p, words, key, nonce, counter0, 0, 0xffffffffu, 0) != cudaSuccess ||
+      cudaMemcpy(out, b.p, words * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("phe_chacha20_keystream: CUDA error");
+  b.release();
+  return rc;
 }
 
 int phe_host_powm_program(const uint32_t* e, int e_words, uint32_t* out, int out_cap) {
