@@ -308,7 +308,10 @@ def run_gpu(args):
         roofline = {
             "bound": "int_pipe", "kernel": dom_name,
             "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s", "frac": achieved / peak,
-            "traffic": None, "launch_ms": per_launch_ms, "launches": dom_n,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one k_dec_pair launch, ncu --set full, r01
+            # (profiles/r01_ncu_k_dec_pair_summary.txt): 3.52 + 1.00 GB against 64 MB of algorithmic bytes -- the
+            # per-lane window tables (388 MB per launch) do not fit the 126 MB L2; at 66 GB/s it is 1 % of HBM bandwidth
+            "traffic": 4.52e9 if (pair[0] and N == 100000) else None, "launch_ms": per_launch_ms, "launches": dom_n,
             "peak_source": "measured live: phe_int_pipe_peak (IMAD.WIDE.U32 issue rate, all SMs)",
             "algorithmic_mac32_per_op": W_DEC_2048,
             "note": "algorithmic MAC32 of the reference algorithm (SURVEY 8d: two 2048-bit windowed modexps) against the "
