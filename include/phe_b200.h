@@ -120,8 +120,14 @@ int phe_add(const phe_pubkey* pk, const uint32_t* a, size_t na, const uint32_t* 
 int phe_mul(const phe_pubkey* pk, const uint32_t* ct, size_t n, const uint32_t* e, int e_words, size_t ne,
             uint32_t* out);
 
+/* out[i] = ct[i]^-1 mod n^2 (count rows of 2 n_words words).  The reference inverts ciphertexts one by one on the host
+ * for HE-mul by a negative plaintext (gmpy2.invert, ipcl_python.py:272-276, 426-441, 470-479); here the whole batch
+ * costs 6 Montgomery products per element on the device (Montgomery's trick) plus at most 16 host inversions.  Fails
+ * (and writes nothing useful) if some ct[i] is not invertible modulo n^2. */
+int phe_invert(const phe_pubkey* pk, const uint32_t* ct, size_t count, uint32_t* out);
+
 /* ipcl::modExp(base, exp, mod) element-wise with one shared odd modulus:
- *   out[i] = base[i] ^ exp[i] mod modulus; all operands `words` words; supports moduli up to 6144 bits. */
+ *   out[i] = base[i] ^ exp[i] mod modulus; all operands `words` words; supports moduli up to 8312 bits. */
 int phe_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulus, int words, size_t count,
                uint32_t* out);
 

@@ -21,7 +21,7 @@ SYMBOLS = [
     "phe_privkey_create", "phe_privkey_destroy", "phe_privkey_get_p", "phe_privkey_get_q", "phe_keygen",
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
-    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_chacha20_keystream",
+    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_chacha20_keystream", "phe_invert",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
     "phe_product_mix_peak",
 ]
@@ -202,6 +202,13 @@ class PubKey:
         out = np.empty_like(a)
         _check(lib().phe_add(self.h, _p(a), ctypes.c_size_t(a.shape[0]), _p(b), ctypes.c_size_t(b.shape[0]), _p(out)),
                "phe_add")
+        return out
+
+    def invert(self, ct):
+        """Row-wise modular inverse modulo n^2 (batched on the device)."""
+        ct = np.ascontiguousarray(ct, dtype=np.uint32).reshape(-1, 2 * self.n_words)
+        out = np.empty_like(ct)
+        _check(lib().phe_invert(self.h, _p(ct), ctypes.c_size_t(ct.shape[0]), _p(out)), "phe_invert")
         return out
 
     def mul(self, ct, e):

@@ -196,6 +196,30 @@ inline BN gcd(BN a, BN b) { while (!b.is_zero()) { BN r = mod(a, b); a = b; b = 
 // inverse of a modulo a PRIME p (Fermat)
 inline BN modinv_prime(const BN& a, const BN& p) { return modexp(a, sub(p, BN(2)), p); }
 
+// a^-1 mod m for any m > 1 (extended Euclid); throws if gcd(a, m) != 1
+inline BN modinv(const BN& a, const BN& m) {
+  BN r0 = m, r1 = mod(a, m);
+  BN t0, t1(1);          // coefficients of a, kept as magnitudes with signs
+  bool s0 = false, s1 = false;
+  while (!r1.is_zero()) {
+    BN q, r2;
+    divmod(r0, r1, &q, &r2);
+    // t2 = t0 - q * t1
+    const BN qt = mul(q, t1);
+    BN t2; bool s2;
+    if (s0 == s1) {       // same sign: t0 - qt
+      if (cmp(t0, qt) >= 0) { t2 = sub(t0, qt); s2 = s0; } else { t2 = sub(qt, t0); s2 = !s0; }
+    } else {              // opposite signs: magnitudes add, sign of t0
+      t2 = add(t0, qt); s2 = s0;
+    }
+    r0 = r1; r1 = r2; t0 = t1; s0 = s1; t1 = t2; s1 = s2;
+  }
+  if (!(r0 == BN(1))) throw std::runtime_error("BN::modinv: not invertible");
+  BN t = mod(t0, m);
+  if (s0 && !t.is_zero()) t = sub(m, t);
+  return t;
+}
+
 // -n^-1 mod 2^28 for odd n
 inline uint32_t neg_inv28(uint32_t n0) {
   uint32_t x = 1; for (int i = 0; i < 5; ++i) x *= 2u - n0 * x;

@@ -405,6 +405,21 @@ std::shared_ptr<CipherText> ct_add(const CipherText& a, const CipherText& b) {
   return std::make_shared<CipherText>(a.pk, std::move(out));
 }
 
+// Row-wise inverse modulo n^2 (not part of the reference module: the reference's Python inverts with gmpy2 one element
+// at a time; pailliercryptolib_python_b200/ipcl_python.py calls this instead).
+std::shared_ptr<CipherText> ct_modinv(const CipherText& a) {
+  Packed out;
+  out.count = a.count; out.stride = a.stride;
+  out.data.resize(a.data.size());
+  int rc;
+  {
+    py::gil_scoped_release nogil;
+    rc = phe_invert(a.pk->h, a.data.data(), a.count, out.data.data());
+  }
+  if (rc) throw_phe("CipherText modinv");
+  return std::make_shared<CipherText>(a.pk, std::move(out));
+}
+
 std::shared_ptr<CipherText> ct_mul(const CipherText& a, const PlainText& b) {
   if (b.count != a.count && b.count != 1) throw std::runtime_error("CipherText *: size mismatch");
   // exponent words: trim to what is used, never more than n_words
@@ -627,6 +642,7 @@ PYBIND11_MODULE(ipcl_bindings, m) {
       .def("__str__", [](const CipherText& s) { return "<ipclCipherText " + addr_tag(&s) + ">"; })
       .def("__getitem__", [](const CipherText& s, size_t i) { return std::make_shared<BigNumber>(s.element(i)); })
       .def("__getitem__", [](const CipherText& s, const py::slice& sl) { size_t len; const size_t st = slice_bounds(s, sl, &len); return std::make_shared<CipherText>(s.pk, s.chunk(st, len)); })
+      .def("modinv", [](const CipherText& a) { return ct_modinv(a); })
       .def("__add__", [](const CipherText& a, const CipherText& b) { return ct_add(a, b); })
       .def("__add__", [](const CipherText& a, const PlainText& b) { return ct_add(a, *encrypt(a.pk, b, false)); })
       .def("__mul__", [](const CipherText& a, const PlainText& b) { return ct_mul(a, b); })

@@ -564,6 +564,61 @@ int add_dev_impl(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uin
   return 0;
 }
 
+// out[i] = a[i]^-1 mod n^2 for count device rows (Montgomery's trick, recursive over block totals; the last <= 16
+// values are inverted on the host).  Fails with "not invertible" if any a[i] shares a factor with n.
+int invert_dev_impl(const phe_pubkey* pk, const uint32_t* d_a, size_t count, uint32_t* d_out, cudaStream_t s) {
+  const ShapeOps* o = pk->ops;
+  const int cw = 2 * pk->n_words;
+  if (count == 0) return 0;
+  if (count <= 16) {
+    std::vector<uint32_t> h(count * cw);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), d_a, h.size() * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    try {
+      for (size_t i = 0; i < count; ++i)
+        hbn::modinv(BN::from_words(&h[i * cw], cw), pk->nsq).to_words(&h[i * cw], cw);
+    } catch (const std::exception&) { return fail("phe_invert: an element is not invertible modulo n^2"); }
+    CUDA_TRY(cudaMemcpyAsync(d_out, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));   // h is a stack-lifetime staging buffer
+    return 0;
+  }
+  const size_t groups = (size_t)o->resident_groups();
+  size_t block = (count + groups - 1) / groups;
+  if (block < 4) block = 4;
+  if (block > 256) block = 256;
+  const size_t nblocks = (count + block - 1) / block, padded = nblocks * block;
+  DevBuf in_pad, P, totals, tinv, out_pad;
+  const uint32_t* src = d_a;
+  uint32_t* dst = d_out;
+  int rc = 0;
+  if (padded != count) {        // pad with ones so that every block has the same length
+    rc = in_pad.ensure(padded * cw);
+    if (!rc) rc = out_pad.ensure(padded * cw);
+    if (!rc) {
+      std::vector<uint32_t> ones((padded - count) * cw, 0);
+      for (size_t i = 0; i < padded - count; ++i) ones[i * cw] = 1;
+      if (cudaMemcpyAsync(in_pad.p, d_a, count * cw * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+          cudaMemcpyAsync(in_pad.p + count * cw, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+          cudaStreamSynchronize(s) != cudaSuccess) rc = fail("phe_invert: padding copy failed");
+      src = in_pad.p; dst = out_pad.p;
+    }
+  }
+  if (!rc) rc = P.ensure(padded * EW(o));
+  if (!rc) rc = totals.ensure(nblocks * cw);
+  if (!rc) rc = tinv.ensure(nblocks * cw);
+  InvArgs a{};
+  a.c_w = src; a.nwords = cw; a.count = (int)padded; a.block = (int)block;
+  a.P = reinterpret_cast<double*>(P.p); a.total_w = totals.p; a.tinv_w = tinv.p; a.out_w = dst; a.ctx = pk->ctx;
+  if (!rc && o->inv_block(a, false, s) != cudaSuccess) rc = fail("phe_invert: prefix kernel launch failed");
+  if (!rc) rc = invert_dev_impl(pk, totals.p, nblocks, tinv.p, s);
+  if (!rc && o->inv_block(a, true, s) != cudaSuccess) rc = fail("phe_invert: unwind kernel launch failed");
+  if (!rc && padded != count &&
+      cudaMemcpyAsync(d_out, out_pad.p, count * cw * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail("phe_invert: copy failed");
+  if (cudaStreamSynchronize(s) != cudaSuccess && !rc) rc = fail("phe_invert: kernel failed");
+  for (DevBuf* b : {&in_pad, &P, &totals, &tinv, &out_pad}) b->release();
+  return rc;
+}
+
 int mul_dev_impl(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
                  int exp_bits, uint32_t* d_out, cudaStream_t s) {
   if (ne != n && ne != 1) return fail("phe_mul: size mismatch (exponents must have n or 1 elements)");
@@ -1010,6 +1065,27 @@ int phe_mul(const phe_pubkey* pk, const uint32_t* ct, size_t n, const uint32_t* 
     CUDA_TRY(cudaMemcpy(out, pk->ws_c.p, n * cw * 4, cudaMemcpyDeviceToHost));
     return 0;
   } catch (const std::exception& e) { return fail(std::string("phe_mul: ") + e.what()); }
+}
+
+int phe_invert(const phe_pubkey* pk, const uint32_t* ct, size_t count, uint32_t* out) {
+  try {
+    if (!pk || !ct || !out) return fail("phe_invert: null argument");
+    if (count == 0) return 0;
+    std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
+    CUDA_TRY(cudaSetDevice(pk->device));
+    const int cw = 2 * pk->n_words;
+    int rc = 0;
+    for (size_t off = 0; off < count && !rc; off += CHUNK) {
+      const size_t c = std::min(CHUNK, count - off);
+      PHE_TRY(pk->ws_a.ensure(c * cw));
+      PHE_TRY(pk->ws_b.ensure(c * cw));
+      CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, ct + off * cw, c * cw * 4, cudaMemcpyHostToDevice, 0));
+      rc = invert_dev_impl(pk, pk->ws_a.p, c, pk->ws_b.p, 0);
+      if (!rc) CUDA_TRY(cudaMemcpy(out + off * cw, pk->ws_b.p, c * cw * 4, cudaMemcpyDeviceToHost));
+    }
+    return rc;
+  } catch (const std::exception& e) { return fail(std::string("phe_invert: ") + e.what()); }
 }
 
 int phe_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulus, int words, size_t count,

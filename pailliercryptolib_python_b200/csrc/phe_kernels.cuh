@@ -79,6 +79,43 @@ __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_modmul(const uint32_t* __
   }
 }
 
+// ---- batched modular inverse (Montgomery's trick): one block of `block` consecutive elements per lane group --------
+struct InvArgs {
+  const uint32_t* c_w;     // [count][nwords]
+  int nwords, count, block;   // count % block == 0
+  double* P;               // [count][KP] prefix products (Montgomery form)
+  uint32_t* total_w;       // k_inv_prefix: [nblocks][nwords] block totals (canonical)
+  const uint32_t* tinv_w;  // k_inv_unwind: [nblocks][nwords] inverses of the block totals
+  uint32_t* out_w;         // k_inv_unwind: [count][nwords]
+  MontCtxArgs ctx;
+};
+
+template <int L, int TPI, bool UNWIND>
+__global__ void __launch_bounds__(NT, MinCtas<L>::V) k_inv_block(InvArgs p) {
+  using Env = DevEnv<TPI>;
+  using KS = KShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<KS::KP>(smem, p.ctx.entries, ME_COUNT);
+  GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
+  const int g = threadIdx.x / TPI;
+  const int nblocks = p.count / p.block;   // count is a multiple of block (the host pads with ones): every group of a
+  const int cnt = p.block;                // warp runs the same number of products, so the shuffles stay convergent
+  for (int base = blockIdx.x * KS::GPB; base < nblocks; base += gridDim.x * KS::GPB) {
+    const int want = base + g;
+    const int b = want < nblocks ? want : nblocks - 1;      // past the end: redo the last block (same values stored)
+    const int first = b * p.block;
+    if (!UNWIND)
+      item_inv_prefix<L, TPI, Env>(p.c_w + (size_t)first * p.nwords, p.nwords, cnt, p.P + (size_t)first * KS::KP,
+                                   p.total_w + (size_t)b * p.nwords, smem + ME_N * KS::KP, p.ctx.n0inv,
+                                   smem + ME_R2 * KS::KP, smem + ME_ONEM * KS::KP, smem + ME_ONE * KS::KP, sm);
+    else
+      item_inv_unwind<L, TPI, Env>(p.c_w + (size_t)first * p.nwords, p.nwords, cnt, p.P + (size_t)first * KS::KP,
+                                   p.tinv_w + (size_t)b * p.nwords, want < nblocks ? p.out_w + (size_t)first * p.nwords : nullptr,
+                                   smem + ME_N * KS::KP, p.ctx.n0inv, smem + ME_R2 * KS::KP, smem + ME_ONEM * KS::KP,
+                                   smem + ME_ONE * KS::KP, sm);
+  }
+}
+
 // ---- generic fixed-window modexp ----------------------------------------------------------------
 // gridDim.y selects one of up to two modulus contexts (decrypt: y=0 -> p^2, y=1 -> q^2); each has its own
 // exponent (shared by all items when e_stride == 0) and output array.

@@ -100,6 +100,26 @@ template <int L, int TPI> struct Launch {
     }
     return cudaGetLastError();
   }
+  static cudaError_t inv_block(const InvArgs& p, bool unwind, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int nblocks = p.count / p.block;
+    if (unwind) {
+      const int grid = grid_for(k_inv_block<L, TPI, true>, smem, nblocks, KS::GPB, 1);
+      { TimedLaunch tl_(KK_MODMUL, s);
+      k_inv_block<L, TPI, true><<<grid, NT, smem, s>>>(p);
+      }
+    } else {
+      const int grid = grid_for(k_inv_block<L, TPI, false>, smem, nblocks, KS::GPB, 1);
+      { TimedLaunch tl_(KK_MODMUL, s);
+      k_inv_block<L, TPI, false><<<grid, NT, smem, s>>>(p);
+      }
+    }
+    return cudaGetLastError();
+  }
+  static int resident_groups() {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    return grid_for(k_inv_block<L, TPI, false>, smem, 1 << 30, KS::GPB, 1) * KS::GPB;
+  }
   static cudaError_t dec_crt(const DecCrtArgs& p, cudaStream_t s) {
     const size_t smem = KS::smem_bytes(DT_COUNT);
     const int grid = grid_for(k_dec_crt<L, TPI>, smem, p.count, KS::GPB, 1);
@@ -145,7 +165,7 @@ template <int L, int TPI> struct Launch {
   }
 
   static constexpr ShapeOps ops() {
-    return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &powm_prog, &powm_prog_tbl_words, &dec_prep, &dec_tail, &dec_crt,
+    return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &powm_prog, &powm_prog_tbl_words, &dec_prep, &dec_tail, &dec_crt, &inv_block, &resident_groups,
                     &encrypt_comb, &encrypt_finish, &comb_build};
   }
 };

@@ -17,6 +17,7 @@ struct EncFinishArgs;
 struct CombArgs;
 struct DecPairArgs;
 struct DecCrtArgs;
+struct InvArgs;
 
 struct ShapeOps {
   int L, TPI, KP, GPB;   // KP: doubles per padded entry
@@ -31,6 +32,8 @@ struct ShapeOps {
   cudaError_t (*dec_prep)(const DecPrepArgs& p, cudaStream_t s);
   cudaError_t (*dec_tail)(const DecTailArgs& p, cudaStream_t s);
   cudaError_t (*dec_crt)(const DecCrtArgs& p, cudaStream_t s);
+  cudaError_t (*inv_block)(const InvArgs& p, bool unwind, cudaStream_t s);   // batched modular inverse, one level
+  int (*resident_groups)();
   cudaError_t (*encrypt_comb)(const EncCombArgs& p, cudaStream_t s);
   cudaError_t (*encrypt_finish)(const EncFinishArgs& p, cudaStream_t s);
   cudaError_t (*comb_build)(const CombArgs& p, cudaStream_t s);

@@ -10,7 +10,7 @@ What is different underneath (B200-first, not a translation):
   * exponent alignment gathers the rows that need scaling, raises them to 2^delta in one batched HE-mul and scatters
     them back with numpy indexing (reference: ipcl_python.py:528-741, per-element lists);
   * negative plaintext factors still invert the ciphertext first (ipcl_python.py:272-276, 426-441, 470-479) so results
-    are bit-identical to the reference's; the inverse is Python's pow(x, -1, n^2) instead of gmpy2.invert;
+    are bit-identical to the reference's; the inverses are computed in one batched device call (phe_invert);
   * sum()/dot()/@ reduce with a log-depth tree of batched HE-adds; sum() works for any length (the reference's passes
     a list where it needs a ciphertext container, ipcl_python.py:752-755).
 """
@@ -313,9 +313,21 @@ class PaillierEncryptedNumber:
 
     # ---- homomorphic multiply by plaintext ---------------------------------------------------------------------------
     def __invert_rows(self, packed: np.ndarray, rows: np.ndarray) -> None:
-        nsq = self.public_key.nsquare
-        vals = _limbs_to_ints(packed[rows])
-        packed[rows] = _ints_to_limbs([pow(v, -1, nsq) for v in vals], packed.shape[1])
+        """packed[rows] <- inverses modulo n^2, one batched device call (Montgomery's trick); the reference calls
+        gmpy2.invert per element (ipcl_python.py:272-276)."""
+        if rows.size == 0:
+            return
+        sub = ipclCipherText.from_packed(self.public_key.pubkey, np.ascontiguousarray(packed[rows]))
+        try:
+            packed[rows] = sub.modinv().to_packed()
+        except RuntimeError:
+            # some element shares a factor with n: reproduce the element-wise error of the reference's gmpy2.invert
+            nsq = self.public_key.nsquare
+            vals = _limbs_to_ints(packed[rows])
+            try:
+                packed[rows] = _ints_to_limbs([pow(v, -1, nsq) for v in vals], packed.shape[1])
+            except ValueError as e:
+                raise ZeroDivisionError("invert() no inverse exists") from e
 
     def _mul_encoded(self, packed: np.ndarray, pt_limbs: np.ndarray, ct_expo, pt_expo):
         """ct[i] ^ pt[i] with the reference's negative-plaintext rule: if pt >= n - max_int use (ct^-1)^(n - pt) so the

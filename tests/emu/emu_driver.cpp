@@ -157,6 +157,32 @@ int do_powm_prog(const uint32_t* base, int base_words, const double* base_mont, 
 }
 
 template <int L, int TPI>
+int do_inv_block(bool unwind, const uint32_t* c, int nwords, int count, int block, double* P, uint32_t* totals,
+                 const uint32_t* tinv, uint32_t* out, const double* n_e, uint64_t n0inv, const double* r2_e,
+                 const double* oneM_e, const double* one_e) {
+  using Env = EmuEnv<TPI>;
+  constexpr int KP = phe::Shape<L, TPI>::KP;
+  AlignedCopy ne(n_e, KP), r2(r2_e, KP), oneM(oneM_e, KP), one(one_e, KP);
+  std::vector<double> Pa((size_t)count * KP + 2);
+  double* Pp = (double*)(((uintptr_t)Pa.data() + 15) & ~(uintptr_t)15);
+  if (unwind) std::memcpy(Pp, P, (size_t)count * KP * 8);
+  for (int b = 0; b < count / block; ++b) {
+    Bufs<L, TPI> bufs;
+    const size_t first = (size_t)b * block;
+    run_group<TPI>([&] {
+      if (!unwind)
+        phe::item_inv_prefix<L, TPI, Env>(c + first * nwords, nwords, block, Pp + first * KP, totals + (size_t)b * nwords,
+                                          ne.p, n0inv, r2.p, oneM.p, one.p, bufs.sm);
+      else
+        phe::item_inv_unwind<L, TPI, Env>(c + first * nwords, nwords, block, Pp + first * KP, tinv + (size_t)b * nwords,
+                                          out + first * nwords, ne.p, n0inv, r2.p, oneM.p, one.p, bufs.sm);
+    });
+  }
+  if (!unwind) std::memcpy(P, Pp, (size_t)count * KP * 8);
+  return 0;
+}
+
+template <int L, int TPI>
 int do_dec_prep(const uint32_t* c, int hw, double* out_entries, int count, const double* n_e, uint64_t n0inv,
                 const double* r2_e, const double* k2_e) {
   using Env = EmuEnv<TPI>;
@@ -300,6 +326,12 @@ int emu_powm_prog(int shape, const uint32_t* base, int base_words, const double*
                   int nprog, uint32_t* out, int out_words, int count, const double* n_e, uint64_t n0inv,
                   const double* r2_e, const double* oneM_e, const double* one_e) {
   DISPATCH_SHAPE((do_powm_prog<L, TPI>(base, base_words, base_mont, prog, nprog, out, out_words, count, n_e, n0inv, r2_e, oneM_e, one_e)));
+}
+
+int emu_inv_block(int shape, int unwind, const uint32_t* c, int nwords, int count, int block, double* P,
+                  uint32_t* totals, const uint32_t* tinv, uint32_t* out, const double* n_e, uint64_t n0inv,
+                  const double* r2_e, const double* oneM_e, const double* one_e) {
+  DISPATCH_SHAPE((do_inv_block<L, TPI>(unwind != 0, c, nwords, count, block, P, totals, tinv, out, n_e, n0inv, r2_e, oneM_e, one_e)));
 }
 
 int emu_dec_prep(int shape, const uint32_t* c, int hw, double* out_entries, int count, const double* n_e,

@@ -239,3 +239,41 @@ def test_decrypt_pair_engine(emu, bits, L, shape):
     assert emu.emu_dec_crt(shape_id(*shape), P(halves[0]), P(halves[1]), half, P(mo), hw, len(cs), PD(cst), P64(n0)) == 0
     assert from_words(mo) == O.decrypt_batch(sk, cs)
     assert from_words(mo)[:len(ms)] == ms
+
+
+@pytest.mark.parametrize("L,TPI,bits,block", [(20, 1, 1024, 4), (20, 2, 2048, 5), (15, 4, 3072, 4)])
+def test_batched_inverse_blocks(emu, L, TPI, bits, block):
+    """Montgomery's trick as run by k_inv_block: prefix products + block totals, then the unwind given the inverse of
+    each total (computed here with Python ints) == element-wise pow(c, -1, N)."""
+    rng = random.Random(bits + block)
+    nw = bits // 32
+    N = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+    mc = mont_consts(N, L, TPI)
+    import math
+    cs = []
+    while len(cs) < 3 * block - 2:
+        c = rng.randrange(1, N)
+        if math.gcd(c, N) == 1:
+            cs.append(c)
+    cs += [1, N - 1]
+    cw = to_words(cs, nw)
+    nb = len(cs) // block
+    KP = len(mc["n"])
+    P_ = np.zeros((len(cs), KP), dtype=np.float64)
+    totals = np.zeros((nb, nw), dtype=np.uint32)
+    rc = emu.emu_inv_block(shape_id(L, TPI), 0, P(cw), nw, len(cs), block, PD(P_), P(totals), None, None,
+                           PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"]), PD(mc["oneM"]), PD(mc["one"]))
+    assert rc == 0
+    want_tot = []
+    for b in range(nb):
+        t = 1
+        for c in cs[b * block:(b + 1) * block]:
+            t = t * c % N
+        want_tot.append(t)
+    assert from_words(totals) == want_tot
+    tinv = to_words([pow(t, -1, N) for t in want_tot], nw)
+    out = np.zeros_like(cw)
+    rc = emu.emu_inv_block(shape_id(L, TPI), 1, P(cw), nw, len(cs), block, PD(P_), None, P(tinv), P(out),
+                           PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"]), PD(mc["oneM"]), PD(mc["one"]))
+    assert rc == 0
+    assert from_words(out) == [pow(c, -1, N) for c in cs]

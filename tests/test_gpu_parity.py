@@ -339,3 +339,22 @@ def test_device_csprng_chacha20_kat_and_internal_r(key2048):
     assert np.array_equal(sk.decrypt(c1), m) and np.array_equal(sk.decrypt(c2), m)
     rows = {c.tobytes() for c in np.concatenate([c1, c2])}
     assert len(rows) == 16                      # fresh r for every element of every call
+
+
+@pytest.mark.parametrize("count", [1, 5, 16, 17, 1000, 20011])
+def test_batched_modular_inverse(key2048, count):
+    """phe_invert (Montgomery's trick on the device, recursive over block totals) == pow(c, -1, n^2) row by row."""
+    pk_o, sk_o, pk, sk = key2048
+    rng = random.Random(SEED + count)
+    cs = _rand_cts(pk_o, rng, min(count, 40))
+    cs = (cs * (count // len(cs) + 1))[:count]          # repeated rows are fine: every row is inverted on its own
+    cs[0] = 1
+    cs[-1] = pk_o.nsquare - 1
+    got = pk.invert(capi.ints_to_array(cs, 128))
+    inv = {c: pow(c, -1, pk_o.nsquare) for c in set(cs)}
+    assert capi.array_to_ints(got) == [inv[c] for c in cs]
+    if count >= 17:
+        bad = list(cs)
+        bad[count // 2] = sk_o.p * 12345                # shares the factor p with n
+        with pytest.raises(RuntimeError):
+            pk.invert(capi.ints_to_array(bad, 128))
