@@ -103,6 +103,10 @@ int phe_keygen(int bits, uint32_t* n_out, uint32_t* p_out, uint32_t* q_out);
  *   -- the deterministic hook used by the parity tests. */
 int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uint32_t* r, int r_words,
                 int make_secure, uint32_t* ct_out);
+/* Same with plaintext rows of m_words <= n_words words each (upper words are zero): a batch of 53-bit fixed-point
+ * mantissas is 2 words per element instead of n_words = 64, i.e. 32 times less to copy to the device. */
+int phe_encrypt_compact(const phe_pubkey* pk, const uint32_t* m, int m_words, size_t count, const uint32_t* r,
+                        int r_words, int make_secure, uint32_t* ct_out);
 
 /* ipcl::PublicKey::applyObfuscator(vector<BigNumber>&) (ipcl_bindings_classes.cpp:71-83): ct *= obf(r). */
 int phe_obfuscate(const phe_pubkey* pk, uint32_t* ct_inout, size_t count, const uint32_t* r, int r_words);

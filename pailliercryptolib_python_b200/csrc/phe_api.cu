@@ -520,8 +520,9 @@ int random_r_dev(const phe_pubkey* pk, size_t count, int* r_words, cudaStream_t 
 }
 
 int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
-                     uint32_t* d_ct, cudaStream_t s) {
+                     uint32_t* d_ct, cudaStream_t s, int m_words = 0) {
   const int cw = 2 * pk->n_words;
+  if (m_words <= 0) m_words = pk->n_words;   // stride of the plaintext rows
   if (count == 0) return 0;
   if (!d_r || pk->djn) {
     if (d_r) {
@@ -531,7 +532,7 @@ int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, co
     for (size_t off = 0; off < count; off += CHUNK) {
       const int c = (int)std::min(CHUNK, count - off);
       EncCombArgs a{};
-      a.m_w = d_m + off * pk->n_words; a.m_words = pk->n_words;
+      a.m_w = d_m + off * (size_t)m_words; a.m_words = m_words;
       a.r_w = d_r ? d_r + off * r_words : nullptr; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
       a.out_w = d_ct + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
       CUDA_TRY(pk->ops->encrypt_comb(a, s));
@@ -544,7 +545,7 @@ int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, co
     const int c = (int)std::min(CHUNK, count - off);
     PHE_TRY(obfuscators_dev(pk, d_r + off * r_words, r_words, c, pk->ws_c.p, s));
     EncFinishArgs f{};
-    f.m_w = d_m + off * pk->n_words; f.m_words = pk->n_words; f.obf_w = pk->ws_c.p;
+    f.m_w = d_m + off * (size_t)m_words; f.m_words = m_words; f.obf_w = pk->ws_c.p;
     f.out_w = d_ct + off * cw; f.out_words = cw; f.count = c; f.ctx = pk->ctx;
     CUDA_TRY(pk->ops->encrypt_finish(f, s));
   }
@@ -949,8 +950,14 @@ int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint
 // ---- host-buffer entry points ------------------------------------------------------------------------------
 int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uint32_t* r, int r_words,
                 int make_secure, uint32_t* ct_out) {
+  return phe_encrypt_compact(pk, m, pk ? pk->n_words : 0, count, r, r_words, make_secure, ct_out);
+}
+
+int phe_encrypt_compact(const phe_pubkey* pk, const uint32_t* m, int m_words, size_t count, const uint32_t* r,
+                        int r_words, int make_secure, uint32_t* ct_out) {
   try {
     if (!pk || !m || !ct_out) return fail("phe_encrypt: null argument");
+    if (m_words < 1 || m_words > pk->n_words) return fail("phe_encrypt: m_words must be in [1, n_words]");
     if (count == 0) return 0;
     std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));
@@ -960,9 +967,9 @@ int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uin
     const bool device_r = make_secure && !r && pk->djn;   // DJN: r uniform in [0, 2^randbits), drawn on the device
     if (make_secure && !r && !device_r) { PHE_TRY(make_r_host(pk, count, rgen, &r_words)); r = rgen.data(); }
     if (!make_secure) r = nullptr;
-    PHE_TRY(pk->ws_a.ensure(count * pk->n_words));
+    PHE_TRY(pk->ws_a.ensure(count * (size_t)m_words));
     PHE_TRY(pk->ws_b.ensure(count * cw));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, m, count * pk->n_words * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, m, count * (size_t)m_words * 4, cudaMemcpyHostToDevice, 0));
     const uint32_t* d_r = nullptr;
     if (device_r) {
       PHE_TRY(random_r_dev(pk, count, &r_words, 0));
@@ -972,7 +979,7 @@ int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uin
       CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice, 0));
       d_r = pk->ws_r.p;
     }
-    int rc = encrypt_dev_impl(pk, pk->ws_a.p, count, d_r, r_words, pk->ws_b.p, 0);
+    int rc = encrypt_dev_impl(pk, pk->ws_a.p, count, d_r, r_words, pk->ws_b.p, 0, m_words);
     if (!rc) {
       cudaError_t e = cudaMemcpy(ct_out, pk->ws_b.p, count * cw * 4, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) rc = fail(std::string("phe_encrypt D2H: ") + cudaGetErrorString(e));

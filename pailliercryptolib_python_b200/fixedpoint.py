@@ -177,12 +177,13 @@ def _sub_from_modulus(n_limbs, mag_lo, mag_hi, rows):
     return out
 
 
-def encode_array(values, n, max_int, words):
+def encode_array(values, n, max_int, words, compact=False):
     """Vectorised FixedPointNumber.encode over a 1-D array: returns (limbs [N, words] uint32, exponents [N] int64).
 
     float arrays: exponent = 53 - frexp(x)[1], mantissa = round(x * 2^exponent) (|mantissa| < 2^53, exact);
     int16/32/64 arrays: exponent 0.  Anything else (object arrays, Python big ints, mixed lists) goes through the scalar
     codec element by element so the results are identical by construction.
+    compact=True allows a [N, 2] result when every encoding is a non-negative 64-bit value (upper words all zero).
     """
     if isinstance(values, np.ndarray):
         arr = values
@@ -225,6 +226,12 @@ def encode_array(values, n, max_int, words):
         return limbs, expo
     lo = (mag & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     hi = (mag >> np.uint64(32)).astype(np.uint32)
+    if compact and words > 2 and not neg.any():
+        # all magnitudes fit two words: hand back [count, 2] (the C ABI takes short plaintext rows: 32x less to copy)
+        limbs = np.empty((count, 2), dtype=np.uint32)
+        limbs[:, 0] = lo
+        limbs[:, 1] = hi
+        return limbs, expo
     limbs = np.zeros((count, words), dtype=np.uint32)
     limbs[:, 0] = lo
     if words > 1:

@@ -109,7 +109,7 @@ class PaillierPublicKey:
                 raise ValueError("PaillierPublicKey.encrypt: input value(s) should be integer or float")
         elif arr.ndim != 1 or arr.dtype.kind not in "iuf":
             raise ValueError("PaillierPublicKey.encrypt: input value(s) should be integer or float")
-        limbs, expos = encode_array(values, self.n, self.max_int, self.n_words)
+        limbs, expos = encode_array(values, self.n, self.max_int, self.n_words, compact=True)
         ct = self.pubkey.encrypt(ipclPlainText.from_packed(limbs), apply_obfuscator)
         return PaillierEncryptedNumber(self, ct, exponents=expos, length=len(expos))
 
