@@ -285,7 +285,7 @@ def run_gpu(args):
     # dominant kernel: the two CRT halves of decrypt -- k_dec_pair (p-adic pair engine) for balanced keys, else k_powm
     pair = [capi.pair_block(sk, y) for y in (0, 1)]
     if pair[0] and ktimes["k_dec_pair"][1]:
-        dom_name, (dom_ms, dom_n) = "k_dec_pair<20> (decrypt: L_x(c^(x-1) mod x^2) h_x mod x, one launch each for x = p, q, one ciphertext per lane)", ktimes["k_dec_pair"]
+        dom_name, (dom_ms, dom_n) = "k_dec_pair<20> (decrypt: L_x(c^(x-1) mod x^2) h_x mod x, x = p, q in one launch, one ciphertext per lane, warp-granular units)", ktimes["k_dec_pair"]
         Lp = pair[0]["L"]
         passes = 0
         for blk in pair:      # a square is 2 reduction passes, a multiplication 3; each pass = 2 L^2 limb products

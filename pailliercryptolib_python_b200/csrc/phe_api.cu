@@ -342,7 +342,7 @@ struct phe_privkey {
   int ebits[2] = {0, 0};
   int hw = 0;  // words of x^2 (= n_words)
   uint64_t n0invs[3] = {0, 0, 0};
-  mutable DevBuf ws_in, ws_out, ws_mont[2], ws_u[2], ws_tbl;
+  mutable DevBuf ws_in, ws_out, ws_mont[2], ws_u[2], ws_tbl, ws_sched;
   mutable std::mutex mu;
   mutable bool dev_ready = false;
   std::vector<uint32_t> h_ctx[2], h_exp[2], h_prog[2], h_tail;   // host copies uploaded on first compute call
@@ -645,19 +645,21 @@ int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count,
   constexpr int slots = 1 << (PROG_WS - 1);
   for (int y = 0; y < 2; ++y) PHE_TRY(sk->ws_u[y].ensure(chunk * half));
   PHE_TRY(sk->ws_tbl.ensure(po->tbl_words((int)chunk, slots)));
+  PHE_TRY(sk->ws_sched.ensure(1024));
   for (size_t off = 0; off < count; off += CHUNK) {
     const int c = (int)std::min(CHUNK, count - off);
+    const int L = sk->pairb[0].L;
+    DecPairArgs a{};
+    a.c_w = d_ct + off * cw; a.c_words = cw; a.chunk_words = half; a.out_words = half; a.count = c; a.slots = slots;
     for (int y = 0; y < 2; ++y) {
-      const int L = sk->pairb[y].L;
-      DecPairArgs a{};
-      a.c_w = d_ct + off * cw; a.c_words = cw; a.chunk_words = half; a.out_words = half; a.count = c; a.slots = slots;
-      a.prog = sk->d_pair_prog[y].p; a.out_w = sk->ws_u[y].p;
-      a.dcon = reinterpret_cast<const double*>(sk->d_pair_mod[y].p) + L;
-      a.cst = reinterpret_cast<const double*>(sk->d_pair_cst[y].p);
-      a.n0inv = sk->pairb[y].n0inv;
-      a.tbl = reinterpret_cast<double*>(sk->ws_tbl.p);   // the two launches run back to back on the stream
-      CUDA_TRY(po->dec_pair(a, sk->pairb[y].mod.data(), s));
+      a.prog[y] = sk->d_pair_prog[y].p; a.out_w[y] = sk->ws_u[y].p;
+      a.dcon[y] = reinterpret_cast<const double*>(sk->d_pair_mod[y].p) + L;
+      a.cst[y] = reinterpret_cast<const double*>(sk->d_pair_cst[y].p);
+      a.n0inv[y] = sk->pairb[y].n0inv;
     }
+    a.tbl = reinterpret_cast<double*>(sk->ws_tbl.p);
+    a.sched = reinterpret_cast<int*>(sk->ws_sched.p);
+    CUDA_TRY(po->dec_pair(a, sk->pairb[0].mod.data(), sk->pairb[1].mod.data(), s));
     DecCrtArgs t{};
     t.mp_w = sk->ws_u[0].p; t.mq_w = sk->ws_u[1].p; t.half_words = half; t.m_w = d_m + off * hw; t.m_words = hw;
     t.count = c; t.cst = reinterpret_cast<const double*>(sk->d_tail.p);
@@ -847,7 +849,7 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
 void phe_privkey_destroy(phe_privkey* sk) {
   if (!sk) return;
   for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->d_pair_mod[0], &sk->d_pair_mod[1], &sk->d_pair_cst[0], &sk->d_pair_cst[1], &sk->d_pair_prog[0], &sk->d_pair_prog[1], &sk->ws_in, &sk->ws_out,
-                    &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl}) b->release();
+                    &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl, &sk->ws_sched}) b->release();
   delete sk;
 }
 int phe_privkey_get_p(const phe_privkey* sk, uint32_t* o) { if (!sk || !o) return fail("null"); sk->p.to_words(o, sk->hw); return 0; }

@@ -237,38 +237,49 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
 }
 
 // ---- decrypt on the p-adic pair engine: one (ciphertext, modulus) per lane ---------------------------------------
-// One launch per modulus (x = p, then x = q).  The limbs of x travel inside the kernel parameters: after unrolling
-// every use has a compile-time offset, so the N-part products read them as constant-bank operands of the DFMA
-// itself (c[0x0][..]) -- no load instructions and no registers for the modulus.
+// Work unit = one warp's worth (32 ciphertexts) of ONE modulus: unit u -> modulus u & 1 (0: p, 1: q), ciphertexts
+// [32 (u >> 1), +32).  Warps pull units from a global counter (there are no shuffles in this kernel, so warps of a CTA
+// may run different numbers of units).  100 000 ciphertexts are 6250 units for 1184 resident warps = 5.28 per warp:
+// CTA-granular loops, or one launch per modulus, pay 6 rounds (tools/tail_probe.py: 2.64 waves cost exactly 3).  Here
+// the first 5 x 1184 units go to whoever asks, and the remaining 330 only to the warps of the FIRST CTA that landed on
+// each SM, i.e. at most one extra unit per SM sub-partition: 11 unit-times per sub-partition instead of 12.
+// The limbs of both moduli travel inside the kernel parameters and are selected into registers once per unit.
 struct DecPairArgs {
   const uint32_t* c_w;       // [count][c_words]
   int c_words, chunk_words;
-  const uint32_t* prog;      // pair-engine program for x (paillier_items.cuh: PairOp)
-  uint32_t* out_w;           // m_x: [count][out_words]
+  const uint32_t* prog[2];   // pair-engine programs for x = p, q (paillier_items.cuh: PairOp)
+  uint32_t* out_w[2];        // m_p, m_q: [count][out_words]
   int out_words;
   int count;
-  const double* dcon;        // [L + 1] limbs of D = ceil(R / x) x  (global; staged to shared memory: indexed by row)
-  uint64_t n0inv;
-  const double* cst;         // [PC_COUNT][2][L] constant pairs
+  const double* dcon[2];     // [L + 1] limbs of D = ceil(R / x) x  (global; staged to shared memory: indexed by row)
+  uint64_t n0inv[2];
+  const double* cst[2];      // [PC_COUNT][2][L] constant pairs
   double* tbl;               // [gridDim.x * NT / 32][slots][2][L][32]
   int slots;
+  int* sched;                // zeroed before the launch: [0] phase-1 counter, [1] phase-2 counter, [2 + smid] CTA ranks
 };
-template <int L> struct ModLimbs { double v[L]; };
+template <int L> struct ModLimbs { double v[2][L]; };
 
 template <int L> struct PairShape {
-  static constexpr int LE = (L + 2) & ~1;                       // L + 1 entries of E, padded to even
+  static constexpr int LE = (L + 2) & ~1;                       // L + 1 entries of E / D, padded to even
   static constexpr int PER_LANE = 4 * L + LE;                   // doubles of shared memory per lane
-  static constexpr size_t smem_bytes() { return (size_t)(LE + PER_LANE * NT) * sizeof(double); }
+  static constexpr size_t smem_bytes() { return (size_t)(2 * LE + PER_LANE * NT) * sizeof(double); }
 };
 
 template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(const DecPairArgs p, const ModLimbs<L> mod) {
   using PE = DevPairEnv;
   using PS = PairShape<L>;
   extern __shared__ __align__(16) double smem[];
-  for (int i = threadIdx.x; i < L + 1; i += NT) smem[i] = p.dcon[i];
+  __shared__ int s_rank;
+  for (int i = threadIdx.x; i < 2 * (L + 1); i += NT) smem[(i / (L + 1)) * PS::LE + i % (L + 1)] = p.dcon[i / (L + 1)][i % (L + 1)];
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_rank = atomicAdd(&p.sched[2 + smid], 1);
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, col = threadIdx.x & 31;
-  double* wbase = smem + PS::LE + (size_t)warp * PS::PER_LANE * 32 + col;
+  double* wbase = smem + 2 * PS::LE + (size_t)warp * PS::PER_LANE * 32 + col;
   PairSmem<PE> sm;
   sm.xs0 = wbase;
   sm.x1 = wbase + L * 32;
@@ -276,12 +287,33 @@ template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(const DecPa
   sm.y1 = wbase + 3 * L * 32;
   sm.e = reinterpret_cast<int64_t*>(wbase + 4 * L * 32);
   double* tbl = p.tbl + ((size_t)blockIdx.x * (NT / 32) + warp) * ((size_t)p.slots * 2 * L * 32) + col;
-  for (int base = blockIdx.x * NT; base < p.count; base += gridDim.x * NT) {
-    const int want = base + (int)threadIdx.x;
-    const int item = want < p.count ? want : p.count - 1;
-    item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog,
-                         want < p.count ? p.out_w + (size_t)item * p.out_words : nullptr, p.out_words, mod.v,
-                         smem, p.n0inv, p.cst, tbl, sm);
+
+  const int blocks = (p.count + 31) / 32;
+  const int units = 2 * blocks;
+  const int warps = gridDim.x * (NT / 32);
+  const int rem = units % warps;
+  const int units1 = units - rem;                           // phase 1: a whole number of rounds
+  // phase 2 (the remainder) is reserved for the first CTA of each SM when it fits one unit per such warp
+  const bool phase2 = (s_rank == 0) || (2 * rem > warps);
+#pragma unroll 1
+  for (int phase = 0; phase < 2; ++phase) {
+    if (phase == 1 && !phase2) break;
+#pragma unroll 1
+    for (;;) {
+      int u = 0;
+      if (col == 0) u = atomicAdd(&p.sched[phase], 1);
+      u = __shfl_sync(0xffffffffu, u, 0) + (phase ? units1 : 0);
+      if (u >= (phase ? units : units1)) break;
+      const int y = u & 1;
+      const int want = (u >> 1) * 32 + col;
+      const int item = want < p.count ? want : p.count - 1;
+      double n[L];
+#pragma unroll
+      for (int j = 0; j < L; ++j) n[j] = y ? mod.v[1][j] : mod.v[0][j];
+      item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog[y],
+                           want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
+                           smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+    }
   }
 }
 

@@ -172,15 +172,18 @@ template <int L, int TPI> struct Launch {
 
 // Launcher of the one-bignum-per-lane pair engine (L = limbs of p, q).
 template <int L> struct PairLaunch {
-  static int grid(int count) {
-    return grid_for(k_dec_pair<L>, PairShape<L>::smem_bytes(), count, NT, 1);
+  static int grid(int count) {   // both moduli: 2 * ceil(count / 32) warp units, NT / 32 warps per CTA
+    const int units = 2 * ((count + 31) / 32);
+    return grid_for(k_dec_pair<L>, PairShape<L>::smem_bytes(), units, NT / 32, 1);
   }
-  // mod: L limbs of x (doubles)
-  static cudaError_t dec_pair(const DecPairArgs& p, const double* mod, cudaStream_t s) {
+  // mod_p, mod_q: L limbs each (doubles); p.sched: >= 2 + number of SMs ints, zeroed here on the stream
+  static cudaError_t dec_pair(const DecPairArgs& p, const double* mod_p, const double* mod_q, cudaStream_t s) {
     const size_t smem = PairShape<L>::smem_bytes();
     const int g = grid(p.count);
     ModLimbs<L> m;
-    for (int i = 0; i < L; ++i) m.v[i] = mod[i];
+    for (int i = 0; i < L; ++i) { m.v[0][i] = mod_p[i]; m.v[1][i] = mod_q[i]; }
+    cudaError_t e = cudaMemsetAsync(p.sched, 0, (size_t)(2 + sm_count()) * sizeof(int), s);
+    if (e != cudaSuccess) return e;
     { TimedLaunch tl_(KK_DEC_PAIR, s);
     k_dec_pair<L><<<g, NT, smem, s>>>(p, m);
     }

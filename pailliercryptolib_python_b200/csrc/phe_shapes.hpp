@@ -44,7 +44,7 @@ const ShapeOps* shape_ops(int L, int TPI);   // nullptr if not built
 // p-adic pair engine (decrypt halves, one bignum of L limbs per lane)
 struct PairOps {
   int L;
-  cudaError_t (*dec_pair)(const DecPairArgs& p, const double* mod_limbs, cudaStream_t s);   // one modulus per launch
+  cudaError_t (*dec_pair)(const DecPairArgs& p, const double* mod_p, const double* mod_q, cudaStream_t s);
   size_t (*tbl_words)(int count, int slots);   // table scratch (u32 words) for a launch
 };
 const PairOps* pair_ops(int L);   // nullptr if not built
