@@ -30,6 +30,9 @@ UNIT = "ops/s"
 SEED = 20240611
 
 # W(op) in 32x32->64 multiply-accumulates, SURVEY.md 8(d): MM(k) = 2k^2 + k, NMM(E) = E + ceil(E/5) + 32
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_dec_pair launch at N = 100 000 (ncu --set full, r01)
+TRAFFIC_K_DEC_PAIR = 7.48e9 + 2.10e9
+
 def _mm(k): return 2 * k * k + k
 def _nmm(e): return e + (e + 4) // 5 + 32
 W_ENC_DJN_2048 = _nmm(1024) * _mm(128) + 2 * _mm(128)   # 41.55 M
@@ -309,9 +312,9 @@ def run_gpu(args):
             "bound": "int_pipe", "kernel": dom_name,
             "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one k_dec_pair launch, ncu --set full, r01
-            # (profiles/r01_ncu_k_dec_pair_summary.txt): 3.52 + 1.00 GB against 64 MB of algorithmic bytes -- the
-            # per-lane window tables (388 MB per launch) do not fit the 126 MB L2; at 66 GB/s it is 1 % of HBM bandwidth
-            "traffic": 4.52e9 if (pair[0] and N == 100000) else None, "launch_ms": per_launch_ms, "launches": dom_n,
+            # (profiles/r01_ncu_k_dec_pair_summary.txt): ~7 + 2 GB against 102 MB of algorithmic bytes -- the
+            # per-lane window tables (388 MB) do not fit the 126 MB L2; at ~70 GB/s it is 1 % of HBM bandwidth
+            "traffic": TRAFFIC_K_DEC_PAIR if (pair[0] and N == 100000) else None, "launch_ms": per_launch_ms, "launches": dom_n,
             "peak_source": "measured live: phe_int_pipe_peak (IMAD.WIDE.U32 issue rate, all SMs)",
             "algorithmic_mac32_per_op": W_DEC_2048,
             "note": "algorithmic MAC32 of the reference algorithm (SURVEY 8d: two 2048-bit windowed modexps) against the "
