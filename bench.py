@@ -367,7 +367,9 @@ def run_gpu(args):
             "dtype": "f64 (exact 52-bit integer limbs, 64-bit integer accumulators)", "data": "synthetic",
             "config": {"workload": "2048-bit bench key (DJN), batch=%d encrypt+decrypt per GPU (BASELINE configs[1])" % N,
                        "key_bits": 2048, "batch_per_gpu": N, "scheme": "DJN", "ops_per_step": 2 * N * world,
-                       "l2": "flushed between timed iterations (256 MiB memset inside the timed region)"},
+                       "l2": "flushed between timed iterations (256 MiB memset inside the timed region)",
+                       "comb_bits": pk.comb_bits,
+                       "comb_table": "fixed-base comb table of the DJN obfuscator hs, %d-bit digits, built once per key during warm-up (outside the timed region)" % pk.comb_bits},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernels": kernels, "secondary": secondary,
         }

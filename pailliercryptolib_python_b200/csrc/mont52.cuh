@@ -300,6 +300,93 @@ PHE_HD void montmul(double (&r)[L], const double (&a)[L], const double* b, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// montmul_e: montmul with the run-time extras the multi-lane pair engine (npair_items.cuh) needs; ONE body serves
+// every pass of a pair product (and the final plain product), so a kernel has a single copy of the row loop:
+//   ein   (or null): addend E, K + 1 exact limbs as integers in the padded [TPI][LP] layout, top limb at [TPI * LP]:
+//                    r = (a b + E + m n) / R.  Lane 0 adds digit i to column 0 of row i.
+//   cap   (or null): plain == false: the quotient digits q_i (integers, padded layout; lane 0 writes)
+//                    plain == true : the low half of the product (limb i = retired column i)
+//   plain          : q is forced to 0: r = floor((a b + E) / R), i.e. an ordinary 2K-limb product with cap as low half.
+// cap may alias ein (digit i + 1 of ein is read in the iteration that writes digit i of cap).
+// ------------------------------------------------------------------------------------------------
+template <int L, int TPI, class Env>
+PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, const double* n_entry, uint64_t n0inv,
+                      const uint64_t* ein, uint64_t* cap, bool plain) {
+  static_assert(L >= 2 && L <= 64, "limbs per lane out of range");
+  constexpr int K = L * TPI;
+  constexpr int U = Unroll<L>::U;
+  const int lane = Env::lane();
+  const double* n = n_entry + lane * Pad<L>::LP;
+  const uint64_t topmask = (lane == TPI - 1) ? 0ull : ~0ull;
+  const uint64_t qmask = plain ? 0ull : M52;
+  const bool lead = (lane == 0);
+  constexpr uint64_t INIT = 0ull - bias_of(2 * L, 2 * L);
+  uint64_t acc[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) acc[j] = 0ull - bias_of(2 * (j + 1), 2 * j);
+
+  uint64_t topA, q;
+  double qd;
+  {  // prologue: A-part of row 0 and its quotient digit
+    const double b0 = b[0];
+    uint64_t h;
+    mac_first(acc[0], a[0], b0, h);
+    if (ein && lead) acc[0] += ein[0];
+    q = bcast64<Env>((acc[0] * n0inv) & qmask, 0);
+    mac_span<L, 1, L>(acc, a, b0, h, 0);
+    topA = h;
+    qd = limb_of(q);
+  }
+#pragma unroll 1
+  for (int row0 = 0; row0 < K; row0 += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {   // row i = row0 + u; column c of row i lives in acc[(c + u) % L]
+      const int row = row0 + u;
+      const bool last = (u == U - 1) && (row == K - 1);
+      uint64_t hN, hA = 0;
+      const double n0 = n[0], n1 = n[1];
+      mac_first(acc[u % L], n0, qd, hN);
+      {
+        const double ph = fma_rz(n1, qd, TWO104);
+        const double pl = fma_rz(n1, qd, TWO104P52 - ph);
+        const uint64_t low = acc[u % L];                  // column 0 is complete: retire it
+        if (cap && lead) cap[padded_index<L>(row)] = plain ? (low & M52) : q;
+        acc[(u + 1) % L] += d2u(pl) + hN + (low >> LW);
+        hN = d2u(ph);
+        acc[u % L] = from_above64<Env>(low & M52) & topmask;   // becomes the new top column (column L of row i)
+      }
+      double bn = 0.0;
+      if (!last) {
+        bn = b[padded_index<L>(row + 1)];
+        mac_first(acc[(u + 1) % L], a[0], bn, hA);
+        if (ein && lead) acc[(u + 1) % L] += ein[padded_index<L>(row + 1)];
+        q = bcast64<Env>((acc[(u + 1) % L] * n0inv) & qmask, 0);
+      }
+      mac_span<L, 2, L>(acc, n, qd, hN, u);
+      acc[u % L] += topA + hN + INIT;
+      if (!last) {
+        mac_span<L, 1, L>(acc, a, bn, hA, u + 1);
+        topA = hA;
+        qd = limb_of(q);
+      }
+    }
+    if (U != L) {   // rotate back: column c returns to acc[c]
+      uint64_t t[L];
+#pragma unroll
+      for (int j = 0; j < L; ++j) t[j] = acc[(j + U) % L];
+#pragma unroll
+      for (int j = 0; j < L; ++j) acc[j] = t[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < L; ++j) acc[j] += bias_of(2 * (j + 1), 2 * j);
+  if (ein && lead) acc[0] += ein[TPI * Pad<L>::LP];        // top limb of E: column K
+  normalize_exact<L, TPI, Env>(acc);
+#pragma unroll
+  for (int j = 0; j < L; ++j) r[j] = limb_of(acc[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // p-adic pair arithmetic for the CRT half of decrypt:  numbers mod x^2 (x = p or q) are kept as pairs (X0, X1),
 // X0, X1 < 2x, meaning (X0 + X1 x) R^-1 mod x^2 with R = 2^(52 L) >= 2^8 x.  With  X0 Y0 = u R - m x  (u, m the
 // result and the quotient of an ordinary Montgomery reduction mod x) one gets

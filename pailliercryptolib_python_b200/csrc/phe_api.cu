@@ -172,6 +172,14 @@ struct DevBuf {
     words = want;
     return 0;
   }
+  int ensure_exact(size_t w) {   // large long-lived tables: no geometric slack
+    if (w <= words) return 0;
+    release();
+    cudaError_t e = cudaMalloc(&p, w * 4);
+    if (e != cudaSuccess) { p = nullptr; return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    words = w;
+    return 0;
+  }
   void release() { if (p) cudaFree(p); p = nullptr; words = 0; }
 };
 
@@ -321,7 +329,8 @@ struct phe_pubkey {
   int nwin = 0;
   mutable int comb_bits = 0;      // digit width of the comb table once built (0: not built yet)
   int comb_bits_wanted = 0;       // 0: choose from the free device memory
-  mutable bool comb_ready = false;
+  mutable bool comb_ready = false, comb_wide = false;
+  mutable size_t comb_seen = 0;   // elements encrypted so far under the automatic width (promotion counter)
   mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_r, ws_tbl;  // op workspaces
   mutable DevBuf d_prog_n;                         // classic scheme: sliding-window program of the exponent n
   std::vector<uint32_t> h_prog_n;
@@ -362,27 +371,39 @@ int pk_ensure_device(const phe_pubkey* pk) {
   return 0;
 }
 
-// Comb table of the DJN obfuscator, built on the first obfuscated encrypt.  Digit width: as wide as the device memory
-// comfortably allows (the table is nwin * 2^wb entries: 2.7 GB at wb = 16 for a 2048-bit key, 15 ms to build), because
-// the number of Montgomery products per encrypt is randbits / wb + 2.  PHE_COMB_BITS or phe_pubkey_set_comb_bits override.
-int pk_ensure_comb(const phe_pubkey* pk) {
-  if (pk->comb_ready) return 0;
+// Comb table of the DJN obfuscator.  The number of Montgomery products per encrypt is randbits / wb + 2, so the digit
+// width wb is as wide as the device memory comfortably allows: nwin * 2^wb entries, i.e. 35 GB at wb = 20 for a
+// 2048-bit key (52 + 2 products, ~0.2 s to build) on an idle 180 GB B200, 2.7 GB at wb = 16 (64 + 2 products, 15 ms).
+// A key starts on a small table (wb = 12: 225 MB, < 1 ms) and is promoted to the wide one once it has encrypted
+// COMB_PROMOTE elements, so that a caller with a handful of values never waits for (or holds) the large table.
+// PHE_COMB_BITS or phe_pubkey_set_comb_bits pin the width.
+constexpr size_t COMB_PROMOTE = 32768;
+int pk_ensure_comb(const phe_pubkey* pk, size_t count) {
   if (!pk->djn) return fail("comb table requested for a non-DJN key");
   int wb = pk->comb_bits_wanted;
   if (wb <= 0) { const char* e = getenv("PHE_COMB_BITS"); if (e) wb = atoi(e); }
   const size_t entry_bytes = EW(pk->ops) * 4;
   auto table_bytes = [&](int w) { return (size_t)((pk->randbits + w - 1) / w) * ((size_t)1 << w) * entry_bytes; };
-  if (wb <= 0) {
+  if (wb > 0) {
+    if (pk->comb_ready) return 0;
+  } else {
+    pk->comb_seen += count;
+    const bool wide = pk->comb_seen >= COMB_PROMOTE;
+    if (pk->comb_ready && (pk->comb_wide || !wide)) return 0;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    wb = 16;
-    while (wb > 8 && (table_bytes(wb) > free_b / 8 || table_bytes(wb) > ((size_t)6 << 30))) wb -= 2;
+    if (pk->comb_ready) free_b += table_bytes(pk->comb_bits);   // the current table is released first
+    wb = wide ? 20 : 12;
+    while (wb > 8 && (table_bytes(wb) > free_b / 4 || table_bytes(wb) > ((size_t)40 << 30))) wb -= 2;
+    if (wide) pk->comb_wide = true;
+    if (pk->comb_ready && wb <= pk->comb_bits) return 0;
+    if (pk->comb_ready) { CUDA_TRY(cudaDeviceSynchronize()); pk->d_comb.release(); pk->comb_ready = false; }
   }
   if (wb < 1) wb = 1;
-  if (wb > 16) wb = 16;
+  if (wb > 22) wb = 22;
   pk->comb_bits = wb;
   const_cast<phe_pubkey*>(pk)->nwin = (pk->randbits + wb - 1) / wb;
-  PHE_TRY(pk->d_comb.ensure(table_bytes(wb) / 4));
+  PHE_TRY(pk->d_comb.ensure_exact(table_bytes(wb) / 4));
   std::vector<uint32_t> hsw(2 * (size_t)pk->n_words);
   pk->hs.to_words(hsw.data(), hsw.size());
   DevBuf dhs;
@@ -455,7 +476,7 @@ int obfuscators_dev(const phe_pubkey* pk, const uint32_t* d_r, int r_words, size
   const int cw = 2 * pk->n_words;
   if (pk->djn) {
     // comb kernel with m = 0 gives (1 + 0) * obf
-    PHE_TRY(pk_ensure_comb(pk));
+    PHE_TRY(pk_ensure_comb(pk, count));
     PHE_TRY(pk->ws_d.ensure((size_t)pk->n_words));
     CUDA_TRY(cudaMemsetAsync(pk->ws_d.p, 0, (size_t)pk->n_words * 4, s));
     for (size_t off = 0; off < count; off += CHUNK) {
@@ -526,7 +547,7 @@ int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, co
   if (count == 0) return 0;
   if (!d_r || pk->djn) {
     if (d_r) {
-      PHE_TRY(pk_ensure_comb(pk));
+      PHE_TRY(pk_ensure_comb(pk, count));
       if ((size_t)r_words * 32 < (size_t)pk->randbits) return fail("phe_encrypt: r_words too small for randbits");
     }
     for (size_t off = 0; off < count; off += CHUNK) {
@@ -773,7 +794,7 @@ void phe_pubkey_destroy(phe_pubkey* pk) {
 }
 int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits) {
   if (!pk) return fail("null");
-  if (bits < 0 || bits > 16) return fail("phe_pubkey_set_comb_bits: bits must be in [0, 16] (0 = automatic)");
+  if (bits < 0 || bits > 22) return fail("phe_pubkey_set_comb_bits: bits must be in [0, 22] (0 = automatic)");
   std::lock_guard<std::mutex> lk(pk->mu);
   if (pk->comb_ready && bits != pk->comb_bits) { pk->d_comb.release(); pk->comb_ready = false; }
   pk->comb_bits_wanted = bits;

@@ -42,7 +42,7 @@ def test_encrypt_djn_pinned_r(key2048):
     assert got == O.encrypt_batch(pk_o, ms, None)
 
 
-@pytest.mark.parametrize("comb_bits", [1, 7, 8, 13, 16])
+@pytest.mark.parametrize("comb_bits", [1, 7, 8, 13, 16, 19])
 def test_encrypt_comb_widths(comb_bits):
     """Every digit width of the fixed-base comb table gives the same ciphertexts (table rebuilt on the device)."""
     pk_o, sk_o = O.seeded_keypair(1024, 21)
@@ -54,6 +54,32 @@ def test_encrypt_comb_widths(comb_bits):
     got = capi.array_to_ints(pk.encrypt(capi.ints_to_array(ms, 32), capi.ints_to_array(rs, 16)))
     assert pk.comb_bits == comb_bits
     assert got == O.encrypt_batch(pk_o, ms, rs)
+
+
+def test_comb_table_promotion():
+    """Automatic width: a key starts on the small comb table and moves to the wide one (as wide as a quarter of the
+    free device memory allows, at most 20 bits) once it has encrypted 32768 elements; ciphertexts do not change."""
+    pk_o, sk_o = O.bench_keypair()
+    pk = capi.PubKey(pk_o.n, 2048, djn=True, hs=pk_o.hs)
+    rng = random.Random(SEED + 77)
+    ms = [rng.getrandbits(53) for _ in range(40)]
+    rs = [rng.getrandbits(1024) for _ in ms]
+    m, r = capi.ints_to_array(ms, 64), capi.ints_to_array(rs, 32)
+    want = O.encrypt_batch(pk_o, ms, rs)
+    assert capi.array_to_ints(pk.encrypt(m, r)) == want
+    assert pk.comb_bits == 12
+    big = 33000
+    bm = np.zeros((big, 64), dtype=np.uint32)
+    bm[:, 0] = np.arange(big, dtype=np.uint32)
+    br = np.random.default_rng(SEED).integers(0, 1 << 32, size=(big, 32), dtype=np.uint32)
+    ct = pk.encrypt(bm, br)
+    wide = pk.comb_bits
+    assert 12 < wide <= 20
+    idx = [0, 1, big // 2, big - 1]
+    got = capi.array_to_ints(ct[idx])
+    assert got == O.encrypt_batch(pk_o, [int(bm[i, 0]) for i in idx], capi.array_to_ints(br[idx]))
+    assert capi.array_to_ints(pk.encrypt(m, r)) == want
+    assert pk.comb_bits == wide
 
 
 def test_decrypt_crt(key2048):
