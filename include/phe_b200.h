@@ -158,6 +158,13 @@ int phe_chacha20_keystream(const uint32_t key[8], const uint32_t nonce[3], uint3
  * [TPI][LP] layout): N, R^2 mod N, R mod N, 1, extra (0 here), R = 2^(52 L TPI).  Returns KP (>0) or <0 on
  * error.  out may be NULL to query KP.  n0inv_out = -N^-1 mod 2^52. */
 int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, double* out, uint64_t* n0inv_out);
+/* HE mul, DJN encrypt and the comb table run on the n-adic pair engine (csrc/npair_items.cuh): numbers mod n^2 as
+ * pairs (X0, X1) of n-sized Montgomery operands.  This dumps the constant block the engine is given for the key:
+ * 9 entries x KP doubles (n, 1, D mod R, W00, W01, W10, W11, OM0, OM1 -- csrc/npair_items.cuh: NPairEntry) in the
+ * shape (L, TPI) of n, plus n0inv = -n^-1 mod 2^52 and the top limb of D = ceil(R / n) n.  Returns KP (> 0), 0 if the
+ * key does not use the engine, < 0 on error.  out may be NULL to query. */
+int phe_pubkey_npair_block(const phe_pubkey* pk, int* L_out, int* TPI_out, double* out, uint64_t* n0inv_out,
+                           uint64_t* d_top_out);
 /* Decrypt runs its two CRT halves on the p-adic pair engine when p and q both have exactly bits/2 bits (every key
  * made by a keygen).  This dumps what the engine is given for x = p (y = 0) or q (y = 1): L (limbs per number),
  * n0inv = -x^-1 mod 2^52, mod_out = [L] limbs of x then [L + 1] limbs of D = ceil(R / x) x (doubles), cst_out =

@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "--cudart", "static",
 ]
 CU_SOURCES = ["phe_api.cu", "pipe_peak.cu", "pair_shapes.cu", "chacha20.cu"] + ["shape_%d_%d.cu" % s for s in ((20, 1), (20, 2), (20, 4), (20, 8), (15, 4), (15, 8))]
-HEADERS = ["mont52.cuh", "paillier_items.cuh", "phe_kernels.cuh", "phe_launch.cuh", "phe_shapes.hpp", "hostbn.hpp",
+HEADERS = ["mont52.cuh", "paillier_items.cuh", "npair_items.cuh", "npair_kernels.cuh", "phe_kernels.cuh", "phe_launch.cuh", "phe_shapes.hpp", "hostbn.hpp",
            os.path.join("..", "..", "include", "phe_b200.h")]
 
 

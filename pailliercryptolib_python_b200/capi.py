@@ -21,7 +21,7 @@ SYMBOLS = [
     "phe_privkey_create", "phe_privkey_destroy", "phe_privkey_get_p", "phe_privkey_get_q", "phe_keygen",
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
-    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
+    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
     "phe_product_mix_peak",
 ]
@@ -292,6 +292,22 @@ def host_mont_block(modulus, mod_words, L, TPI):
     lib().phe_host_mont_block(_p(int_to_words(modulus, mod_words)), mod_words, L, TPI,
                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(n0))
     return out.reshape(5, kp), n0.value
+
+
+def npair_block(pk):
+    """Constant block of the n-adic pair engine for this key: dict(L, TPI, cst [9][KP], n0inv, d_top), or None if the key
+    does not use the engine (include/phe_b200.h: phe_pubkey_npair_block)."""
+    L, TPI = ctypes.c_int(), ctypes.c_int()
+    kp = lib().phe_pubkey_npair_block(pk.h, ctypes.byref(L), ctypes.byref(TPI), None, None, None)
+    if kp < 0:
+        raise RuntimeError(lib().phe_last_error().decode())
+    if kp == 0:
+        return None
+    out = np.zeros(9 * kp, dtype=np.float64)
+    n0, dt = ctypes.c_uint64(), ctypes.c_uint64()
+    lib().phe_pubkey_npair_block(pk.h, None, None, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(n0),
+                                 ctypes.byref(dt))
+    return {"L": L.value, "TPI": TPI.value, "cst": out.reshape(9, kp), "n0inv": n0.value, "d_top": dt.value}
 
 
 def pair_block(sk, y):

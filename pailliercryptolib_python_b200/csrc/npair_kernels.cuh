@@ -1,0 +1,135 @@
+// npair_kernels.cuh -- __global__ wrappers of the n-adic pair engine (npair_items.cuh): HE mul, DJN encrypt and the
+// comb-table construction on (X0, X1) pairs of n-sized numbers instead of n^2-sized ones.
+// Shared memory (doubles): [NE_COUNT constant entries][per group: xs0, x1, y0, y1 (KP each), e (KP + 2)] -- 106 KB per
+// CTA at the (20, 2) shape of 2048-bit keys, two CTAs per SM.
+#pragma once
+#include "npair_items.cuh"
+#include "phe_kernels.cuh"
+
+namespace phe {
+
+template <int L, int TPI> struct NKShape {
+  static constexpr int KP = Shape<L, TPI>::KP;
+  static constexpr int GPB = NT / TPI;
+  static constexpr int PER_GROUP = 5 * KP + 2;
+  static constexpr size_t smem_bytes() { return (size_t)(NE_COUNT * KP + GPB * PER_GROUP) * sizeof(double); }
+};
+
+template <int L, int TPI> __device__ __forceinline__ NPairSmem npair_group_smem(double* smem) {
+  using NS = NKShape<L, TPI>;
+  double* g = smem + NE_COUNT * NS::KP + (size_t)(threadIdx.x / TPI) * NS::PER_GROUP;
+  NPairSmem sm;
+  sm.xs0 = g; sm.x1 = g + NS::KP; sm.y0 = g + 2 * NS::KP; sm.y1 = g + 3 * NS::KP;
+  sm.e = reinterpret_cast<uint64_t*>(g + 4 * NS::KP);
+  return sm;
+}
+
+// ---- HE mul: out = c^e mod n^2 ------------------------------------------------------------------------------------
+struct MulNPairArgs {
+  const uint32_t* c_w;    // [count][2 * chunk_words]
+  int chunk_words;        // n_words
+  const uint32_t* e_w;    // [count][e_words], or one row when e_stride == 0
+  int e_words;
+  size_t e_stride;
+  int ebits;
+  uint32_t* out_w;        // [count][2 * chunk_words]
+  int count;
+  NPairCtxArgs ctx;
+  double* tbl;            // [gridDim.x * GPB][1 << WIN][2 * KP]
+};
+
+template <int L, int TPI, int WIN> __global__ void __launch_bounds__(NT, 2) k_mul_npair(MulNPairArgs p) {
+  using Env = DevEnv<TPI>;
+  using NS = NKShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<NS::KP>(smem, p.ctx.entries, NE_COUNT);
+  const NPairSmem sm = npair_group_smem<L, TPI>(smem);
+  const int g = threadIdx.x / TPI;
+  double* tbl = p.tbl + ((size_t)blockIdx.x * NS::GPB + g) * ((size_t)2 * NS::KP << WIN);
+  const int cw = 2 * p.chunk_words;
+  for (int base = blockIdx.x * NS::GPB; base < p.count; base += gridDim.x * NS::GPB) {
+    const int want = base + g;
+    const int item = want < p.count ? want : p.count - 1;
+    NPairPowmCtl<L, TPI, Env, WIN> ctl;
+    ctl.c_w = p.c_w + (size_t)item * cw; ctl.chunk_words = p.chunk_words;
+    ctl.e_w = p.e_w + (size_t)item * p.e_stride; ctl.e_words = p.e_words; ctl.ebits = p.ebits;
+    ctl.out_w = want < p.count ? p.out_w + (size_t)item * cw : nullptr; ctl.out_words = cw;
+    ctl.cst = smem; ctl.tbl = tbl; ctl.sm = sm;
+    npair_run<L, TPI, Env>(ctl, smem, p.ctx.n0inv, p.ctx.d_top, sm);
+  }
+}
+
+// ---- DJN encrypt ------------------------------------------------------------------------------------------------
+struct EncNPairArgs {
+  const uint32_t* m_w; int m_words;
+  const uint32_t* r_w; int r_words;
+  int nwin, wb;
+  uint32_t* out_w; int out_words;
+  int count;
+  NPairCtxArgs ctx;
+  const double* comb;     // [nwin][1 << wb][2 * KP]
+};
+
+template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_encrypt_npair(EncNPairArgs p) {
+  using Env = DevEnv<TPI>;
+  using NS = NKShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<NS::KP>(smem, p.ctx.entries, NE_COUNT);
+  const NPairSmem sm = npair_group_smem<L, TPI>(smem);
+  const int g = threadIdx.x / TPI;
+  for (int base = blockIdx.x * NS::GPB; base < p.count; base += gridDim.x * NS::GPB) {
+    const int want = base + g;
+    const int item = want < p.count ? want : p.count - 1;
+    NPairEncCtl<L, TPI, Env> ctl;
+    ctl.m_w = p.m_w + (size_t)item * p.m_words; ctl.m_words = p.m_words;
+    ctl.r_w = p.r_w ? p.r_w + (size_t)item * p.r_words : nullptr; ctl.r_words = p.r_words;
+    ctl.nwin = p.nwin; ctl.wb = p.wb;
+    ctl.out_w = want < p.count ? p.out_w + (size_t)item * p.out_words : nullptr; ctl.out_words = p.out_words;
+    ctl.cst = smem; ctl.comb = p.comb; ctl.sm = sm;
+    npair_run<L, TPI, Env>(ctl, smem, p.ctx.n0inv, p.ctx.d_top, sm);
+  }
+}
+
+// ---- comb table construction ------------------------------------------------------------------------------------
+struct CombNPairArgs {
+  const uint32_t* hs_w;   // hs canonical words (2 * chunk_words)
+  int chunk_words;
+  int nwin, wb, level;
+  double* comb;
+  NPairCtxArgs ctx;
+};
+
+template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_comb_bases_npair(CombNPairArgs p) {
+  using Env = DevEnv<TPI>;
+  using NS = NKShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<NS::KP>(smem, p.ctx.entries, NE_COUNT);
+  const NPairSmem sm = npair_group_smem<L, TPI>(smem);
+  NPairCombBasesCtl<L, TPI, Env> ctl;
+  ctl.hs_w = p.hs_w; ctl.chunk_words = p.chunk_words; ctl.nwin = p.nwin; ctl.wb = p.wb; ctl.comb = p.comb;
+  ctl.writer = (threadIdx.x / TPI) == 0;   // every group of the single CTA runs the same chain; group 0 stores
+  ctl.cst = smem; ctl.sm = sm;
+  npair_run<L, TPI, Env>(ctl, smem, p.ctx.n0inv, p.ctx.d_top, sm);
+}
+
+template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_comb_level_npair(CombNPairArgs p) {
+  using Env = DevEnv<TPI>;
+  using NS = NKShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<NS::KP>(smem, p.ctx.entries, NE_COUNT);
+  const NPairSmem sm = npair_group_smem<L, TPI>(smem);
+  const int g = threadIdx.x / TPI;
+  const int per_win = (1 << p.level) - 1;
+  const int count = p.nwin * per_win;
+  for (int base = blockIdx.x * NS::GPB; base < count; base += gridDim.x * NS::GPB) {
+    const int want = base + g;
+    const int item = want < count ? want : count - 1;   // past the end: redo the last product, skip the store
+    const int j = item / per_win;
+    NPairCombLevelCtl<L, TPI, Env> ctl;
+    ctl.row = p.comb + (((size_t)j) << p.wb) * 2 * NS::KP; ctl.level = p.level; ctl.e = 1 + item % per_win;
+    ctl.store = want < count; ctl.sm = sm;
+    npair_run<L, TPI, Env>(ctl, smem, p.ctx.n0inv, p.ctx.d_top, sm);
+  }
+}
+
+}  // namespace phe

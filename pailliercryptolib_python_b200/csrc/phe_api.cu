@@ -14,6 +14,7 @@
 #include "../../include/phe_b200.h"
 #include "hostbn.hpp"
 #include "phe_kernels.cuh"
+#include "npair_kernels.cuh"
 #include "phe_shapes.hpp"
 
 using hbn::BN;
@@ -154,6 +155,34 @@ std::vector<uint32_t> mont_block(const BN& N, const BN& extra, const ShapeOps* o
   to_entry(BN(1), o, &blk[(size_t)ME_ONE * EW(o)]);
   to_entry(extra, o, &blk[(size_t)ME_X0 * EW(o)]);
   *n0inv = neg_inv52(N);
+  return blk;
+}
+
+// Constant block of the n-adic pair engine (npair_items.cuh: NPairEntry) for modulus n on shape o.
+std::vector<uint32_t> npair_block(const BN& n, int n_words, const ShapeOps* o, uint64_t* n0inv, uint64_t* d_top) {
+  std::vector<uint32_t> blk((size_t)NE_COUNT * EW(o));
+  const BN R = hbn::shl(BN(1), o->capacity_bits);
+  const BN n2 = hbn::mul(n, n);
+  const BN D = hbn::mul(hbn::div(hbn::add(R, hbn::sub(n, BN(1))), n), n);   // ceil(R / n) n
+  BN dq, dr;
+  hbn::divmod(D, R, &dq, &dr);
+  if (dq.bits() > 52) throw std::runtime_error("npair_block: top limb of D out of range");
+  *d_top = dq.is_zero() ? 0ull : ((uint64_t)dq.w[0] | (dq.w.size() > 1 ? (uint64_t)dq.w[1] << 32 : 0ull));
+  auto put = [&](int idx, const BN& v) { to_entry(v, o, &blk[(size_t)idx * EW(o)]); };
+  put(NE_N, n); put(NE_ONE, BN(1)); put(NE_D, dr);
+  const BN R2 = hbn::mod(hbn::mul(hbn::mod(R, n2), hbn::mod(R, n2)), n2);
+  for (int c = 0; c < 2; ++c) {
+    const BN w = hbn::mulmod(hbn::mod(hbn::shl(BN(1), (size_t)c * 32 * n_words), n2), R2, n2);
+    BN q, r;
+    hbn::divmod(w, n, &q, &r);
+    put(NE_W00 + 2 * c, r); put(NE_W01 + 2 * c, q);
+  }
+  {
+    BN q, r;
+    hbn::divmod(hbn::mod(R, n2), n, &q, &r);
+    put(NE_OM0, r); put(NE_OM1, q);
+  }
+  *n0inv = neg_inv52(n);
   return blk;
 }
 
@@ -323,6 +352,11 @@ struct phe_pubkey {
   int bits = 0, n_words = 0, djn = 0, randbits = 0, device = 0;
   BN n, nsq, hs;
   const ShapeOps* ops = nullptr;  // shape of the n^2 context
+  const ShapeOps* nops = nullptr; // shape of the n-sized numbers of the n-adic pair engine (npair_items.cuh)
+  bool use_npair = false;         // HE mul, DJN encrypt and the comb table run on (X0, X1) pairs mod n
+  mutable NPairCtxArgs nctx{};
+  mutable DevBuf d_nctx;
+  std::vector<uint32_t> h_nctx;
   mutable MontCtxArgs ctx{};
   mutable DevBuf d_ctx, d_comb;
   std::vector<uint32_t> h_ctx;    // Montgomery block, uploaded lazily
@@ -367,6 +401,10 @@ int pk_ensure_device(const phe_pubkey* pk) {
   CUDA_TRY(cudaGetDevice(const_cast<int*>(&pk->device)));
   PHE_TRY(upload(pk->d_ctx, pk->h_ctx));
   pk->ctx.entries = reinterpret_cast<const double*>(pk->d_ctx.p);
+  if (pk->use_npair) {
+    PHE_TRY(upload(pk->d_nctx, pk->h_nctx));
+    pk->nctx.entries = reinterpret_cast<const double*>(pk->d_nctx.p);
+  }
   pk->dev_ready = true;
   return 0;
 }
@@ -382,7 +420,7 @@ int pk_ensure_comb(const phe_pubkey* pk, size_t count) {
   if (!pk->djn) return fail("comb table requested for a non-DJN key");
   int wb = pk->comb_bits_wanted;
   if (wb <= 0) { const char* e = getenv("PHE_COMB_BITS"); if (e) wb = atoi(e); }
-  const size_t entry_bytes = EW(pk->ops) * 4;
+  const size_t entry_bytes = pk->use_npair ? 2 * EW(pk->nops) * 4 : EW(pk->ops) * 4;
   auto table_bytes = [&](int w) { return (size_t)((pk->randbits + w - 1) / w) * ((size_t)1 << w) * entry_bytes; };
   if (wb > 0) {
     if (pk->comb_ready) return 0;
@@ -408,10 +446,18 @@ int pk_ensure_comb(const phe_pubkey* pk, size_t count) {
   pk->hs.to_words(hsw.data(), hsw.size());
   DevBuf dhs;
   PHE_TRY(upload(dhs, hsw));
-  CombArgs ca{};
-  ca.hs_w = dhs.p; ca.hs_words = 2 * pk->n_words; ca.nwin = pk->nwin; ca.wb = wb;
-  ca.comb = reinterpret_cast<double*>(pk->d_comb.p); ca.ctx = pk->ctx;
-  cudaError_t e = pk->ops->comb_build(ca, 0);
+  cudaError_t e;
+  if (pk->use_npair) {
+    CombNPairArgs ca{};
+    ca.hs_w = dhs.p; ca.chunk_words = pk->n_words; ca.nwin = pk->nwin; ca.wb = wb;
+    ca.comb = reinterpret_cast<double*>(pk->d_comb.p); ca.ctx = pk->nctx;
+    e = pk->nops->comb_build_npair(ca, 0);
+  } else {
+    CombArgs ca{};
+    ca.hs_w = dhs.p; ca.hs_words = 2 * pk->n_words; ca.nwin = pk->nwin; ca.wb = wb;
+    ca.comb = reinterpret_cast<double*>(pk->d_comb.p); ca.ctx = pk->ctx;
+    e = pk->ops->comb_build(ca, 0);
+  }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   dhs.release();
   if (e != cudaSuccess) return fail(std::string("comb table build: ") + cudaGetErrorString(e));
@@ -470,6 +516,26 @@ int launch_powm(const ShapeOps* o, const MontCtxArgs& ctx, const uint32_t* d_bas
 
 constexpr size_t CHUNK = 1u << 20;  // items per launch (bounds scratch and int indexing)
 
+// one DJN comb launch (n^2 Montgomery engine or n-adic pair engine)
+int launch_encrypt_comb(const phe_pubkey* pk, const uint32_t* m_w, int m_words, const uint32_t* r_w, int r_words,
+                        uint32_t* out_w, int count, cudaStream_t s) {
+  const int cw = 2 * pk->n_words;
+  if (pk->use_npair) {
+    EncNPairArgs a{};
+    a.m_w = m_w; a.m_words = m_words; a.r_w = r_w; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
+    a.out_w = out_w; a.out_words = cw; a.count = count; a.ctx = pk->nctx;
+    a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
+    CUDA_TRY(pk->nops->encrypt_npair(a, s));
+    return 0;
+  }
+  EncCombArgs a{};
+  a.m_w = m_w; a.m_words = m_words; a.r_w = r_w; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
+  a.out_w = out_w; a.out_words = cw; a.count = count; a.ctx = pk->ctx;
+  a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
+  CUDA_TRY(pk->ops->encrypt_comb(a, s));
+  return 0;
+}
+
 // obf[i] for r[i] into d_obf (canonical ciphertext words).  d_r: device, r_words per item.
 int obfuscators_dev(const phe_pubkey* pk, const uint32_t* d_r, int r_words, size_t count, uint32_t* d_obf,
                     cudaStream_t s) {
@@ -481,11 +547,8 @@ int obfuscators_dev(const phe_pubkey* pk, const uint32_t* d_r, int r_words, size
     CUDA_TRY(cudaMemsetAsync(pk->ws_d.p, 0, (size_t)pk->n_words * 4, s));
     for (size_t off = 0; off < count; off += CHUNK) {
       const int c = (int)std::min(CHUNK, count - off);
-      EncCombArgs a{};
-      a.m_w = pk->ws_d.p; a.m_words = 0;   // zero words: m = 0 for every item
-      a.r_w = d_r + off * r_words; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
-      a.out_w = d_obf + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
-      CUDA_TRY(pk->ops->encrypt_comb(a, s));
+      // zero words: m = 0 for every item
+      PHE_TRY(launch_encrypt_comb(pk, pk->ws_d.p, 0, d_r + off * r_words, r_words, d_obf + off * cw, c, s));
     }
     return 0;
   }
@@ -552,11 +615,8 @@ int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, co
     }
     for (size_t off = 0; off < count; off += CHUNK) {
       const int c = (int)std::min(CHUNK, count - off);
-      EncCombArgs a{};
-      a.m_w = d_m + off * (size_t)m_words; a.m_words = m_words;
-      a.r_w = d_r ? d_r + off * r_words : nullptr; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
-      a.out_w = d_ct + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->ctx; a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
-      CUDA_TRY(pk->ops->encrypt_comb(a, s));
+      PHE_TRY(launch_encrypt_comb(pk, d_m + off * (size_t)m_words, m_words, d_r ? d_r + off * r_words : nullptr, r_words,
+                                  d_ct + off * cw, c, s));
     }
     return 0;
   }
@@ -649,6 +709,19 @@ int mul_dev_impl(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uin
   int ebits = exp_bits > 0 ? exp_bits : e_words * 32;
   if (ebits > e_words * 32) ebits = e_words * 32;
   const bool bc = (ne == 1 && n != 1);
+  if (pk->use_npair) {
+    const int win = window_for_bits(ebits);
+    for (size_t off = 0; off < n; off += CHUNK) {
+      const int c = (int)std::min(CHUNK, n - off);
+      PHE_TRY(pk->ws_tbl.ensure(pk->nops->mul_npair_tbl_words(win, c)));
+      MulNPairArgs a{};
+      a.c_w = d_ct + off * cw; a.chunk_words = pk->n_words;
+      a.e_w = bc ? d_e : d_e + off * e_words; a.e_words = e_words; a.e_stride = bc ? 0 : (size_t)e_words; a.ebits = ebits;
+      a.out_w = d_out + off * cw; a.count = c; a.ctx = pk->nctx; a.tbl = reinterpret_cast<double*>(pk->ws_tbl.p);
+      CUDA_TRY(pk->nops->mul_npair(win, a, s));
+    }
+    return 0;
+  }
   for (size_t off = 0; off < n; off += CHUNK) {
     const int c = (int)std::min(CHUNK, n - off);
     PHE_TRY(launch_powm(pk->ops, pk->ctx, d_ct + off * cw, cw, bc ? d_e : d_e + off * e_words, e_words,
@@ -766,6 +839,14 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
     if (!pk->ops) return fail("phe_pubkey_create: key too large (n^2 up to 8192 bits supported)");
     const BN R = hbn::shl(BN(1), pk->ops->capacity_bits);
     pk->h_ctx = mont_block(pk->nsq, hbn::mulmod(N, hbn::mod(R, pk->nsq), pk->nsq), pk->ops, &pk->ctx.n0inv);
+    {   // n-adic pair engine: needs n to fill its words (the chunks of a ciphertext are n_words words each)
+      const char* off = getenv("PHE_NO_NPAIR_ENGINE");
+      pk->nops = shape_for_bits(n_words * 32);
+      if (pk->nops && !(off && off[0] == '1')) {
+        pk->h_nctx = npair_block(N, n_words, pk->nops, &pk->nctx.n0inv, &pk->nctx.d_top);
+        pk->use_npair = true;
+      }
+    }
     if (djn) {
       pk->randbits = randbits > 0 ? randbits : bits / 2;
       if (hs) {
@@ -789,7 +870,7 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
 
 void phe_pubkey_destroy(phe_pubkey* pk) {
   if (!pk) return;
-  for (DevBuf* b : {&pk->d_ctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
+  for (DevBuf* b : {&pk->d_ctx, &pk->d_nctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
   delete pk;
 }
 int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits) {
@@ -1180,6 +1261,18 @@ int phe_host_mont_block(const uint32_t* mod, int mod_words, int L, int TPI, doub
     if (n0inv_out) *n0inv_out = n0;
     return o->KP;
   } catch (const std::exception& e) { fail(e.what()); return -1; }
+}
+
+int phe_pubkey_npair_block(const phe_pubkey* pk, int* L_out, int* TPI_out, double* out, uint64_t* n0inv_out,
+                           uint64_t* d_top_out) {
+  if (!pk) { fail("phe_pubkey_npair_block: null key"); return -1; }
+  if (!pk->use_npair) return 0;
+  if (L_out) *L_out = pk->nops->L;
+  if (TPI_out) *TPI_out = pk->nops->TPI;
+  if (out) std::memcpy(out, pk->h_nctx.data(), pk->h_nctx.size() * 4);
+  if (n0inv_out) *n0inv_out = pk->nctx.n0inv;
+  if (d_top_out) *d_top_out = pk->nctx.d_top;
+  return pk->nops->KP;
 }
 
 int phe_privkey_pair_block(const phe_privkey* sk, int y, int* L_out, uint64_t* n0inv_out, double* mod_out,

@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "phe_kernels.cuh"
+#include "npair_kernels.cuh"
 #include "phe_shapes.hpp"
 
 namespace phe {
@@ -164,9 +165,68 @@ template <int L, int TPI> struct Launch {
     return e;
   }
 
+  // ---- n-adic pair engine ----
+  using NS = NKShape<L, TPI>;
+  template <int WIN> static cudaError_t mul_npair_w(const MulNPairArgs& p, cudaStream_t s) {
+    const size_t smem = NS::smem_bytes();
+    const int grid = grid_for(k_mul_npair<L, TPI, WIN>, smem, p.count, NS::GPB, 1);
+    { TimedLaunch tl_(KK_POWM, s);
+    k_mul_npair<L, TPI, WIN><<<grid, NT, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+  }
+  static cudaError_t mul_npair(int win, const MulNPairArgs& p, cudaStream_t s) {
+    switch (win) {
+      case 1: return mul_npair_w<1>(p, s);
+      case 3: return mul_npair_w<3>(p, s);
+      case 5: return mul_npair_w<5>(p, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  template <int WIN> static size_t mul_npair_tbl_w(int count) {
+    const int grid = grid_for(k_mul_npair<L, TPI, WIN>, NS::smem_bytes(), count, NS::GPB, 1);
+    return (size_t)grid * NS::GPB * ((size_t)2 * NS::KP << WIN) * 2;   // doubles -> u32 words
+  }
+  static size_t mul_npair_tbl_words(int win, int count) {
+    switch (win) {
+      case 1: return mul_npair_tbl_w<1>(count);
+      case 3: return mul_npair_tbl_w<3>(count);
+      case 5: return mul_npair_tbl_w<5>(count);
+      default: return 0;
+    }
+  }
+  static cudaError_t encrypt_npair(const EncNPairArgs& p, cudaStream_t s) {
+    const size_t smem = NS::smem_bytes();
+    const int grid = grid_for(k_encrypt_npair<L, TPI>, smem, p.count, NS::GPB, 1);
+    { TimedLaunch tl_(KK_ENC_COMB, s);
+    k_encrypt_npair<L, TPI><<<grid, NT, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+  }
+  static cudaError_t comb_build_npair(const CombNPairArgs& p0, cudaStream_t s) {
+    const size_t smem = NS::smem_bytes();
+    cudaFuncSetAttribute(k_comb_bases_npair<L, TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { TimedLaunch tl_(KK_COMB_BUILD, s);
+    k_comb_bases_npair<L, TPI><<<1, NT, smem, s>>>(p0);
+    }
+    cudaError_t e = cudaGetLastError();
+    for (int k = 1; k < p0.wb && e == cudaSuccess; ++k) {
+      CombNPairArgs p = p0;
+      p.level = k;
+      const int count = p.nwin * ((1 << k) - 1);
+      const int grid = grid_for(k_comb_level_npair<L, TPI>, smem, count, NS::GPB, 1);
+      { TimedLaunch tl_(KK_COMB_BUILD, s);
+      k_comb_level_npair<L, TPI><<<grid, NT, smem, s>>>(p);
+      }
+      e = cudaGetLastError();
+    }
+    return e;
+  }
+
   static constexpr ShapeOps ops() {
     return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &powm_prog, &powm_prog_tbl_words, &dec_prep, &dec_tail, &dec_crt, &inv_block, &resident_groups,
-                    &encrypt_comb, &encrypt_finish, &comb_build};
+                    &encrypt_comb, &encrypt_finish, &comb_build,
+                    &mul_npair, &mul_npair_tbl_words, &encrypt_npair, &comb_build_npair};
   }
 };
 

@@ -18,6 +18,9 @@ struct CombArgs;
 struct DecPairArgs;
 struct DecCrtArgs;
 struct InvArgs;
+struct MulNPairArgs;
+struct EncNPairArgs;
+struct CombNPairArgs;
 
 struct ShapeOps {
   int L, TPI, KP, GPB;   // KP: doubles per padded entry
@@ -37,6 +40,11 @@ struct ShapeOps {
   cudaError_t (*encrypt_comb)(const EncCombArgs& p, cudaStream_t s);
   cudaError_t (*encrypt_finish)(const EncFinishArgs& p, cudaStream_t s);
   cudaError_t (*comb_build)(const CombArgs& p, cudaStream_t s);
+  // n-adic pair engine on this shape as the n-sized one (npair_kernels.cuh)
+  cudaError_t (*mul_npair)(int win, const MulNPairArgs& p, cudaStream_t s);
+  size_t (*mul_npair_tbl_words)(int win, int count);
+  cudaError_t (*encrypt_npair)(const EncNPairArgs& p, cudaStream_t s);
+  cudaError_t (*comb_build_npair)(const CombNPairArgs& p, cudaStream_t s);
 };
 
 const ShapeOps* shape_ops(int L, int TPI);   // nullptr if not built

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../pailliercryptolib_python_b200/csrc/paillier_items.cuh"
+#include "../../pailliercryptolib_python_b200/csrc/npair_items.cuh"
 
 namespace {
 
@@ -291,6 +292,91 @@ int do_dec_crt(const uint32_t* mp, const uint32_t* mq, int half_words, uint32_t*
   return 0;
 }
 
+// ---- n-adic pair engine (npair_items.cuh) ----
+template <int L, int TPI> struct NBufs {
+  static constexpr int KP = phe::Shape<L, TPI>::KP;
+  std::vector<double> store;
+  phe::NPairSmem sm;
+  NBufs() : store(5 * KP + 6) {
+    double* g = (double*)(((uintptr_t)store.data() + 15) & ~(uintptr_t)15);
+    sm.xs0 = g; sm.x1 = g + KP; sm.y0 = g + 2 * KP; sm.y1 = g + 3 * KP; sm.e = reinterpret_cast<uint64_t*>(g + 4 * KP);
+  }
+};
+
+template <int L, int TPI, int WIN>
+int do_mul_npair(const uint32_t* c, int chunk_words, const uint32_t* e, int e_words, int e_stride, int ebits,
+                 uint32_t* out, int count, const double* cst_e, uint64_t n0inv, uint64_t d_top) {
+  using Env = EmuEnv<TPI>;
+  constexpr int KP = phe::Shape<L, TPI>::KP;
+  AlignedCopy cst(cst_e, (size_t)phe::NE_COUNT * KP);
+  const int cw = 2 * chunk_words;
+  for (int i = 0; i < count; ++i) {
+    NBufs<L, TPI> bufs;
+    std::vector<double> tbl((size_t)(2 << WIN) * KP + 2);
+    double* tp = (double*)(((uintptr_t)tbl.data() + 15) & ~(uintptr_t)15);
+    run_group<TPI>([&] {
+      phe::NPairPowmCtl<L, TPI, Env, WIN> ctl;
+      ctl.c_w = c + (size_t)i * cw; ctl.chunk_words = chunk_words;
+      ctl.e_w = e + (size_t)i * e_stride; ctl.e_words = e_words; ctl.ebits = ebits;
+      ctl.out_w = out + (size_t)i * cw; ctl.out_words = cw; ctl.cst = cst.p; ctl.tbl = tp; ctl.sm = bufs.sm;
+      phe::npair_run<L, TPI, Env>(ctl, cst.p, n0inv, d_top, bufs.sm);
+    });
+  }
+  return 0;
+}
+
+template <int L, int TPI>
+int do_comb_npair(const uint32_t* hs, int chunk_words, int nwin, int wb, double* comb, const double* cst_e,
+                  uint64_t n0inv, uint64_t d_top) {
+  using Env = EmuEnv<TPI>;
+  constexpr int KP = phe::Shape<L, TPI>::KP;
+  AlignedCopy cst(cst_e, (size_t)phe::NE_COUNT * KP);
+  const size_t total = ((size_t)nwin << wb) * 2 * KP;
+  std::vector<double> store(total + 2);
+  double* cb = (double*)(((uintptr_t)store.data() + 15) & ~(uintptr_t)15);
+  {
+    NBufs<L, TPI> bufs;
+    run_group<TPI>([&] {
+      phe::NPairCombBasesCtl<L, TPI, Env> ctl;
+      ctl.hs_w = hs; ctl.chunk_words = chunk_words; ctl.nwin = nwin; ctl.wb = wb; ctl.comb = cb; ctl.writer = true;
+      ctl.cst = cst.p; ctl.sm = bufs.sm;
+      phe::npair_run<L, TPI, Env>(ctl, cst.p, n0inv, d_top, bufs.sm);
+    });
+  }
+  for (int level = 1; level < wb; ++level)
+    for (int j = 0; j < nwin; ++j)
+      for (int e = 1; e < (1 << level); ++e) {
+        NBufs<L, TPI> bufs;
+        run_group<TPI>([&] {
+          phe::NPairCombLevelCtl<L, TPI, Env> ctl;
+          ctl.row = cb + (((size_t)j) << wb) * 2 * KP; ctl.level = level; ctl.e = e; ctl.store = true; ctl.sm = bufs.sm;
+          phe::npair_run<L, TPI, Env>(ctl, cst.p, n0inv, d_top, bufs.sm);
+        });
+      }
+  std::memcpy(comb, cb, total * 8);
+  return 0;
+}
+
+template <int L, int TPI>
+int do_encrypt_npair(const uint32_t* m, int m_words, const uint32_t* r, int r_words, int nwin, int wb, uint32_t* out,
+                     int out_words, int count, const double* cst_e, uint64_t n0inv, uint64_t d_top, const double* comb,
+                     size_t comb_doubles) {
+  using Env = EmuEnv<TPI>;
+  constexpr int KP = phe::Shape<L, TPI>::KP;
+  AlignedCopy cst(cst_e, (size_t)phe::NE_COUNT * KP), cb(comb, comb_doubles);
+  for (int i = 0; i < count; ++i) {
+    NBufs<L, TPI> bufs;
+    run_group<TPI>([&] {
+      phe::NPairEncCtl<L, TPI, Env> ctl;
+      ctl.m_w = m + (size_t)i * m_words; ctl.m_words = m_words;
+      ctl.r_w = r ? r + (size_t)i * r_words : nullptr; ctl.r_words = r_words; ctl.nwin = nwin; ctl.wb = wb;
+      ctl.out_w = out + (size_t)i * out_words; ctl.out_words = out_words; ctl.cst = cst.p; ctl.comb = cb.p; ctl.sm = bufs.sm;
+      phe::npair_run<L, TPI, Env>(ctl, cst.p, n0inv, d_top, bufs.sm);
+    });
+  }
+  return 0;
+}
+
 }  // namespace
 
 #define DISPATCH_SHAPE(CALL)                       \
@@ -366,5 +452,24 @@ int emu_dec_crt(int shape, const uint32_t* mp, const uint32_t* mq, int half_word
 int emu_dec_tail(int shape, const uint32_t* up, const uint32_t* uq, int u_words, uint32_t* m, int m_words, int count,
                  const double* cst, const uint64_t* n0invs) {
   DISPATCH_SHAPE((do_dec_tail<L, TPI>(up, uq, u_words, m, m_words, count, cst, n0invs)));
+}
+int emu_mul_npair(int shape, int win, const uint32_t* c, int chunk_words, const uint32_t* e, int e_words, int e_stride,
+                  int ebits, uint32_t* out, int count, const double* cst, uint64_t n0inv, uint64_t d_top) {
+#define NPM_CALL(W) do_mul_npair<L, TPI, W>(c, chunk_words, e, e_words, e_stride, ebits, out, count, cst, n0inv, d_top)
+  if (win == 5) { DISPATCH_SHAPE((NPM_CALL(5))); }
+  if (win == 3) { DISPATCH_SHAPE((NPM_CALL(3))); }
+  if (win == 1) { DISPATCH_SHAPE((NPM_CALL(1))); }
+  return -2;
+}
+
+int emu_comb_npair(int shape, const uint32_t* hs, int chunk_words, int nwin, int wb, double* comb, const double* cst,
+                   uint64_t n0inv, uint64_t d_top) {
+  DISPATCH_SHAPE((do_comb_npair<L, TPI>(hs, chunk_words, nwin, wb, comb, cst, n0inv, d_top)));
+}
+
+int emu_encrypt_npair(int shape, const uint32_t* m, int m_words, const uint32_t* r, int r_words, int nwin, int wb,
+                      uint32_t* out, int out_words, int count, const double* cst, uint64_t n0inv, uint64_t d_top,
+                      const double* comb, uint64_t comb_doubles) {
+  DISPATCH_SHAPE((do_encrypt_npair<L, TPI>(m, m_words, r, r_words, nwin, wb, out, out_words, count, cst, n0inv, d_top, comb, comb_doubles)));
 }
 }

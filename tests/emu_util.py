@@ -70,7 +70,7 @@ def load_emu():
         return _emu
     src = os.path.join(HERE, "emu", "emu_driver.cpp")
     so = os.path.join(HERE, "emu", "libphe_emu.so")
-    deps = [src] + [os.path.join(HERE, "..", "pailliercryptolib_python_b200", "csrc", f) for f in ("mont52.cuh", "paillier_items.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "pailliercryptolib_python_b200", "csrc", f) for f in ("mont52.cuh", "paillier_items.cuh", "npair_items.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         # -frounding-math: the emulator runs under FE_TOWARDZERO (fma.rz.f64); no constant folding across that
         subprocess.check_call(["g++", "-O2", "-std=c++20", "-frounding-math", "-ffp-contract=off", "-pthread", "-shared",
@@ -98,3 +98,23 @@ def PD(a):
 def P64(a):
     assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+
+
+NE_NAMES = ["N", "ONE", "D", "W00", "W01", "W10", "W11", "OM0", "OM1"]
+
+
+def npair_consts(n, L, TPI, n_words):
+    """Constant block of the n-adic pair engine (csrc/npair_items.cuh: NPairEntry) from Python ints."""
+    K = L * TPI
+    R = 1 << (LW * K)
+    assert n % 2 == 1 and n << 8 <= R and 32 * n_words + 8 <= LW * K
+    n2 = n * n
+    D = -(-R // n) * n
+    vals = {"N": n, "ONE": 1, "D": D % R}
+    for c in range(2):
+        w = (1 << (32 * n_words * c)) * R * R % n2
+        vals["W%d0" % c], vals["W%d1" % c] = w % n, w // n
+    om = R % n2
+    vals["OM0"], vals["OM1"] = om % n, om // n
+    block = np.concatenate([to_entry(vals[k], L, TPI) for k in NE_NAMES])
+    return {"cst": block, "n0inv": (-pow(n, -1, 1 << LW)) % (1 << LW), "d_top": D >> (LW * K), "R": R}

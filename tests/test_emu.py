@@ -277,3 +277,82 @@ def test_batched_inverse_blocks(emu, L, TPI, bits, block):
                            PD(mc["n"]), U64(mc["n0inv"]), PD(mc["r2"]), PD(mc["oneM"]), PD(mc["one"]))
     assert rc == 0
     assert from_words(out) == [pow(c, -1, N) for c in cs]
+
+
+# ---- n-adic pair engine (csrc/npair_items.cuh): arithmetic mod n^2 on pairs of n-sized numbers ----------------------
+from emu_util import npair_consts  # noqa: E402
+
+NPAIR_SHAPES = [(20, 1, 1024), (20, 2, 2048), (15, 4, 3072), (7, 4, 1408)]
+
+
+@pytest.mark.parametrize("L,TPI,bits,win,ebits", [(20, 1, 1024, 3, 53), (20, 2, 2048, 3, 53), (20, 2, 2048, 5, 300),
+                                                   (20, 2, 2048, 1, 5), (15, 4, 3072, 3, 64), (7, 4, 1408, 5, 170)])
+def test_npair_mul(emu, L, TPI, bits, win, ebits):
+    rng = random.Random(bits * 3 + win)
+    nw = bits // 32
+    ew = (ebits + 31) // 32
+    for top in (bits, bits - 3):
+        n = rng.getrandbits(top) | 1 | (1 << (top - 1))
+        n2 = n * n
+        nc = npair_consts(n, L, TPI, nw)
+        base = [rng.randrange(n2) for _ in range(3)] + [0, 1, n2 - 1, n, n - 1]
+        exps = [rng.getrandbits(ebits) for _ in range(3)] + [3, 0, (1 << ebits) - 1, 2, 1]
+        exps[0] |= 1 << (ebits - 1)
+        cw, ewa = to_words(base, 2 * nw), to_words(exps, ew)
+        out = np.zeros_like(cw)
+        rc = emu.emu_mul_npair(shape_id(L, TPI), win, P(cw), nw, P(ewa), ew, ew, ebits, P(out), len(base),
+                               PD(nc["cst"]), U64(nc["n0inv"]), U64(nc["d_top"]))
+        assert rc == 0
+        assert from_words(out) == [pow(b, e, n2) for b, e in zip(base, exps)]
+
+
+def _npair_encrypt_case(emu, bits, L, TPI, WB, seed):
+    rng = random.Random(seed)
+    pk_o, sk_o = O.seeded_keypair(bits, seed)
+    n, n2 = pk_o.n, pk_o.nsquare
+    nw = bits // 32
+    randbits = bits // 2
+    nwin = (randbits + WB - 1) // WB
+    nc = npair_consts(n, L, TPI, nw)
+    KP = len(nc["cst"]) // 9
+    hs_w = to_words([pk_o.hs], 2 * nw)
+    comb = np.zeros(((nwin << WB) * 2 * KP,), dtype=np.float64)
+    assert emu.emu_comb_npair(shape_id(L, TPI), P(hs_w), nw, nwin, WB, PD(comb), PD(nc["cst"]), U64(nc["n0inv"]), U64(nc["d_top"])) == 0
+    # spot-check table entries: T[j][d] = hs^(d 2^(WB j)) in pair-Montgomery form
+    R = nc["R"]
+    for j, d in [(0, 0), (0, 1), (nwin - 1, (1 << WB) - 1), (1 % nwin, 2)]:
+        ent = comb[((j << WB) + d) * 2 * KP:((j << WB) + d + 1) * 2 * KP]
+        x0, x1 = from_entry(ent[:KP], L, TPI), from_entry(ent[KP:], L, TPI)
+        assert (x0 + x1 * n) * pow(R, -1, n2) % n2 == pow(pk_o.hs, d << (WB * j), n2)
+    ms = [0, 1, n - 1, n // 3 - 1] + [rng.randrange(n) for _ in range(3)] + [rng.getrandbits(53) for _ in range(3)]
+    rs = [0, 1, (1 << randbits) - 1] + [rng.getrandbits(randbits) for _ in range(len(ms) - 3)]
+    mw, rw = to_words(ms, nw), to_words(rs, (randbits + 31) // 32)
+    out = np.zeros((len(ms), 2 * nw), dtype=np.uint32)
+    rc = emu.emu_encrypt_npair(shape_id(L, TPI), P(mw), nw, P(rw), rw.shape[1], nwin, WB, P(out), 2 * nw, len(ms),
+                               PD(nc["cst"]), U64(nc["n0inv"]), U64(nc["d_top"]), PD(comb), U64(comb.size))
+    assert rc == 0
+    assert from_words(out) == O.encrypt_batch(pk_o, ms, rs)
+    # make_secure = False
+    rc = emu.emu_encrypt_npair(shape_id(L, TPI), P(mw), nw, None, 0, nwin, WB, P(out), 2 * nw, len(ms),
+                               PD(nc["cst"]), U64(nc["n0inv"]), U64(nc["d_top"]), PD(comb), U64(comb.size))
+    assert rc == 0
+    assert from_words(out) == O.encrypt_batch(pk_o, ms, None)
+
+
+@pytest.mark.parametrize("bits,L,TPI,WB", [(1024, 20, 1, 3), (2048, 20, 2, 2), (1408 - 64, 7, 4, 4)])
+def test_npair_encrypt(emu, bits, L, TPI, WB):
+    _npair_encrypt_case(emu, bits, L, TPI, WB, bits + WB)
+
+
+@pytest.mark.parametrize("bits", [1024, 2048, 3072])
+def test_npair_host_block_matches_python(bits):
+    """The constant block the library builds for the n-adic pair engine (hostbn) == the one from Python ints, and the
+    emulated HE mul on the library's block agrees with pow()."""
+    from pailliercryptolib_python_b200 import capi
+    pk_o, _ = O.seeded_keypair(bits, 5)
+    pk = capi.PubKey(pk_o.n, bits, djn=True, hs=pk_o.hs)
+    blk = capi.npair_block(pk)
+    assert blk is not None
+    nc = npair_consts(pk_o.n, blk["L"], blk["TPI"], bits // 32)
+    assert np.array_equal(blk["cst"].reshape(-1), nc["cst"])
+    assert blk["n0inv"] == nc["n0inv"] and blk["d_top"] == nc["d_top"]

@@ -384,3 +384,36 @@ def test_batched_modular_inverse(key2048, count):
         bad[count // 2] = sk_o.p * 12345                # shares the factor p with n
         with pytest.raises(RuntimeError):
             pk.invert(capi.ints_to_array(bad, 128))
+
+
+@pytest.mark.parametrize("bits", [1024, 2048, 3072])
+def test_npair_engine_and_n2_engine_agree(monkeypatch, bits):
+    """HE mul and DJN encrypt run on the n-adic pair engine by default; PHE_NO_NPAIR_ENGINE=1 keeps a key on the
+    Montgomery engine mod n^2.  Both must give the oracle's bits."""
+    pk_o, sk_o = O.seeded_keypair(bits, 9)
+    nw = bits // 32
+    rng = random.Random(SEED + bits)
+    ms = [0, 1, pk_o.n - 1] + [rng.randrange(pk_o.n) for _ in range(40)] + [rng.getrandbits(53) for _ in range(60)]
+    rs = [0, 1, (1 << (bits // 2)) - 1] + [rng.getrandbits(bits // 2) for _ in range(len(ms) - 3)]
+    cts = [0, 1, pk_o.nsquare - 1, pk_o.n] + [rng.randrange(pk_o.nsquare) for _ in range(60)]
+    want_ct = O.encrypt_batch(pk_o, ms, rs)
+    for ebits in (1, 53, 200, bits):
+        es = [rng.getrandbits(ebits) for _ in cts]
+        es[0] |= 1 << (ebits - 1)
+        es[1] = 0
+        want_mul = [pow(c, e, pk_o.nsquare) for c, e in zip(cts, es)]
+        for off in ("0", "1"):
+            monkeypatch.setenv("PHE_NO_NPAIR_ENGINE", off)
+            pk = capi.PubKey(pk_o.n, bits, djn=True, hs=pk_o.hs)
+            assert (capi.npair_block(pk) is None) == (off == "1")
+            pk.set_comb_bits(6)
+            got = capi.array_to_ints(pk.mul(capi.ints_to_array(cts, 2 * nw), capi.ints_to_array(es, (ebits + 31) // 32)))
+            assert got == want_mul
+            if ebits == 53:
+                got = capi.array_to_ints(pk.encrypt(capi.ints_to_array(ms, nw), capi.ints_to_array(rs, (bits // 2 + 31) // 32)))
+                assert got == want_ct
+                got = capi.array_to_ints(pk.encrypt(capi.ints_to_array(ms, nw), None, make_secure=False))
+                assert got == O.encrypt_batch(pk_o, ms, None)
+                # broadcast exponent
+                got = capi.array_to_ints(pk.mul(capi.ints_to_array(cts, 2 * nw), capi.ints_to_array(es[:1], 2)))
+                assert got == [pow(c, es[0], pk_o.nsquare) for c in cts]
