@@ -283,7 +283,8 @@ def run_gpu(args):
     peak = capi.int_pipe_peak(5)
     fp64_peak = capi.fp64_pipe_peak(5)
     mix_peak = capi.product_mix_peak(5)
-    comb_ms, comb_n = ktimes["k_encrypt_comb"]
+    enc_kernel = "k_encrypt_npair" if ktimes["k_encrypt_npair"][1] else "k_encrypt_comb"
+    comb_ms, comb_n = ktimes[enc_kernel]
     roofline = None
     # dominant kernel: the two CRT halves of decrypt -- k_dec_pair (p-adic pair engine) for balanced keys, else k_powm
     pair = [capi.pair_block(sk, y) for y in (0, 1)]
@@ -335,8 +336,8 @@ def run_gpu(args):
         }
     kernels = {k: {"ms_total": v[0], "launches": v[1]} for k, v in ktimes.items() if v[1]}
     if comb_n:
-        kernels["k_encrypt_comb"]["encrypt_ops_s"] = N * args.steps / (comb_ms * 1e-3)
-        kernels["k_encrypt_comb"]["frac_of_int_pipe_peak_on_reference_work"] = W_ENC_DJN_2048 * N * args.steps / (comb_ms * 1e-3) / peak
+        kernels[enc_kernel]["encrypt_ops_s"] = N * args.steps / (comb_ms * 1e-3)
+        kernels[enc_kernel]["frac_of_int_pipe_peak_on_reference_work"] = W_ENC_DJN_2048 * N * args.steps / (comb_ms * 1e-3) / peak
     dec_ms = sum(ktimes[k][0] for k in ("k_dec_prep", "k_powm", "k_dec_tail", "k_dec_pair", "k_dec_crt"))
     if dec_ms:
         kernels["decrypt_ops_s"] = N * args.steps / (dec_ms * 1e-3)

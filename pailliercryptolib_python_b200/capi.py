@@ -89,7 +89,7 @@ def kernel_launches():
 
 
 KERNEL_KINDS = ["k_modmul", "k_powm", "k_dec_prep", "k_dec_tail", "k_encrypt_comb", "k_encrypt_finish", "k_comb_build",
-                "k_dec_pair", "k_dec_crt"]
+                "k_dec_pair", "k_dec_crt", "k_encrypt_npair", "k_mul_npair"]
 
 
 def timing_enable(on=True):

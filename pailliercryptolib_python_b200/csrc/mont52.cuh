@@ -48,7 +48,14 @@ constexpr double TWO104 = 20282409603651670423947251286016.0;     // 2^104
 constexpr double TWO104P52 = 20282409603651674927546878656512.0;  // 2^104 + 2^52
 
 // limbs per lane padded to an even count: every lane block starts 16-byte aligned
-template <int L> struct Pad { static constexpr int LP = (L + 1) & ~1; };
+// ... and never a multiple of 16 doubles: lane t reads limb j of ITS block (modulus, operands) at t * LP + j, and
+// with LP = 16 (L = 15) every lane of a group hits the same shared-memory bank -- ncu on k_encrypt_npair<15,4>:
+// short_scoreboard 3.1 stalled warps per issue, issue_active 0.36.  LP = 18 spreads LDS.128 of 4 / 8 lanes over
+// 16 / 32 distinct banks.
+template <int L> struct Pad {
+  static constexpr int LP0 = (L + 1) & ~1;
+  static constexpr int LP = (LP0 % 16 == 0) ? LP0 + 2 : LP0;
+};
 
 template <int L, int TPI> struct Shape {
   static constexpr int LP = Pad<L>::LP;
@@ -207,7 +214,8 @@ PHE_HD void mac_span(uint64_t (&acc)[L], const X& x, double y, uint64_t& hprev, 
 #ifndef PHE52_U
 #define PHE52_U 5
 #endif
-template <int L> struct Unroll { static constexpr int U = (L % PHE52_U == 0) ? PHE52_U : (L % 5 == 0) ? 5 : (L % 4 == 0) ? 4 : (L % 3 == 0) ? 3 : (L % 2 == 0) ? 2 : 1; };
+// L = 30 (one-lane pair engine of 3072-bit keys): 5 rows are 300 products = 27 KB of code, 3 rows 16 KB
+template <int L> struct Unroll { static constexpr int U = (L > 24 && L % 3 == 0) ? 3 : (L % PHE52_U == 0) ? PHE52_U : (L % 5 == 0) ? 5 : (L % 4 == 0) ? 4 : (L % 3 == 0) ? 3 : (L % 2 == 0) ? 2 : 1; };
 
 // index of limb `row` in the padded [TPI][LP] layout
 template <int L> PHE_HD int padded_index(int row) {
@@ -409,6 +417,9 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
                       const double* n, const double* dcon, uint64_t n0inv) {
   constexpr int U = Unroll<L>::U;
   constexpr int ST = PE::STRIDE;
+  // product chains in flight per batch: 20 at L <= 20; at L = 30 a batch of 20 (120 registers of temporaries next to
+  // 60 + 60 for a and the accumulators) spills, 15 = half a row does not
+  constexpr int G = (L > 20) ? (L + 1) / 2 : PHE52_G;
   constexpr uint64_t INIT = 0ull - bias_of(2 * L, 2 * L);
   uint64_t acc[L];
 #pragma unroll
@@ -422,7 +433,7 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
     mac_first(acc[0], a[0], b0, h);
     if (e_in) acc[0] += (uint64_t)e_in[0];
     q = (acc[0] * n0inv) & M52;
-    mac_span<L, 1, L>(acc, a, b0, h, 0);
+    mac_span<L, 1, L, double[L], G>(acc, a, b0, h, 0);
     topA = h;
     qd = limb_of(q);
   }
@@ -451,10 +462,10 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
         if (e_in) acc[(u + 1) % L] += (uint64_t)e_in[(row + 1) * ST];
         q = (acc[(u + 1) % L] * n0inv) & M52;
       }
-      mac_span<L, 2, L>(acc, n, qd, hN, u);
+      mac_span<L, 2, L, const double*, G>(acc, n, qd, hN, u);
       acc[u % L] += topA + hN + INIT;
       if (!last) {
-        mac_span<L, 1, L>(acc, a, bn, hA, u + 1);
+        mac_span<L, 1, L, double[L], G>(acc, a, bn, hA, u + 1);
         topA = hA;
         qd = limb_of(q);
       }

@@ -359,6 +359,102 @@ struct NPairPowmCtl {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Sliding-window exponentiation mod n^2 for an exponent SHARED by every item (classic obfuscator r^n; the program
+// format is item_powm_prog's, paillier_items.cuh): table of the odd powers T[k] = x^(2k+1), k < 2^(WS-1), as pair
+// entries in global memory.  Base: nchunks (1 or 2) chunks of chunk_words words.
+// ------------------------------------------------------------------------------------------------
+template <int L, int TPI, class Env, int WS>
+struct NPairProgCtl {
+  static constexpr int KP = Shape<L, TPI>::KP;
+  static constexpr int TS = 1 << (WS - 1);
+  const uint32_t* c_w; int chunk_words, nchunks;
+  const uint32_t* prog; int nprog;
+  uint32_t* out_w; int out_words;
+  const double* cst; double* tbl; NPairSmem sm;
+  int phase = 0, ti = 1, sq = 0, pc = 1;
+  uint32_t op = 0;
+
+  PHE_HD int next(double (&x)[L], const double*& y0, const double*& y1) {
+#pragma unroll 1
+    for (;;) {
+      switch (phase) {
+        case 0:
+          npair_conv_step<L, TPI, Env>(0, x, c_w, chunk_words, cst, sm, y0, y1);
+          phase = (nchunks > 1) ? 1 : 3;
+          return NK_X1Z;
+        case 1:
+          npair_conv_step<L, TPI, Env>(1, x, c_w, chunk_words, cst, sm, y0, y1);
+          phase = 2;
+          return NK_X1Z;
+        case 2:
+          npair_conv_step<L, TPI, Env>(2, x, c_w, chunk_words, cst, sm, y0, y1);
+          phase = 3;
+          break;
+        case 3:   // X = x in pair form: T[0]; then x^2 as the table multiplier
+          npair_store<L, TPI, Env>(tbl, x, sm);
+          if (TS > 1 && prog[0] != PROG_ONE) { phase = 4; return NK_SQR; }
+          phase = 6;
+          break;
+        case 4:   // X = x^2: park it in slot 1 (rewritten by x^3 later), Y = x^2, restart from T[0]
+          npair_store<L, TPI, Env>(tbl + 2 * KP, x, sm);
+          npair_set_y<L, TPI, Env>(tbl + 2 * KP, sm);
+          npair_load<L, TPI, Env>(x, tbl, sm);
+          y0 = sm.y0; y1 = sm.y1;
+          phase = 5;
+          return NK_MUL;
+        case 5:
+          npair_store<L, TPI, Env>(tbl + (size_t)ti * 2 * KP, x, sm);
+          if (++ti < TS) { y0 = sm.y0; y1 = sm.y1; return NK_MUL; }
+          phase = 6;
+          break;
+        case 6: {  // leading window
+          const uint32_t i0 = prog[0];
+          if (i0 == PROG_ONE) {
+            limbs_from_mem<L, TPI, Env>(x, cst + NE_OM0 * KP);
+            Env::sync();
+            limbs_to_mem<L, TPI, Env>(sm.xs0, x);
+            copy_entry<L, TPI, Env>(sm.x1, cst + NE_OM1 * KP);
+            Env::sync();
+          } else {
+            npair_load<L, TPI, Env>(x, tbl + (size_t)i0 * 2 * KP, sm);
+          }
+          pc = 1;
+          phase = 7;
+          break;
+        }
+        case 7:   // next program entry
+          if (pc > nprog) { phase = 10; break; }
+          op = prog[pc++];
+          sq = (int)(op >> 8);
+          phase = 8;
+          break;
+        case 8:
+          if (sq > 0) { --sq; return NK_SQR; }
+          phase = 7;
+          if ((op & 0xffu) != PROG_NOMUL) {
+            npair_set_y<L, TPI, Env>(tbl + (size_t)(op & 0xffu) * 2 * KP, sm);
+            y0 = sm.y0; y1 = sm.y1;
+            return NK_MUL;
+          }
+          break;
+        case 10:
+          y0 = cst + NE_ONE * KP; y1 = nullptr;
+          phase = 11;
+          return NK_Y1Z;
+        case 11:
+          npair_canon_setup<L, TPI, Env>(x, cst, sm, nullptr);
+          y0 = cst + NE_N * KP;
+          phase = 12;
+          return NK_PLAIN;
+        default:
+          npair_store_words<L, TPI, Env>(out_w, out_words, x, sm);
+          return NK_DONE;
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // DJN encrypt on the pair engine with a fixed-base comb table of pair entries:
 //   obf = prod_j T[j][digit_j(r)],  T[j][d] = hs^(d 2^(wb j)) in pair form;  ct = (1 + m n) obf mod n^2
 // With obf = V0 + V1 n:  ct = V0 + (V1 + m V0 mod n) n, and m V0 mod n = montmul(m, X0) (X0 = V0 R mod n).

@@ -59,6 +59,39 @@ template <int L, int TPI, int WIN> __global__ void __launch_bounds__(NT, 2) k_mu
   }
 }
 
+// ---- shared-exponent sliding-window modexp mod n^2 (classic obfuscator r^n) -----------------------------------------
+struct ProgNPairArgs {
+  const uint32_t* c_w;    // [count][nchunks * chunk_words]
+  int chunk_words, nchunks;
+  const uint32_t* prog; int nprog;
+  uint32_t* out_w;        // [count][out_words]
+  int out_words;
+  int count;
+  NPairCtxArgs ctx;
+  double* tbl;            // [gridDim.x * GPB][1 << (PROG_WS - 1)][2 * KP]
+};
+
+template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_powm_prog_npair(ProgNPairArgs p) {
+  using Env = DevEnv<TPI>;
+  using NS = NKShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<NS::KP>(smem, p.ctx.entries, NE_COUNT);
+  const NPairSmem sm = npair_group_smem<L, TPI>(smem);
+  const int g = threadIdx.x / TPI;
+  double* tbl = p.tbl + ((size_t)blockIdx.x * NS::GPB + g) * ((size_t)2 * NS::KP << (PROG_WS - 1));
+  const int cw = p.nchunks * p.chunk_words;
+  for (int base = blockIdx.x * NS::GPB; base < p.count; base += gridDim.x * NS::GPB) {
+    const int want = base + g;
+    const int item = want < p.count ? want : p.count - 1;
+    NPairProgCtl<L, TPI, Env, PROG_WS> ctl;
+    ctl.c_w = p.c_w + (size_t)item * cw; ctl.chunk_words = p.chunk_words; ctl.nchunks = p.nchunks;
+    ctl.prog = p.prog; ctl.nprog = p.nprog;
+    ctl.out_w = want < p.count ? p.out_w + (size_t)item * p.out_words : nullptr; ctl.out_words = p.out_words;
+    ctl.cst = smem; ctl.tbl = tbl; ctl.sm = sm;
+    npair_run<L, TPI, Env>(ctl, smem, p.ctx.n0inv, p.ctx.d_top, sm);
+  }
+}
+
 // ---- DJN encrypt ------------------------------------------------------------------------------------------------
 struct EncNPairArgs {
   const uint32_t* m_w; int m_words;

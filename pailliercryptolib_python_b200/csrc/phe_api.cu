@@ -554,6 +554,19 @@ int obfuscators_dev(const phe_pubkey* pk, const uint32_t* d_r, int r_words, size
   }
   // classic: r^n mod n^2, shared exponent n -> sliding-window program
   if (!pk->d_prog_n.p) PHE_TRY(upload(pk->d_prog_n, pk->h_prog_n));
+  if (pk->use_npair && r_words <= pk->n_words) {   // r < n: one chunk
+    for (size_t off = 0; off < count; off += CHUNK) {
+      const int c = (int)std::min(CHUNK, count - off);
+      PHE_TRY(pk->ws_tbl.ensure(pk->nops->powm_prog_npair_tbl_words(c)));
+      ProgNPairArgs a{};
+      a.c_w = d_r + off * r_words; a.chunk_words = r_words; a.nchunks = 1;
+      a.prog = pk->d_prog_n.p; a.nprog = (int)pk->h_prog_n.size() - 1;
+      a.out_w = d_obf + off * cw; a.out_words = cw; a.count = c; a.ctx = pk->nctx;
+      a.tbl = reinterpret_cast<double*>(pk->ws_tbl.p);
+      CUDA_TRY(pk->nops->powm_prog_npair(a, s));
+    }
+    return 0;
+  }
   for (size_t off = 0; off < count; off += CHUNK) {
     const int c = (int)std::min(CHUNK, count - off);
     PHE_TRY(pk->ws_tbl.ensure(pk->ops->powm_prog_tbl_words(1, c)));
@@ -821,7 +834,8 @@ int phe_timing_read(int kind, double* ms_total, unsigned long long* launches) {
 }
 const char* phe_timing_kind_name(int kind) {
   static const char* names[KK_COUNT] = {"k_modmul", "k_powm", "k_dec_prep", "k_dec_tail", "k_encrypt_comb",
-                                        "k_encrypt_finish", "k_comb_build", "k_dec_pair", "k_dec_crt"};
+                                        "k_encrypt_finish", "k_comb_build", "k_dec_pair", "k_dec_crt", "k_encrypt_npair",
+                                        "k_mul_npair"};
   return (kind >= 0 && kind < KK_COUNT) ? names[kind] : nullptr;
 }
 

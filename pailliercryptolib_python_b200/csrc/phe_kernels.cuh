@@ -263,7 +263,11 @@ template <int L> struct ModLimbs { double v[2][L]; };
 template <int L> struct PairShape {
   static constexpr int LE = (L + 2) & ~1;                       // L + 1 entries of E / D, padded to even
   static constexpr int PER_LANE = 4 * L + LE;                   // doubles of shared memory per lane
-  static constexpr size_t smem_bytes() { return (size_t)(2 * LE + PER_LANE * NT) * sizeof(double); }
+  // L > 20: the 2 L modulus limbs do not fit the register file next to the accumulators (k_dec_pair<30> spilled
+  // 256 bytes with them in registers): they are staged into shared memory instead ([2][LE] doubles after D)
+  static constexpr bool MOD_IN_SMEM = L > 20;
+  static constexpr int MOD_DOUBLES = MOD_IN_SMEM ? 2 * LE : 0;
+  static constexpr size_t smem_bytes() { return (size_t)(2 * LE + MOD_DOUBLES + PER_LANE * NT) * sizeof(double); }
 };
 
 template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(const DecPairArgs p, const ModLimbs<L> mod) {
@@ -272,6 +276,8 @@ template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(const DecPa
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_rank;
   for (int i = threadIdx.x; i < 2 * (L + 1); i += NT) smem[(i / (L + 1)) * PS::LE + i % (L + 1)] = p.dcon[i / (L + 1)][i % (L + 1)];
+  if (PS::MOD_IN_SMEM)
+    for (int i = threadIdx.x; i < 2 * L; i += NT) smem[2 * PS::LE + (i / L) * PS::LE + i % L] = mod.v[i / L][i % L];
   if (threadIdx.x == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -279,7 +285,7 @@ template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(const DecPa
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, col = threadIdx.x & 31;
-  double* wbase = smem + 2 * PS::LE + (size_t)warp * PS::PER_LANE * 32 + col;
+  double* wbase = smem + 2 * PS::LE + PS::MOD_DOUBLES + (size_t)warp * PS::PER_LANE * 32 + col;
   PairSmem<PE> sm;
   sm.xs0 = wbase;
   sm.x1 = wbase + L * 32;
@@ -307,12 +313,18 @@ template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(const DecPa
       const int y = u & 1;
       const int want = (u >> 1) * 32 + col;
       const int item = want < p.count ? want : p.count - 1;
-      double n[L];
+      if (PS::MOD_IN_SMEM) {
+        item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog[y],
+                             want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words,
+                             smem + 2 * PS::LE + y * PS::LE, smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+      } else {
+        double n[L];
 #pragma unroll
-      for (int j = 0; j < L; ++j) n[j] = y ? mod.v[1][j] : mod.v[0][j];
-      item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog[y],
-                           want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
-                           smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+        for (int j = 0; j < L; ++j) n[j] = y ? mod.v[1][j] : mod.v[0][j];
+        item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog[y],
+                             want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
+                             smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+      }
     }
   }
 }

@@ -170,7 +170,7 @@ template <int L, int TPI> struct Launch {
   template <int WIN> static cudaError_t mul_npair_w(const MulNPairArgs& p, cudaStream_t s) {
     const size_t smem = NS::smem_bytes();
     const int grid = grid_for(k_mul_npair<L, TPI, WIN>, smem, p.count, NS::GPB, 1);
-    { TimedLaunch tl_(KK_POWM, s);
+    { TimedLaunch tl_(KK_MUL_NPAIR, s);
     k_mul_npair<L, TPI, WIN><<<grid, NT, smem, s>>>(p);
     }
     return cudaGetLastError();
@@ -198,10 +198,22 @@ template <int L, int TPI> struct Launch {
   static cudaError_t encrypt_npair(const EncNPairArgs& p, cudaStream_t s) {
     const size_t smem = NS::smem_bytes();
     const int grid = grid_for(k_encrypt_npair<L, TPI>, smem, p.count, NS::GPB, 1);
-    { TimedLaunch tl_(KK_ENC_COMB, s);
+    { TimedLaunch tl_(KK_ENC_NPAIR, s);
     k_encrypt_npair<L, TPI><<<grid, NT, smem, s>>>(p);
     }
     return cudaGetLastError();
+  }
+  static cudaError_t powm_prog_npair(const ProgNPairArgs& p, cudaStream_t s) {
+    const size_t smem = NS::smem_bytes();
+    const int grid = grid_for(k_powm_prog_npair<L, TPI>, smem, p.count, NS::GPB, 1);
+    { TimedLaunch tl_(KK_MUL_NPAIR, s);
+    k_powm_prog_npair<L, TPI><<<grid, NT, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+  }
+  static size_t powm_prog_npair_tbl_words(int count) {
+    const int grid = grid_for(k_powm_prog_npair<L, TPI>, NS::smem_bytes(), count, NS::GPB, 1);
+    return (size_t)grid * NS::GPB * ((size_t)2 * NS::KP << (PROG_WS - 1)) * 2;
   }
   static cudaError_t comb_build_npair(const CombNPairArgs& p0, cudaStream_t s) {
     const size_t smem = NS::smem_bytes();
@@ -226,7 +238,8 @@ template <int L, int TPI> struct Launch {
   static constexpr ShapeOps ops() {
     return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &powm_prog, &powm_prog_tbl_words, &dec_prep, &dec_tail, &dec_crt, &inv_block, &resident_groups,
                     &encrypt_comb, &encrypt_finish, &comb_build,
-                    &mul_npair, &mul_npair_tbl_words, &encrypt_npair, &comb_build_npair};
+                    &mul_npair, &mul_npair_tbl_words, &encrypt_npair, &comb_build_npair, &powm_prog_npair,
+                    &powm_prog_npair_tbl_words};
   }
 };
 

@@ -21,6 +21,7 @@ struct InvArgs;
 struct MulNPairArgs;
 struct EncNPairArgs;
 struct CombNPairArgs;
+struct ProgNPairArgs;
 
 struct ShapeOps {
   int L, TPI, KP, GPB;   // KP: doubles per padded entry
@@ -45,6 +46,8 @@ struct ShapeOps {
   size_t (*mul_npair_tbl_words)(int win, int count);
   cudaError_t (*encrypt_npair)(const EncNPairArgs& p, cudaStream_t s);
   cudaError_t (*comb_build_npair)(const CombNPairArgs& p, cudaStream_t s);
+  cudaError_t (*powm_prog_npair)(const ProgNPairArgs& p, cudaStream_t s);
+  size_t (*powm_prog_npair_tbl_words)(int count);
 };
 
 const ShapeOps* shape_ops(int L, int TPI);   // nullptr if not built
@@ -61,7 +64,7 @@ void count_launch();
 
 // Per-kernel-kind device timing (phe_timing_* in the C ABI): when enabled every launch is bracketed by a
 // cudaEvent pair on its own stream.  Off by default (no events recorded).
-enum KernelKind { KK_MODMUL = 0, KK_POWM, KK_DEC_PREP, KK_DEC_TAIL, KK_ENC_COMB, KK_ENC_FINISH, KK_COMB_BUILD, KK_DEC_PAIR, KK_DEC_CRT, KK_COUNT };
+enum KernelKind { KK_MODMUL = 0, KK_POWM, KK_DEC_PREP, KK_DEC_TAIL, KK_ENC_COMB, KK_ENC_FINISH, KK_COMB_BUILD, KK_DEC_PAIR, KK_DEC_CRT, KK_ENC_NPAIR, KK_MUL_NPAIR, KK_COUNT };
 void timing_begin(int kind, cudaStream_t s);
 void timing_end(int kind, cudaStream_t s);
 struct TimedLaunch {   // RAII: brackets one kernel launch, counts it

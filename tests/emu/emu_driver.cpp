@@ -326,6 +326,28 @@ int do_mul_npair(const uint32_t* c, int chunk_words, const uint32_t* e, int e_wo
 }
 
 template <int L, int TPI>
+int do_powm_prog_npair(const uint32_t* c, int chunk_words, int nchunks, const uint32_t* prog, int nprog, uint32_t* out,
+                       int out_words, int count, const double* cst_e, uint64_t n0inv, uint64_t d_top) {
+  using Env = EmuEnv<TPI>;
+  constexpr int KP = phe::Shape<L, TPI>::KP;
+  constexpr int WS = 6;
+  AlignedCopy cst(cst_e, (size_t)phe::NE_COUNT * KP);
+  const int cw = nchunks * chunk_words;
+  for (int i = 0; i < count; ++i) {
+    NBufs<L, TPI> bufs;
+    std::vector<double> tbl((size_t)(2 << (WS - 1)) * KP + 2);
+    double* tp = (double*)(((uintptr_t)tbl.data() + 15) & ~(uintptr_t)15);
+    run_group<TPI>([&] {
+      phe::NPairProgCtl<L, TPI, Env, WS> ctl;
+      ctl.c_w = c + (size_t)i * cw; ctl.chunk_words = chunk_words; ctl.nchunks = nchunks; ctl.prog = prog; ctl.nprog = nprog;
+      ctl.out_w = out + (size_t)i * out_words; ctl.out_words = out_words; ctl.cst = cst.p; ctl.tbl = tp; ctl.sm = bufs.sm;
+      phe::npair_run<L, TPI, Env>(ctl, cst.p, n0inv, d_top, bufs.sm);
+    });
+  }
+  return 0;
+}
+
+template <int L, int TPI>
 int do_comb_npair(const uint32_t* hs, int chunk_words, int nwin, int wb, double* comb, const double* cst_e,
                   uint64_t n0inv, uint64_t d_top) {
   using Env = EmuEnv<TPI>;
@@ -460,6 +482,11 @@ int emu_mul_npair(int shape, int win, const uint32_t* c, int chunk_words, const 
   if (win == 3) { DISPATCH_SHAPE((NPM_CALL(3))); }
   if (win == 1) { DISPATCH_SHAPE((NPM_CALL(1))); }
   return -2;
+}
+
+int emu_powm_prog_npair(int shape, const uint32_t* c, int chunk_words, int nchunks, const uint32_t* prog, int nprog,
+                        uint32_t* out, int out_words, int count, const double* cst, uint64_t n0inv, uint64_t d_top) {
+  DISPATCH_SHAPE((do_powm_prog_npair<L, TPI>(c, chunk_words, nchunks, prog, nprog, out, out_words, count, cst, n0inv, d_top)));
 }
 
 int emu_comb_npair(int shape, const uint32_t* hs, int chunk_words, int nwin, int wb, double* comb, const double* cst,

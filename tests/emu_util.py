@@ -16,7 +16,8 @@ def shape_id(L, TPI):
 
 
 def lp(L):
-    return (L + 1) & ~1
+    v = (L + 1) & ~1
+    return v + 2 if v % 16 == 0 else v   # csrc/mont52.cuh: Pad<L> (no lane stride that is a multiple of 16 doubles)
 
 
 def to_entry(val, L, TPI):

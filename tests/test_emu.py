@@ -356,3 +356,25 @@ def test_npair_host_block_matches_python(bits):
     nc = npair_consts(pk_o.n, blk["L"], blk["TPI"], bits // 32)
     assert np.array_equal(blk["cst"].reshape(-1), nc["cst"])
     assert blk["n0inv"] == nc["n0inv"] and blk["d_top"] == nc["d_top"]
+
+
+@pytest.mark.parametrize("L,TPI,bits,ebits,nchunks", [(20, 1, 1024, 200, 1), (20, 2, 2048, 300, 2), (7, 4, 1408, 1408, 1)])
+def test_npair_shared_exponent_program(emu, L, TPI, bits, ebits, nchunks):
+    """Sliding-window program of a shared exponent on the n-adic pair engine (classic obfuscator r^n mod n^2)."""
+    from pailliercryptolib_python_b200 import capi
+    rng = random.Random(bits + ebits)
+    nw = bits // 32
+    n = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+    n2 = n * n
+    nc = npair_consts(n, L, TPI, nw)
+    lim = n if nchunks == 1 else n2
+    base = [rng.randrange(lim) for _ in range(2)] + [0, 1, lim - 1]
+    bw = to_words(base, nchunks * nw)
+    for e in (rng.getrandbits(ebits) | (1 << (ebits - 1)), 1 << (ebits - 1), 1, 0, 0b1000001000000):
+        prog = capi.host_powm_program(e, (ebits + 31) // 32 + 1)
+        pa = np.array(prog, dtype=np.uint32)
+        out = np.zeros((len(base), 2 * nw), dtype=np.uint32)
+        rc = emu.emu_powm_prog_npair(shape_id(L, TPI), P(bw), nw, nchunks, P(pa), len(prog) - 1, P(out), 2 * nw, len(base),
+                                     PD(nc["cst"]), U64(nc["n0inv"]), U64(nc["d_top"]))
+        assert rc == 0
+        assert from_words(out) == [pow(b, e, n2) for b in base]

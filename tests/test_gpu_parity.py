@@ -279,7 +279,7 @@ def test_timing_hooks_and_pipe_peak(key2048):
     sk.decrypt(ct)
     t = capi.timing_read()
     capi.timing_enable(False)
-    assert t["k_encrypt_comb"][1] == 1 and t["k_dec_pair"][1] == 1 and t["k_dec_pair"][0] > 0 and t["k_dec_crt"][1] == 1
+    assert t["k_encrypt_npair"][1] == 1 and t["k_encrypt_comb"][1] == 0 and t["k_dec_pair"][1] == 1 and t["k_dec_pair"][0] > 0 and t["k_dec_crt"][1] == 1
     peak = capi.int_pipe_peak(2)
     assert 4e12 < peak < 12e12   # IMAD.WIDE.U32: one warp instruction per 4 cycles per SM sub-partition
     assert 10e12 < capi.fp64_pipe_peak(2) < 20e12      # DFMA: one warp instruction per 2 cycles per sub-partition

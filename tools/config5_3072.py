@@ -27,17 +27,23 @@ def main():
     ap.add_argument("--count", type=int, default=100000)
     ap.add_argument("--bits", type=int, default=3072)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--scheme", default="djn", choices=["djn", "classic"], help="classic: obf = r^n mod n^2, r < n")
     args = ap.parse_args()
     bits, N = args.bits, args.count
     nw = bits // 32
-    pk_o, sk_o = O.seeded_keypair(bits, 77)
-    pk = capi.PubKey(pk_o.n, bits, djn=True, hs=pk_o.hs)
+    djn = args.scheme == "djn"
+    pk_o, sk_o = O.seeded_keypair(bits, 77, djn=djn)
+    pk = capi.PubKey(pk_o.n, bits, djn=djn, hs=pk_o.hs if djn else None)
     sk = capi.PrivKey(pk, sk_o.p, sk_o.q)
     rng = np.random.Generator(np.random.PCG64(20240611))
     m_np = np.zeros((N, nw), dtype=np.uint32)
     m_np[:, :2] = rng.integers(0, 1 << 32, size=(N, 2), dtype=np.uint64).astype(np.uint32)
     m_np[:, 1] &= (1 << 21) - 1                      # 53-bit plaintexts (float64 mantissas), as configs[1]
-    r_np = rng.integers(0, 1 << 32, size=(N, nw // 2), dtype=np.uint64).astype(np.uint32)
+    rw = nw // 2 if djn else nw
+    r_np = rng.integers(0, 1 << 32, size=(N, rw), dtype=np.uint64).astype(np.uint32)
+    if not djn:
+        r_np[:, -1] &= (1 << 30) - 1                 # r < 2^(bits - 2) < n
+        r_np[:, 0] |= 1                              # r >= 1
     dev = torch.device("cuda", 0)
     m = torch.from_numpy(m_np.view(np.int32)).to(dev)
     r = torch.from_numpy(r_np.view(np.int32)).to(dev)
@@ -49,7 +55,7 @@ def main():
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         torch.cuda.synchronize()
         e0.record()
-        pk.encrypt_dev(m.data_ptr(), N, r.data_ptr(), nw // 2, ct.data_ptr(), stream)
+        pk.encrypt_dev(m.data_ptr(), N, r.data_ptr(), rw, ct.data_ptr(), stream)
         e1.record()
         sk.decrypt_dev(ct.data_ptr(), N, out.data_ptr(), stream)
         e2.record()
@@ -64,7 +70,7 @@ def main():
     rs = capi.array_to_ints(r_np[idx])
     ok = capi.array_to_ints(ct_h) == O.encrypt_batch(pk_o, ms, rs)
     print(json.dumps({
-        "workload": "%d-bit DJN key, batch=%d encrypt + decrypt on 1 GPU (BASELINE configs[4])" % (bits, N),
+        "workload": "%d-bit %s key, batch=%d encrypt + decrypt on 1 GPU%s" % (bits, args.scheme, N, " (BASELINE configs[4])" if bits == 3072 and djn else ""),
         "encrypt_ops_s": N / (best[0] * 1e-3), "decrypt_ops_s": N / (best[1] * 1e-3),
         "ops_s": 2 * N / (sum(best) * 1e-3), "ms_encrypt": best[0], "ms_decrypt": best[1],
         "comb_bits": pk.comb_bits, "round_trip": True, "parity_spot_check": bool(ok)}))
