@@ -66,11 +66,12 @@ int phe_product_mix_peak(int reps, double* products_per_s);
 int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const uint32_t* hs, int randbits,
                       phe_pubkey** out);
 void phe_pubkey_destroy(phe_pubkey* pk);
-/* Digit width (1..16 bits, 0 = automatic from the free device memory) of the DJN fixed-base comb table
- * T[j][d] = hs^(d 2^(bits j)): an obfuscated encrypt costs randbits / bits + 2 Montgomery products and the table
- * nwin * 2^bits entries of HBM (2.7 GB at 16 bits for a 2048-bit key).  Takes effect at the next table build
- * (the first obfuscated encrypt, or immediately if the width changes).  The environment variable PHE_COMB_BITS
- * sets the default.  phe_pubkey_comb_bits returns the width in use (0 before the table exists). */
+/* Digit width (1..22 bits, 0 = automatic) of the DJN fixed-base comb table T[j][d] = hs^(d 2^(bits j)): an obfuscated
+ * encrypt costs randbits / bits table products and the table nwin * 2^bits entries of HBM (2.7 GB at 16 bits, 35 GB at
+ * 20 bits for a 2048-bit key).  Automatic: a 12-bit table at first, promoted to the widest one that fits a quarter of
+ * the free device memory (at most 20 bits / 40 GB) once the key has encrypted 32768 elements.  A pinned width takes
+ * effect at the next table build (the first obfuscated encrypt, or immediately if the width changes).  The environment
+ * variable PHE_COMB_BITS sets the default.  phe_pubkey_comb_bits returns the width in use (0 before a table exists). */
 int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits);
 int phe_pubkey_comb_bits(const phe_pubkey* pk);
 int phe_pubkey_bits(const phe_pubkey* pk);

@@ -365,7 +365,7 @@ struct phe_pubkey {
   int comb_bits_wanted = 0;       // 0: choose from the free device memory
   mutable bool comb_ready = false, comb_wide = false;
   mutable size_t comb_seen = 0;   // elements encrypted so far under the automatic width (promotion counter)
-  mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_r, ws_tbl;  // op workspaces
+  mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_r, ws_tbl, ws_inv;  // op workspaces
   mutable DevBuf d_prog_n;                         // classic scheme: sliding-window program of the exponent n
   std::vector<uint32_t> h_prog_n;
   mutable std::mutex mu;
@@ -661,57 +661,87 @@ int add_dev_impl(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uin
 
 // out[i] = a[i]^-1 mod n^2 for count device rows (Montgomery's trick, recursive over block totals; the last <= 16
 // values are inverted on the host).  Fails with "not invertible" if any a[i] shares a factor with n.
+// Batched modular inverse (Montgomery's trick), level by level: every level turns `count` elements into count / block
+// block totals (k_inv_block, prefix), the totals are inverted one level down, and the way back (unwind) turns the inverse
+// of a total into the inverses of its elements.  Block sizes: ~count / resident groups (>= 4) while there is parallel
+// work, then ~sqrt(count), then one block, so that exactly ONE number is left for the host's extended Euclid (3 ms at
+// 4096 bits).  All levels live in one persistent workspace of the key (no cudaMalloc / cudaFree per call).
 int invert_dev_impl(const phe_pubkey* pk, const uint32_t* d_a, size_t count, uint32_t* d_out, cudaStream_t s) {
   const ShapeOps* o = pk->ops;
-  const int cw = 2 * pk->n_words;
+  const size_t cw = 2 * (size_t)pk->n_words;
   if (count == 0) return 0;
-  if (count <= 16) {
-    std::vector<uint32_t> h(count * cw);
-    CUDA_TRY(cudaMemcpyAsync(h.data(), d_a, h.size() * 4, cudaMemcpyDeviceToHost, s));
+  struct Lvl { size_t count, block, nblocks, padded, in_pad, out_pad, P, totals, tinv; };
+  std::vector<Lvl> lv;
+  const size_t groups = (size_t)o->resident_groups();
+  size_t words = 0;
+  auto carve = [&](size_t n) { const size_t at = words; words += (n + 3) & ~(size_t)3; return at; };
+  for (size_t c = count; c > 1;) {
+    Lvl l{};
+    l.count = c;
+    if (c <= 32) l.block = c;
+    else if (c <= 1024) { l.block = 1; while (l.block * l.block < c) ++l.block; }
+    else { l.block = (c + groups - 1) / groups; if (l.block < 4) l.block = 4; if (l.block > 256) l.block = 256; }
+    l.nblocks = (c + l.block - 1) / l.block;
+    l.padded = l.nblocks * l.block;
+    if (l.padded != c) { l.in_pad = carve(l.padded * cw); l.out_pad = carve(l.padded * cw); }
+    l.P = carve(l.padded * EW(o));
+    l.totals = carve(l.nblocks * cw);
+    l.tinv = carve(l.nblocks * cw);
+    lv.push_back(l);
+    c = l.nblocks;
+  }
+  const size_t base = carve(cw);   // the single value the host inverts when count == 1
+  PHE_TRY(pk->ws_inv.ensure(words));
+  uint32_t* W = pk->ws_inv.p;
+  // forward: prefix products and block totals
+  const uint32_t* src = d_a;
+  std::vector<const uint32_t*> srcs(lv.size());
+  std::vector<uint32_t*> dsts(lv.size());
+  for (size_t k = 0; k < lv.size(); ++k) {
+    const Lvl& l = lv[k];
+    uint32_t* dst = (k == 0) ? d_out : W + lv[k - 1].tinv;
+    if (l.padded != l.count) {   // pad with ones so that every block has the same length
+      std::vector<uint32_t> ones((l.padded - l.count) * cw, 0);
+      for (size_t i = 0; i < l.padded - l.count; ++i) ones[i * cw] = 1;
+      CUDA_TRY(cudaMemcpyAsync(W + l.in_pad, src, l.count * cw * 4, cudaMemcpyDeviceToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(W + l.in_pad + l.count * cw, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaStreamSynchronize(s));   // `ones` is a stack-lifetime staging buffer
+      src = W + l.in_pad;
+    }
+    srcs[k] = src; dsts[k] = dst;
+    InvArgs a{};
+    a.c_w = src; a.nwords = (int)cw; a.count = (int)l.padded; a.block = (int)l.block;
+    a.P = reinterpret_cast<double*>(W + l.P); a.total_w = W + l.totals; a.ctx = pk->ctx;
+    if (o->inv_block(a, false, s) != cudaSuccess) return fail("phe_invert: prefix kernel launch failed");
+    src = W + l.totals;
+  }
+  // the one inverse left: on the host
+  {
+    const uint32_t* one_src = lv.empty() ? d_a : W + lv.back().totals;
+    uint32_t* one_dst = lv.empty() ? d_out : W + lv.back().tinv;
+    std::vector<uint32_t> h(cw);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), one_src, cw * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     try {
-      for (size_t i = 0; i < count; ++i)
-        hbn::modinv(BN::from_words(&h[i * cw], cw), pk->nsq).to_words(&h[i * cw], cw);
+      hbn::modinv(BN::from_words(h.data(), cw), pk->nsq).to_words(h.data(), cw);
     } catch (const std::exception&) { return fail("phe_invert: an element is not invertible modulo n^2"); }
-    CUDA_TRY(cudaMemcpyAsync(d_out, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaStreamSynchronize(s));   // h is a stack-lifetime staging buffer
-    return 0;
+    CUDA_TRY(cudaMemcpyAsync(W + base, h.data(), cw * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(one_dst, W + base, cw * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));     // h is a stack-lifetime staging buffer
   }
-  const size_t groups = (size_t)o->resident_groups();
-  size_t block = (count + groups - 1) / groups;
-  if (block < 4) block = 4;
-  if (block > 256) block = 256;
-  const size_t nblocks = (count + block - 1) / block, padded = nblocks * block;
-  DevBuf in_pad, P, totals, tinv, out_pad;
-  const uint32_t* src = d_a;
-  uint32_t* dst = d_out;
-  int rc = 0;
-  if (padded != count) {        // pad with ones so that every block has the same length
-    rc = in_pad.ensure(padded * cw);
-    if (!rc) rc = out_pad.ensure(padded * cw);
-    if (!rc) {
-      std::vector<uint32_t> ones((padded - count) * cw, 0);
-      for (size_t i = 0; i < padded - count; ++i) ones[i * cw] = 1;
-      if (cudaMemcpyAsync(in_pad.p, d_a, count * cw * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
-          cudaMemcpyAsync(in_pad.p + count * cw, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-          cudaStreamSynchronize(s) != cudaSuccess) rc = fail("phe_invert: padding copy failed");
-      src = in_pad.p; dst = out_pad.p;
-    }
+  // backward: unwind every level
+  for (size_t k = lv.size(); k-- > 0;) {
+    const Lvl& l = lv[k];
+    InvArgs a{};
+    a.c_w = srcs[k]; a.nwords = (int)cw; a.count = (int)l.padded; a.block = (int)l.block;
+    a.P = reinterpret_cast<double*>(W + l.P); a.tinv_w = W + l.tinv;
+    a.out_w = (l.padded != l.count) ? W + l.out_pad : dsts[k]; a.ctx = pk->ctx;
+    if (o->inv_block(a, true, s) != cudaSuccess) return fail("phe_invert: unwind kernel launch failed");
+    if (l.padded != l.count)
+      CUDA_TRY(cudaMemcpyAsync(dsts[k], W + l.out_pad, l.count * cw * 4, cudaMemcpyDeviceToDevice, s));
   }
-  if (!rc) rc = P.ensure(padded * EW(o));
-  if (!rc) rc = totals.ensure(nblocks * cw);
-  if (!rc) rc = tinv.ensure(nblocks * cw);
-  InvArgs a{};
-  a.c_w = src; a.nwords = cw; a.count = (int)padded; a.block = (int)block;
-  a.P = reinterpret_cast<double*>(P.p); a.total_w = totals.p; a.tinv_w = tinv.p; a.out_w = dst; a.ctx = pk->ctx;
-  if (!rc && o->inv_block(a, false, s) != cudaSuccess) rc = fail("phe_invert: prefix kernel launch failed");
-  if (!rc) rc = invert_dev_impl(pk, totals.p, nblocks, tinv.p, s);
-  if (!rc && o->inv_block(a, true, s) != cudaSuccess) rc = fail("phe_invert: unwind kernel launch failed");
-  if (!rc && padded != count &&
-      cudaMemcpyAsync(d_out, out_pad.p, count * cw * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail("phe_invert: copy failed");
-  if (cudaStreamSynchronize(s) != cudaSuccess && !rc) rc = fail("phe_invert: kernel failed");
-  for (DevBuf* b : {&in_pad, &P, &totals, &tinv, &out_pad}) b->release();
-  return rc;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
 }
 
 int mul_dev_impl(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
@@ -884,7 +914,7 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
 
 void phe_pubkey_destroy(phe_pubkey* pk) {
   if (!pk) return;
-  for (DevBuf* b : {&pk->d_ctx, &pk->d_nctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
+  for (DevBuf* b : {&pk->ws_inv, &pk->d_ctx, &pk->d_nctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
   delete pk;
 }
 int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits) {

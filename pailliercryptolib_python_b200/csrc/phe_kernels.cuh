@@ -263,21 +263,25 @@ template <int L> struct ModLimbs { double v[2][L]; };
 template <int L> struct PairShape {
   static constexpr int LE = (L + 2) & ~1;                       // L + 1 entries of E / D, padded to even
   static constexpr int PER_LANE = 4 * L + LE;                   // doubles of shared memory per lane
+  // threads per CTA.  L = 30 needs 1216 B of shared memory per lane: one 128-thread CTA per SM is all that fits; a
+  // 160-thread CTA (a fifth warp, 195 KB) was measured and is no faster (518 vs 513 ms per 100 000 at 3072-bit keys)
+  static constexpr int NTP = NT;
+  static constexpr int CTAS = (L > 20) ? 1 : 2;
   // L > 20: the 2 L modulus limbs do not fit the register file next to the accumulators (k_dec_pair<30> spilled
   // 256 bytes with them in registers): they are staged into shared memory instead ([2][LE] doubles after D)
   static constexpr bool MOD_IN_SMEM = L > 20;
   static constexpr int MOD_DOUBLES = MOD_IN_SMEM ? 2 * LE : 0;
-  static constexpr size_t smem_bytes() { return (size_t)(2 * LE + MOD_DOUBLES + PER_LANE * NT) * sizeof(double); }
+  static constexpr size_t smem_bytes() { return (size_t)(2 * LE + MOD_DOUBLES + PER_LANE * NTP) * sizeof(double); }
 };
 
-template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(const DecPairArgs p, const ModLimbs<L> mod) {
+template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<L>::CTAS) k_dec_pair(const DecPairArgs p, const ModLimbs<L> mod) {
   using PE = DevPairEnv;
   using PS = PairShape<L>;
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_rank;
-  for (int i = threadIdx.x; i < 2 * (L + 1); i += NT) smem[(i / (L + 1)) * PS::LE + i % (L + 1)] = p.dcon[i / (L + 1)][i % (L + 1)];
+  for (int i = threadIdx.x; i < 2 * (L + 1); i += PS::NTP) smem[(i / (L + 1)) * PS::LE + i % (L + 1)] = p.dcon[i / (L + 1)][i % (L + 1)];
   if (PS::MOD_IN_SMEM)
-    for (int i = threadIdx.x; i < 2 * L; i += NT) smem[2 * PS::LE + (i / L) * PS::LE + i % L] = mod.v[i / L][i % L];
+    for (int i = threadIdx.x; i < 2 * L; i += PS::NTP) smem[2 * PS::LE + (i / L) * PS::LE + i % L] = mod.v[i / L][i % L];
   if (threadIdx.x == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -292,11 +296,11 @@ template <int L> __global__ void __launch_bounds__(NT, 2) k_dec_pair(const DecPa
   sm.y0 = wbase + 2 * L * 32;
   sm.y1 = wbase + 3 * L * 32;
   sm.e = reinterpret_cast<int64_t*>(wbase + 4 * L * 32);
-  double* tbl = p.tbl + ((size_t)blockIdx.x * (NT / 32) + warp) * ((size_t)p.slots * 2 * L * 32) + col;
+  double* tbl = p.tbl + ((size_t)blockIdx.x * (PS::NTP / 32) + warp) * ((size_t)p.slots * 2 * L * 32) + col;
 
   const int blocks = (p.count + 31) / 32;
   const int units = 2 * blocks;
-  const int warps = gridDim.x * (NT / 32);
+  const int warps = gridDim.x * (PS::NTP / 32);
   const int rem = units % warps;
   const int units1 = units - rem;                           // phase 1: a whole number of rounds
   // phase 2 (the remainder) is reserved for the first CTA of each SM when it fits one unit per such warp

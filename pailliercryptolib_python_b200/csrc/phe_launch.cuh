@@ -18,10 +18,10 @@ inline int sm_count() {
 }
 
 // grid.x for a persistent-style launch: a whole number of resident waves, never more CTAs than work
-template <class K> int grid_for(K kernel, size_t smem, int count, int gpb, int ny) {
+template <class K> int grid_for(K kernel, size_t smem, int count, int gpb, int ny, int threads = NT) {
   int occ = 0;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NT, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
   if (occ < 1) occ = 1;
   const int resident = std::max(1, sm_count() * occ / ny);
   const int need = (count + gpb - 1) / gpb;
@@ -245,9 +245,10 @@ template <int L, int TPI> struct Launch {
 
 // Launcher of the one-bignum-per-lane pair engine (L = limbs of p, q).
 template <int L> struct PairLaunch {
+  static constexpr int NTP = PairShape<L>::NTP;
   static int grid(int count) {   // both moduli: 2 * ceil(count / 32) warp units, NT / 32 warps per CTA
     const int units = 2 * ((count + 31) / 32);
-    return grid_for(k_dec_pair<L>, PairShape<L>::smem_bytes(), units, NT / 32, 1);
+    return grid_for(k_dec_pair<L>, PairShape<L>::smem_bytes(), units, NTP / 32, 1, NTP);
   }
   // mod_p, mod_q: L limbs each (doubles); p.sched: >= 2 + number of SMs ints, zeroed here on the stream
   static cudaError_t dec_pair(const DecPairArgs& p, const double* mod_p, const double* mod_q, cudaStream_t s) {
@@ -258,12 +259,12 @@ template <int L> struct PairLaunch {
     cudaError_t e = cudaMemsetAsync(p.sched, 0, (size_t)(2 + sm_count()) * sizeof(int), s);
     if (e != cudaSuccess) return e;
     { TimedLaunch tl_(KK_DEC_PAIR, s);
-    k_dec_pair<L><<<g, NT, smem, s>>>(p, m);
+    k_dec_pair<L><<<g, NTP, smem, s>>>(p, m);
     }
     return cudaGetLastError();
   }
   static size_t tbl_words(int count, int slots) {   // u32 words
-    return (size_t)grid(count) * (NT / 32) * slots * 2 * L * 32 * 2;
+    return (size_t)grid(count) * (NTP / 32) * slots * 2 * L * 32 * 2;
   }
   static constexpr PairOps ops() { return PairOps{L, &dec_pair, &tbl_words}; }
 };
