@@ -21,7 +21,7 @@ SYMBOLS = [
     "phe_privkey_create", "phe_privkey_destroy", "phe_privkey_get_p", "phe_privkey_get_q", "phe_keygen",
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
-    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
+    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_dev_alloc", "phe_dev_free", "phe_copy", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
     "phe_product_mix_peak",
 ]

@@ -337,11 +337,59 @@ struct PlainText : Packed {
   explicit PlainText(Packed p) : Packed(std::move(p)) {}
 };
 
+// Ciphertext batches stay in HBM between operations: encrypt / + / * / modinv leave their result on the device only
+// (dev set, host_valid false, data empty) and take operands from wherever they are -- the C ABI accepts host and
+// device pointers alike.  Anything that looks at the words (indexing, getTexts, to_packed, pickle ...) goes through
+// H(), which brings the batch to the host once.
 struct CipherText : Packed {
   PubPtr pk;
+  mutable uint32_t* dev = nullptr;
+  mutable bool host_valid = true;
   CipherText(PubPtr k, Packed p) : Packed(std::move(p)), pk(std::move(k)) {
     const size_t cw = 2 * (size_t)pk->n_words;
     if (stride != cw) { data = restride(cw, "ipclCipherText"); stride = cw; }
+  }
+  CipherText(PubPtr k, size_t n, uint32_t* d) : pk(std::move(k)), dev(d), host_valid(false) {   // device-resident result
+    count = n; stride = 2 * (size_t)pk->n_words;
+  }
+  CipherText(const CipherText&) = delete;
+  CipherText& operator=(const CipherText&) = delete;
+  ~CipherText() { if (dev) phe_dev_free(dev); }
+  size_t words() const { return count * stride; }
+  void sync_host() const {
+    if (host_valid) return;
+    Words& d = const_cast<Words&>(data);
+    d.resize(words());
+    int rc;
+    {
+      py::gil_scoped_release nogil;
+      rc = phe_copy(d.data(), dev, words() * 4);
+    }
+    if (rc) throw_phe("ipclCipherText (device -> host)");
+    host_valid = true;
+  }
+  const uint32_t* operand() const { return host_valid ? data.data() : dev; }   // host or device pointer for the C ABI
+};
+inline const CipherText& H(const CipherText& c) { c.sync_host(); return c; }
+
+// Output buffer of a ciphertext-valued operation: device memory when it can be had, else a host vector.
+struct CtOut {
+  PubPtr pk;
+  size_t count;
+  uint32_t* dev = nullptr;
+  Packed host;
+  CtOut(const PubPtr& k, size_t n) : pk(k), count(n) {
+    const size_t cw = 2 * (size_t)pk->n_words;
+    if (n == 0 || phe_dev_alloc(pk->h, n * cw, &dev) != 0) {
+      dev = nullptr;
+      host.count = n; host.stride = cw; host.data.resize(n * cw);
+    }
+  }
+  uint32_t* ptr() { return dev ? dev : host.data.data(); }
+  void drop() { if (dev) { phe_dev_free(dev); dev = nullptr; } }
+  std::shared_ptr<CipherText> finish() {
+    if (dev) { uint32_t* d = dev; dev = nullptr; return std::make_shared<CipherText>(pk, count, d); }
+    return std::make_shared<CipherText>(pk, std::move(host));
   }
 };
 
@@ -353,16 +401,14 @@ std::shared_ptr<CipherText> encrypt(const PubPtr& pk, const PlainText& pt, bool 
   const uint32_t* m = pt.data.data();
   size_t m_words = pt.stride;
   if (pt.stride > (size_t)pk->n_words) { wide = pt.restride((size_t)pk->n_words, "encrypt"); m = wide.data(); m_words = (size_t)pk->n_words; }
-  Packed out;
-  out.count = pt.count; out.stride = 2 * (size_t)pk->n_words;
-  out.data.resize(out.count * out.stride);
+  CtOut out(pk, pt.count);
   int rc;
   {
     py::gil_scoped_release nogil;
-    rc = phe_encrypt_compact(pk->h, m, (int)m_words, pt.count, nullptr, 0, make_secure ? 1 : 0, out.data.data());
+    rc = phe_encrypt_compact(pk->h, m, (int)m_words, pt.count, nullptr, 0, make_secure ? 1 : 0, out.ptr());
   }
-  if (rc) throw_phe("encrypt");
-  return std::make_shared<CipherText>(pk, std::move(out));
+  if (rc) { out.drop(); throw_phe("encrypt"); }
+  return out.finish();
 }
 
 Packed obfuscate(const PubPtr& pk, Packed ct) {
@@ -401,7 +447,7 @@ struct PrivateKey {
     int rc;
     {
       py::gil_scoped_release nogil;
-      rc = phe_decrypt(h, ct.data.data(), ct.count, out.data.data());
+      rc = phe_decrypt(h, ct.operand(), ct.count, out.data.data());
     }
     if (rc) throw_phe("decrypt");
     return PlainText(std::move(out));
@@ -411,31 +457,27 @@ struct PrivateKey {
 std::shared_ptr<CipherText> ct_add(const CipherText& a, const CipherText& b) {
   if (cmp(a.pk->n, b.pk->n) != 0) throw std::runtime_error("CipherText +: two different public keys detected");
   if (b.count != a.count && b.count != 1) throw std::runtime_error("CipherText +: size mismatch");
-  Packed out;
-  out.count = a.count; out.stride = a.stride;
-  out.data.resize(a.data.size());
+  CtOut out(a.pk, a.count);
   int rc;
   {
     py::gil_scoped_release nogil;
-    rc = phe_add(a.pk->h, a.data.data(), a.count, b.data.data(), b.count, out.data.data());
+    rc = phe_add(a.pk->h, a.operand(), a.count, b.operand(), b.count, out.ptr());
   }
-  if (rc) throw_phe("CipherText +");
-  return std::make_shared<CipherText>(a.pk, std::move(out));
+  if (rc) { out.drop(); throw_phe("CipherText +"); }
+  return out.finish();
 }
 
 // Row-wise inverse modulo n^2 (not part of the reference module: the reference's Python inverts with gmpy2 one element
 // at a time; pailliercryptolib_python_b200/ipcl_python.py calls this instead).
 std::shared_ptr<CipherText> ct_modinv(const CipherText& a) {
-  Packed out;
-  out.count = a.count; out.stride = a.stride;
-  out.data.resize(a.data.size());
+  CtOut out(a.pk, a.count);
   int rc;
   {
     py::gil_scoped_release nogil;
-    rc = phe_invert(a.pk->h, a.data.data(), a.count, out.data.data());
+    rc = phe_invert(a.pk->h, a.operand(), a.count, out.ptr());
   }
-  if (rc) throw_phe("CipherText modinv");
-  return std::make_shared<CipherText>(a.pk, std::move(out));
+  if (rc) { out.drop(); throw_phe("CipherText modinv"); }
+  return out.finish();
 }
 
 std::shared_ptr<CipherText> ct_mul(const CipherText& a, const PlainText& b) {
@@ -447,16 +489,14 @@ std::shared_ptr<CipherText> ct_mul(const CipherText& a, const PlainText& b) {
       if (b.at(i)[j]) { ew = j + 1; break; }
   if (ew > (size_t)a.pk->n_words) throw std::runtime_error("CipherText *: plaintext larger than n");
   const Words e = b.restride(ew, "CipherText *");
-  Packed out;
-  out.count = a.count; out.stride = a.stride;
-  out.data.resize(a.data.size());
+  CtOut out(a.pk, a.count);
   int rc;
   {
     py::gil_scoped_release nogil;
-    rc = phe_mul(a.pk->h, a.data.data(), a.count, e.data(), (int)ew, b.count, out.data.data());
+    rc = phe_mul(a.pk->h, a.operand(), a.count, e.data(), (int)ew, b.count, out.ptr());
   }
-  if (rc) throw_phe("CipherText *");
-  return std::make_shared<CipherText>(a.pk, std::move(out));
+  if (rc) { out.drop(); throw_phe("CipherText *"); }
+  return out.finish();
 }
 
 // ------------------------------------------------------------------------------------------------ context / hybrid
@@ -585,13 +625,13 @@ PYBIND11_MODULE(ipcl_bindings, m) {
       .def_property_readonly("isDJN", &PublicKey::djn)
       .def_property_readonly("randbits", &PublicKey::randbits)
       .def("encrypt", [](const PubPtr& s, const PlainText& pt, bool make_secure) { return encrypt(s, pt, make_secure); })
-      .def("encrypt_tolist", [](const PubPtr& s, const PlainText& pt, bool make_secure) { return encrypt(s, pt, make_secure)->texts(); })
+      .def("encrypt_tolist", [](const PubPtr& s, const PlainText& pt, bool make_secure) { return H(*encrypt(s, pt, make_secure)).texts(); })
       .def("apply_obfuscator", [](const PubPtr& s, const BigNumber& ct) {
         return std::make_shared<BigNumber>(obfuscate(s, Packed::from_list({ct})).element(0));
       })
-      .def("apply_obfuscator", [](const PubPtr& s, const CipherText& ct) { return obfuscate(s, ct).texts(); })
+      .def("apply_obfuscator", [](const PubPtr& s, const CipherText& ct) { return obfuscate(s, H(ct)).texts(); })
       .def("apply_obfuscator_packed", [](const PubPtr& s, const CipherText& ct) {
-        return std::make_shared<CipherText>(s, obfuscate(s, ct));
+        return std::make_shared<CipherText>(s, obfuscate(s, H(ct)));
       })
       .def(py::pickle([](const PublicKey& s) { return pubkey_state(s); }, [](py::tuple t) { return pubkey_from_state(t); }));
 
@@ -655,24 +695,24 @@ PYBIND11_MODULE(ipcl_bindings, m) {
       .def(py::init([](const PubPtr& pk, const py::list& data) { return std::make_shared<CipherText>(pk, Packed::from_list(data.cast<std::vector<BigNumber>>())); }))
       .def(py::init([](const PubPtr& pk, const py::array_t<uint32_t, py::array::c_style | py::array::forcecast>& a) { return std::make_shared<CipherText>(pk, Packed::from_u32_array(a)); }))
       .def_static("from_packed", [](const PubPtr& pk, const py::array_t<uint32_t, py::array::c_style | py::array::forcecast>& a) { return std::make_shared<CipherText>(pk, Packed::from_matrix(a)); })
-      .def("to_packed", [](const CipherText& s) { return s.to_matrix(s.stride); })
+      .def("to_packed", [](const CipherText& s) { return H(s).to_matrix(s.stride); })
       .def("__repr__", [](const CipherText& s) { return "<ipclCipherText " + addr_tag(&s) + ">"; })
       .def("__str__", [](const CipherText& s) { return "<ipclCipherText " + addr_tag(&s) + ">"; })
-      .def("__getitem__", [](const CipherText& s, size_t i) { return std::make_shared<BigNumber>(s.element(i)); })
-      .def("__getitem__", [](const CipherText& s, const py::slice& sl) { size_t len; const size_t st = slice_bounds(s, sl, &len); return std::make_shared<CipherText>(s.pk, s.chunk(st, len)); })
+      .def("__getitem__", [](const CipherText& s, size_t i) { return std::make_shared<BigNumber>(H(s).element(i)); })
+      .def("__getitem__", [](const CipherText& s, const py::slice& sl) { size_t len; const size_t st = slice_bounds(s, sl, &len); return std::make_shared<CipherText>(s.pk, H(s).chunk(st, len)); })
       .def("modinv", [](const CipherText& a) { return ct_modinv(a); })
       .def("__add__", [](const CipherText& a, const CipherText& b) { return ct_add(a, b); })
       .def("__add__", [](const CipherText& a, const PlainText& b) { return ct_add(a, *encrypt(a.pk, b, false)); })
       .def("__mul__", [](const CipherText& a, const PlainText& b) { return ct_mul(a, b); })
       .def("__len__", [](const CipherText& s) { return s.count; })
-      .def("getCipherText", [](const CipherText& s, size_t i) { return std::make_shared<CipherText>(s.pk, s.chunk(i, 1)); })
-      .def("rotate", [](const CipherText& s, int shift) { return std::make_shared<CipherText>(s.pk, s.rotated(shift)); })
-      .def("getElementVec", [](const CipherText& s, size_t i) { return s.element_vec(i); })
-      .def("getElementHex", [](const CipherText& s, size_t i) { return s.element_hex(i); })
+      .def("getCipherText", [](const CipherText& s, size_t i) { return std::make_shared<CipherText>(s.pk, H(s).chunk(i, 1)); })
+      .def("rotate", [](const CipherText& s, int shift) { return std::make_shared<CipherText>(s.pk, H(s).rotated(shift)); })
+      .def("getElementVec", [](const CipherText& s, size_t i) { return H(s).element_vec(i); })
+      .def("getElementHex", [](const CipherText& s, size_t i) { return H(s).element_hex(i); })
       .def_property_readonly("public_key", [](const CipherText& s) { return s.pk; })
-      .def("getTexts", [](const CipherText& s) { return s.texts(); })
+      .def("getTexts", [](const CipherText& s) { return H(s).texts(); })
       .def("getSize", [](const CipherText& s) { return s.count; })
-      .def(py::pickle([](const CipherText& s) { return py::make_tuple(s.count, s.state_list(), pubkey_state(*s.pk)); },
+      .def(py::pickle([](const CipherText& s) { return py::make_tuple(s.count, H(s).state_list(), pubkey_state(*s.pk)); },
                       [](const py::tuple& t) {
                         PubPtr pk = pubkey_from_state(t[2].cast<py::tuple>());
                         return std::make_shared<CipherText>(pk, Packed::from_state_list(t[0].cast<size_t>(), t[1].cast<py::list>()));

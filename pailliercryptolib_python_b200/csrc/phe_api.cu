@@ -1095,7 +1095,32 @@ int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint
   return mul_dev_impl(pk, d_ct, n, d_e, e_words, ne, exp_bits, d_out, (cudaStream_t)stream);
 }
 
-// ---- host-buffer entry points ------------------------------------------------------------------------------
+// ---- device memory for callers that keep ciphertexts resident between calls (the pybind11 shim) -----------------
+int phe_dev_alloc(const phe_pubkey* pk, size_t words, uint32_t** out) {
+  if (!pk || !out) return fail("phe_dev_alloc: null argument");
+  {
+    std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
+  }
+  CUDA_TRY(cudaSetDevice(pk->device));
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (words ? words : 1) * 4);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("phe_dev_alloc: ") + cudaGetErrorString(e)); }
+  *out = static_cast<uint32_t*>(p);
+  return 0;
+}
+int phe_dev_free(uint32_t* p) {
+  if (p && cudaFree(p) != cudaSuccess) { cudaGetLastError(); return fail("phe_dev_free: cudaFree failed"); }
+  return 0;
+}
+int phe_copy(void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return 0;
+  if (!dst || !src) return fail("phe_copy: null argument");
+  CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+  return 0;
+}
+
+// ---- host-buffer entry points (every input / output pointer may also be a device pointer: unified addressing) ------------------------------------------------------------------------------
 int phe_encrypt(const phe_pubkey* pk, const uint32_t* m, size_t count, const uint32_t* r, int r_words,
                 int make_secure, uint32_t* ct_out) {
   return phe_encrypt_compact(pk, m, pk ? pk->n_words : 0, count, r, r_words, make_secure, ct_out);
@@ -1117,19 +1142,19 @@ int phe_encrypt_compact(const phe_pubkey* pk, const uint32_t* m, int m_words, si
     if (!make_secure) r = nullptr;
     PHE_TRY(pk->ws_a.ensure(count * (size_t)m_words));
     PHE_TRY(pk->ws_b.ensure(count * cw));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, m, count * (size_t)m_words * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, m, count * (size_t)m_words * 4, cudaMemcpyDefault, 0));
     const uint32_t* d_r = nullptr;
     if (device_r) {
       PHE_TRY(random_r_dev(pk, count, &r_words, 0));
       d_r = pk->ws_r.p;
     } else if (r) {   // workspace kept with the key: a cudaMalloc/cudaFree pair per call costs milliseconds and a device sync
       PHE_TRY(pk->ws_r.ensure(count * (size_t)r_words));
-      CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice, 0));
+      CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r, count * (size_t)r_words * 4, cudaMemcpyDefault, 0));
       d_r = pk->ws_r.p;
     }
     int rc = encrypt_dev_impl(pk, pk->ws_a.p, count, d_r, r_words, pk->ws_b.p, 0, m_words);
     if (!rc) {
-      cudaError_t e = cudaMemcpy(ct_out, pk->ws_b.p, count * cw * 4, cudaMemcpyDeviceToHost);
+      cudaError_t e = cudaMemcpy(ct_out, pk->ws_b.p, count * cw * 4, cudaMemcpyDefault);
       if (e != cudaSuccess) rc = fail(std::string("phe_encrypt D2H: ") + cudaGetErrorString(e));
     }
     return rc;
@@ -1150,14 +1175,14 @@ int phe_obfuscate(const phe_pubkey* pk, uint32_t* ct, size_t count, const uint32
     } else {
       if (!r) { PHE_TRY(make_r_host(pk, count, rgen, &r_words)); r = rgen.data(); }
       PHE_TRY(pk->ws_r.ensure(count * (size_t)r_words));
-      CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r, count * (size_t)r_words * 4, cudaMemcpyHostToDevice, 0));
+      CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r, count * (size_t)r_words * 4, cudaMemcpyDefault, 0));
     }
     PHE_TRY(pk->ws_a.ensure(count * cw));   // obfuscators
     PHE_TRY(pk->ws_b.ensure(count * cw));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, ct, count * cw * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, ct, count * cw * 4, cudaMemcpyDefault, 0));
     PHE_TRY(obfuscators_dev(pk, pk->ws_r.p, r_words, count, pk->ws_a.p, 0));
     PHE_TRY(add_dev_impl(pk, pk->ws_b.p, count, pk->ws_a.p, count, pk->ws_b.p, 0));
-    CUDA_TRY(cudaMemcpy(ct, pk->ws_b.p, count * cw * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ct, pk->ws_b.p, count * cw * 4, cudaMemcpyDefault));
     return 0;
   } catch (const std::exception& e) { return fail(std::string("phe_obfuscate: ") + e.what()); }
 }
@@ -1172,9 +1197,9 @@ int phe_decrypt(const phe_privkey* sk, const uint32_t* ct, size_t count, uint32_
     const int hw = sk->hw, cw = 2 * hw;
     PHE_TRY(sk->ws_in.ensure(count * cw));
     PHE_TRY(sk->ws_out.ensure(count * hw));
-    CUDA_TRY(cudaMemcpyAsync(sk->ws_in.p, ct, count * cw * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(sk->ws_in.p, ct, count * cw * 4, cudaMemcpyDefault, 0));
     PHE_TRY(decrypt_dev_impl(sk, sk->ws_in.p, count, sk->ws_out.p, 0));
-    CUDA_TRY(cudaMemcpy(m_out, sk->ws_out.p, count * hw * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(m_out, sk->ws_out.p, count * hw * 4, cudaMemcpyDefault));
     return 0;
   } catch (const std::exception& e) { return fail(std::string("phe_decrypt: ") + e.what()); }
 }
@@ -1191,10 +1216,10 @@ int phe_add(const phe_pubkey* pk, const uint32_t* a, size_t na, const uint32_t* 
     PHE_TRY(pk->ws_a.ensure(na * cw));
     PHE_TRY(pk->ws_b.ensure(nb * cw));
     PHE_TRY(pk->ws_c.ensure(na * cw));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, a, na * cw * 4, cudaMemcpyHostToDevice, 0));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, b, nb * cw * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, a, na * cw * 4, cudaMemcpyDefault, 0));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, b, nb * cw * 4, cudaMemcpyDefault, 0));
     PHE_TRY(add_dev_impl(pk, pk->ws_a.p, na, pk->ws_b.p, nb, pk->ws_c.p, 0));
-    CUDA_TRY(cudaMemcpy(out, pk->ws_c.p, na * cw * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out, pk->ws_c.p, na * cw * 4, cudaMemcpyDefault));
     return 0;
   } catch (const std::exception& e) { return fail(std::string("phe_add: ") + e.what()); }
 }
@@ -1214,10 +1239,10 @@ int phe_mul(const phe_pubkey* pk, const uint32_t* ct, size_t n, const uint32_t* 
     PHE_TRY(pk->ws_a.ensure(n * cw));
     PHE_TRY(pk->ws_b.ensure(ne * (size_t)e_words));
     PHE_TRY(pk->ws_c.ensure(n * cw));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, ct, n * cw * 4, cudaMemcpyHostToDevice, 0));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, e, ne * (size_t)e_words * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, ct, n * cw * 4, cudaMemcpyDefault, 0));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, e, ne * (size_t)e_words * 4, cudaMemcpyDefault, 0));
     PHE_TRY(mul_dev_impl(pk, pk->ws_a.p, n, pk->ws_b.p, e_words, ne, ebits, pk->ws_c.p, 0));
-    CUDA_TRY(cudaMemcpy(out, pk->ws_c.p, n * cw * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out, pk->ws_c.p, n * cw * 4, cudaMemcpyDefault));
     return 0;
   } catch (const std::exception& e) { return fail(std::string("phe_mul: ") + e.what()); }
 }
@@ -1235,9 +1260,9 @@ int phe_invert(const phe_pubkey* pk, const uint32_t* ct, size_t count, uint32_t*
       const size_t c = std::min(CHUNK, count - off);
       PHE_TRY(pk->ws_a.ensure(c * cw));
       PHE_TRY(pk->ws_b.ensure(c * cw));
-      CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, ct + off * cw, c * cw * 4, cudaMemcpyHostToDevice, 0));
+      CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, ct + off * cw, c * cw * 4, cudaMemcpyDefault, 0));
       rc = invert_dev_impl(pk, pk->ws_a.p, c, pk->ws_b.p, 0);
-      if (!rc) CUDA_TRY(cudaMemcpy(out + off * cw, pk->ws_b.p, c * cw * 4, cudaMemcpyDeviceToHost));
+      if (!rc) CUDA_TRY(cudaMemcpy(out + off * cw, pk->ws_b.p, c * cw * 4, cudaMemcpyDefault));
     }
     return rc;
   } catch (const std::exception& e) { return fail(std::string("phe_invert: ") + e.what()); }

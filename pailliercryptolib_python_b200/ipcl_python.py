@@ -329,10 +329,13 @@ class PaillierEncryptedNumber:
             except ValueError as e:
                 raise ZeroDivisionError("invert() no inverse exists") from e
 
-    def _mul_encoded(self, packed: np.ndarray, pt_limbs: np.ndarray, ct_expo, pt_expo):
+    def _mul_encoded(self, packed, pt_limbs: np.ndarray, ct_expo, pt_expo):
         """ct[i] ^ pt[i] with the reference's negative-plaintext rule: if pt >= n - max_int use (ct^-1)^(n - pt) so the
-        exponent stays short (ipcl_python.py:426-441, 470-479).  pt_limbs: [N or 1, n_words]."""
+        exponent stays short (ipcl_python.py:426-441, 470-479).  pt_limbs: [N or 1, n_words].  `packed` is the limb
+        matrix of the ciphertexts (modified in place) or an ipclCipherText, which stays on the device unless some
+        plaintext is negative."""
         pk = self.public_key
+        is_ct = isinstance(packed, ipclCipherText)
         n_l = _ints_to_limbs([pk.n], pk.n_words)[0]
         thr = _ints_to_limbs([pk.n - pk.max_int], pk.n_words)[0]
         # lexicographic compare pt >= thr from the top word down
@@ -347,6 +350,8 @@ class PaillierEncryptedNumber:
                 break
         neg = np.nonzero(ge)[0]
         if neg.size:
+            if is_ct:
+                packed, is_ct = packed.to_packed(), False
             pt_limbs = pt_limbs.copy()
             borrow = np.zeros(neg.size, dtype=np.int64)
             for j in range(pk.n_words):
@@ -360,7 +365,7 @@ class PaillierEncryptedNumber:
         used = pk.n_words
         while used > 1 and not pt_limbs[:, used - 1].any():
             used -= 1
-        ct = ipclCipherText.from_packed(pk.pubkey, packed)
+        ct = packed if is_ct else ipclCipherText.from_packed(pk.pubkey, packed)
         res = ct * ipclPlainText.from_packed(np.ascontiguousarray(pt_limbs[:, :used]))
         return res, np.asarray(ct_expo, dtype=np.int64) + np.asarray(pt_expo, dtype=np.int64)
 
@@ -372,7 +377,7 @@ class PaillierEncryptedNumber:
             if len(other) != self.__length:
                 raise ValueError("PaillierEncryptedNumber.__mul__: Multiply size mismatch")
             pt_limbs, pt_expo = encode_array(other, pk.n, pk.max_int, pk.n_words)
-        res, expo = self._mul_encoded(self.packed(), pt_limbs, self.__expo, pt_expo)
+        res, expo = self._mul_encoded(self.__ct, pt_limbs, self.__expo, pt_expo)
         return self._wrap(res, expo)
 
     def __rmul__(self, other):

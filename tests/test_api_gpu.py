@@ -201,3 +201,32 @@ def test_large_batch_vectorised_path(bench):
     assert np.allclose(pri.decrypt(e), x, rtol=0, atol=1e-6)
     assert np.allclose(pri.decrypt(e + pub.encrypt(y)), x + y)
     assert np.allclose(pri.decrypt(e * y), x * y)
+
+
+def test_device_resident_ciphertexts(bench):
+    """encrypt / + / * leave their results in HBM; every way of looking at the words (packed, indexing, slices,
+    getTexts, rotate, pickle) brings the same bits to the host, and host-built and device-resident operands mix."""
+    from pailliercryptolib_python_b200.bindings.ipcl_bindings import ipclCipherText
+    pk_o, sk_o, pub, pri = bench
+    x = np.arange(1, 41, dtype=np.int64)
+    ct = pub.encrypt(x, apply_obfuscator=False)              # deterministic: 1 + m n
+    want = [(1 + int(v) * pk_o.n) % pk_o.nsquare for v in x]
+    assert _cts(ct) == want                                   # getTexts on a device-resident batch
+    s = ct + ct                                               # device + device
+    assert _cts(s) == [w * w % pk_o.nsquare for w in want]
+    p3 = s * 3                                                # device * plaintext
+    want3 = [pow(w * w % pk_o.nsquare, 3, pk_o.nsquare) for w in want]
+    packed = p3.packed()
+    assert np.array_equal(packed, p3.packed())                # second look: same host copy
+    assert [int.from_bytes(r.tobytes(), "little") for r in packed] == want3
+    assert BNUtils.BN2int(p3.ciphertext()[7]) == want3[7]
+    assert _cts(p3[5:9]) == want3[5:9]
+    rot = p3.ciphertext().rotate(3)
+    assert [BNUtils.BN2int(b) for b in rot.getTexts()] == want3[3:] + want3[:3]
+    back = pickle.loads(pickle.dumps(p3))
+    assert _cts(back) == want3
+    host_ct = ipclCipherText.from_packed(pub.pubkey, packed)  # host-built operand + device-resident operand
+    mixed = host_ct + s.ciphertext()
+    assert [BNUtils.BN2int(b) for b in mixed.getTexts()] == [a * b % pk_o.nsquare for a, b in zip(want3, [w * w % pk_o.nsquare for w in want])]
+    assert pri.decrypt(p3) == [6 * int(v) for v in x]
+    assert pri.decrypt(back) == [6 * int(v) for v in x]
