@@ -421,6 +421,12 @@ def _secondary(torch, capi, pk, dev, stream, args, peak):
     ms = timed(lambda: pk.mul_dev(a.data_ptr(), M, e.data_ptr(), 2, M, 53, out.data_ptr(), stream), 2)
     res["he_mul53_ops_s"] = M / (ms * 1e-3)
     res["he_mul53_frac_int_pipe"] = W_MUL53_2048 * M / (ms * 1e-3) / peak
+    # full-width exponents (2048 bits, SURVEY 8d "mul (full)"): a tenth of the batch
+    Mf = max(1, M // 10)
+    ef = torch.randint(0, 2**31 - 1, (Mf, 64), device=dev, dtype=torch.int32, generator=g)
+    ms = timed(lambda: pk.mul_dev(a.data_ptr(), Mf, ef.data_ptr(), 64, Mf, 2048, out.data_ptr(), stream), 1)
+    res["he_mul2048_batch"] = Mf
+    res["he_mul2048_ops_s"] = Mf / (ms * 1e-3)
     return res
 
 

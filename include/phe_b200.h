@@ -95,8 +95,10 @@ int phe_privkey_get_q(const phe_privkey* sk, uint32_t* q_out);  /* n_words words
 int phe_keygen(int bits, uint32_t* n_out, uint32_t* p_out, uint32_t* q_out);
 
 /* ---- the hot path, host buffers -------------------------------------------------------------------------- */
-/* Every data pointer of this section may be a host pointer or a pointer into the key's device (unified virtual
- * addressing: the copies inside are cudaMemcpyDefault), so a caller can leave results in HBM between calls: */
+/* Every plaintext / ciphertext pointer of this section (m, ct, a, b, out ...) may be a host pointer or a pointer into the
+ * key's device (unified virtual addressing: the copies inside are cudaMemcpyDefault), so a caller can leave results
+ * in HBM between calls; with a device output the call returns once the work is enqueued on the default stream.  The
+ * exponents of phe_mul and explicit obfuscator exponents r are read on the host and must be host pointers. */
 int phe_dev_alloc(const phe_pubkey* pk, size_t words, uint32_t** out);   /* cudaMalloc on the key's device */
 int phe_dev_free(uint32_t* p);
 int phe_copy(void* dst, const void* src, size_t bytes);                  /* host or device on either side; synchronous */
