@@ -147,6 +147,18 @@ int phe_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulu
 
 int phe_encrypt_dev(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
                     uint32_t* d_ct_out, void* stream);
+/* The same fused with the gather of ciphertext shards (BASELINE config 4): every row is also stored to the same row of
+ * n_peers (<= 15) more buffers -- the other ranks' gather buffers, opened with CUDA IPC -- by the encrypt kernel itself,
+ * so the transfer over NVLink overlaps the arithmetic.  d_ct_out and every d_peer_out[k] already point at this rank's
+ * first row.  DJN keys, explicit r.  phe_enable_peer_access(dev) = cudaDeviceEnablePeerAccess on the current device. */
+int phe_encrypt_dev_multi(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
+                          uint32_t* d_ct_out, uint32_t* const* d_peer_out, int n_peers, void* stream);
+int phe_enable_peer_access(int peer_device);
+/* CUDA IPC for those buffers: export a phe_dev_alloc block as a 64-byte handle; open it in another process of the node
+ * (on its current device, peer access enabled lazily); close the mapping. */
+int phe_ipc_export(const uint32_t* d_ptr, unsigned char handle_out[64]);
+int phe_ipc_open(const unsigned char handle[64], uint32_t** out);
+int phe_ipc_close(uint32_t* p);
 int phe_decrypt_dev(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m_out, void* stream);
 int phe_add_dev(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint32_t* d_b, size_t nb,
                 uint32_t* d_out, void* stream);

@@ -21,7 +21,7 @@ SYMBOLS = [
     "phe_privkey_create", "phe_privkey_destroy", "phe_privkey_get_p", "phe_privkey_get_q", "phe_keygen",
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
-    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_dev_alloc", "phe_dev_free", "phe_copy", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
+    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_dev_alloc", "phe_dev_free", "phe_copy", "phe_encrypt_dev_multi", "phe_enable_peer_access", "phe_ipc_export", "phe_ipc_open", "phe_ipc_close", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
     "phe_product_mix_peak",
 ]
@@ -226,6 +226,13 @@ class PubKey:
         _check(lib().phe_encrypt_dev(self.h, _p(d_m), ctypes.c_size_t(count), _p(d_r) if d_r else None, r_words,
                                      _p(d_out), ctypes.c_void_p(stream)), "phe_encrypt_dev")
 
+    def encrypt_dev_multi(self, d_m, count, d_r, r_words, d_out, peer_outs, stream=0):
+        """DJN encrypt whose rows also go to the buffers in peer_outs (device pointers, e.g. peer-mapped gather buffers)."""
+        arr = (ctypes.c_void_p * max(1, len(peer_outs)))(*[ctypes.c_void_p(int(q)) for q in peer_outs])
+        _check(lib().phe_encrypt_dev_multi(self.h, _p(d_m), ctypes.c_size_t(count), _p(d_r), r_words, _p(d_out),
+                                           ctypes.cast(arr, ctypes.c_void_p), len(peer_outs), ctypes.c_void_p(stream)),
+               "phe_encrypt_dev_multi")
+
     def add_dev(self, d_a, na, d_b, nb, d_out, stream=0):
         _check(lib().phe_add_dev(self.h, _p(d_a), ctypes.c_size_t(na), _p(d_b), ctypes.c_size_t(nb), _p(d_out),
                                  ctypes.c_void_p(stream)), "phe_add_dev")
@@ -292,6 +299,37 @@ def host_mont_block(modulus, mod_words, L, TPI):
     lib().phe_host_mont_block(_p(int_to_words(modulus, mod_words)), mod_words, L, TPI,
                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(n0))
     return out.reshape(5, kp), n0.value
+
+
+class DeviceBuffer:
+    """A cudaMalloc block on the key's device (phe_dev_alloc) that can be shared with the other ranks of the node through
+    CUDA IPC; exposes __cuda_array_interface__ so that torch.as_tensor(buf) views it as a [rows, words] uint32->int32 matrix."""
+
+    def __init__(self, pk, rows, words):
+        self.rows, self.words = int(rows), int(words)
+        p = _u32p()
+        _check(lib().phe_dev_alloc(pk.h, ctypes.c_size_t(self.rows * self.words), ctypes.byref(p)), "phe_dev_alloc")
+        self.ptr = ctypes.cast(p, ctypes.c_void_p).value
+        self.__cuda_array_interface__ = {"shape": (self.rows, self.words), "typestr": "<i4", "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+
+    def ipc_handle(self):
+        h = (ctypes.c_ubyte * 64)()
+        _check(lib().phe_ipc_export(_p(self.ptr), h), "phe_ipc_export")
+        return bytes(h)
+
+    def free(self):
+        if self.ptr:
+            lib().phe_dev_free(_p(self.ptr))
+            self.ptr = 0
+
+
+def ipc_open(handle):
+    """Map another process's DeviceBuffer (its ipc_handle()) on the current device; returns the device pointer."""
+    h = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+    p = _u32p()
+    _check(lib().phe_ipc_open(h, ctypes.byref(p)), "phe_ipc_open")
+    return ctypes.cast(p, ctypes.c_void_p).value
 
 
 def npair_block(pk):

@@ -252,9 +252,13 @@ PHE_HD void npair_canon_setup(double (&x)[L], const double* cst, const NPairSmem
   Env::sync();
 }
 
-// After NK_PLAIN: x = high K limbs, sm.e = low K limbs (integers, padded layout) -> little-endian words
+// After NK_PLAIN: x = high K limbs, sm.e = low K limbs (integers, padded layout) -> little-endian words.
+// peers (or null): n_peers more destinations of the same row (the gather buffers of the other GPUs, mapped peer memory:
+// the stores go out over NVLink while the group computes on)
+constexpr int NPAIR_MAX_PEERS = 15;
 template <int L, int TPI, class Env>
-PHE_HD void npair_store_words(uint32_t* out, int nwords, const double (&x)[L], const NPairSmem& sm) {
+PHE_HD void npair_store_words(uint32_t* out, int nwords, const double (&x)[L], const NPairSmem& sm,
+                              uint32_t* const* peers = nullptr, int n_peers = 0, size_t peer_off = 0) {
   constexpr int LP = Pad<L>::LP;
   constexpr int K = L * TPI;
   uint64_t hi[L];
@@ -276,6 +280,7 @@ PHE_HD void npair_store_words(uint32_t* out, int nwords, const double (&x)[L], c
       uint64_t u = limb(g) >> o;
       if (o > LW - 32) u |= limb(g + 1) << (LW - o);
       out[v] = (uint32_t)u;
+      for (int k = 0; k < n_peers; ++k) peers[k][peer_off + v] = (uint32_t)u;
     }
   }
   Env::sync();
@@ -467,6 +472,9 @@ struct NPairEncCtl {
   const uint32_t* r_w; int r_words; int nwin, wb;
   uint32_t* out_w; int out_words;
   const double* cst; const double* comb; NPairSmem sm;
+  uint32_t* const* peers = nullptr;   // n_peers more output matrices (the other GPUs' gather buffers); this row starts
+  int n_peers = 0;                    // peer_off words into each
+  size_t peer_off = 0;
   int phase = 0, j = 1;
 
   PHE_HD const double* entry(int win, uint32_t d) const { return comb + ((((size_t)win) << wb) + d) * 2 * KP; }
@@ -524,7 +532,7 @@ struct NPairEncCtl {
           phase = 9;
           return NK_PLAIN;
         default:
-          npair_store_words<L, TPI, Env>(out_w, out_words, x, sm);
+          npair_store_words<L, TPI, Env>(out_w, out_words, x, sm, peers, out_w ? n_peers : 0, peer_off);
           return NK_DONE;
       }
     }

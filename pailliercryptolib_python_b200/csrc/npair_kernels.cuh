@@ -101,9 +101,11 @@ struct EncNPairArgs {
   int count;
   NPairCtxArgs ctx;
   const double* comb;     // [nwin][1 << wb][2 * KP]
+  uint32_t* peer_out[NPAIR_MAX_PEERS];   // n_peers more [count][out_words] destinations (peer-mapped gather buffers)
+  int n_peers;
 };
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_encrypt_npair(EncNPairArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_encrypt_npair(const __grid_constant__ EncNPairArgs p) {
   using Env = DevEnv<TPI>;
   using NS = NKShape<L, TPI>;
   extern __shared__ __align__(16) double smem[];
@@ -119,6 +121,7 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_encrypt_npa
     ctl.nwin = p.nwin; ctl.wb = p.wb;
     ctl.out_w = want < p.count ? p.out_w + (size_t)item * p.out_words : nullptr; ctl.out_words = p.out_words;
     ctl.cst = smem; ctl.comb = p.comb; ctl.sm = sm;
+    ctl.peers = p.peer_out; ctl.n_peers = p.n_peers; ctl.peer_off = (size_t)item * p.out_words;
     npair_run<L, TPI, Env>(ctl, smem, p.ctx.n0inv, p.ctx.d_top, sm);
   }
 }

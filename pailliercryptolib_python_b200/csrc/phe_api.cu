@@ -439,9 +439,14 @@ int pk_ensure_comb(const phe_pubkey* pk, size_t count) {
   }
   if (wb < 1) wb = 1;
   if (wb > 22) wb = 22;
+  // an allocation that fails (fragmented or shared device) falls back to narrower tables instead of failing the encrypt
+  while (pk->d_comb.ensure_exact(table_bytes(wb) / 4) != 0) {
+    cudaGetLastError();
+    if (wb <= 8 || pk->comb_bits_wanted > 0) return fail("comb table: out of device memory");
+    wb -= 2;
+  }
   pk->comb_bits = wb;
   const_cast<phe_pubkey*>(pk)->nwin = (pk->randbits + wb - 1) / wb;
-  PHE_TRY(pk->d_comb.ensure_exact(table_bytes(wb) / 4));
   std::vector<uint32_t> hsw(2 * (size_t)pk->n_words);
   pk->hs.to_words(hsw.data(), hsw.size());
   DevBuf dhs;
@@ -518,10 +523,14 @@ constexpr size_t CHUNK = 1u << 20;  // items per launch (bounds scratch and int 
 
 // one DJN comb launch (n^2 Montgomery engine or n-adic pair engine)
 int launch_encrypt_comb(const phe_pubkey* pk, const uint32_t* m_w, int m_words, const uint32_t* r_w, int r_words,
-                        uint32_t* out_w, int count, cudaStream_t s) {
+                        uint32_t* out_w, int count, cudaStream_t s, uint32_t* const* peers = nullptr, int n_peers = 0,
+                        size_t peer_row0 = 0) {
   const int cw = 2 * pk->n_words;
+  if (n_peers && !pk->use_npair) return fail("phe_encrypt_dev_multi needs the n-adic pair engine");
   if (pk->use_npair) {
     EncNPairArgs a{};
+    a.n_peers = n_peers;
+    for (int k = 0; k < n_peers; ++k) a.peer_out[k] = peers[k] + peer_row0 * cw;
     a.m_w = m_w; a.m_words = m_words; a.r_w = r_w; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
     a.out_w = out_w; a.out_words = cw; a.count = count; a.ctx = pk->nctx;
     a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
@@ -617,7 +626,7 @@ int random_r_dev(const phe_pubkey* pk, size_t count, int* r_words, cudaStream_t 
 }
 
 int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
-                     uint32_t* d_ct, cudaStream_t s, int m_words = 0) {
+                     uint32_t* d_ct, cudaStream_t s, int m_words = 0, uint32_t* const* peers = nullptr, int n_peers = 0) {
   const int cw = 2 * pk->n_words;
   if (m_words <= 0) m_words = pk->n_words;   // stride of the plaintext rows
   if (count == 0) return 0;
@@ -629,7 +638,7 @@ int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, co
     for (size_t off = 0; off < count; off += CHUNK) {
       const int c = (int)std::min(CHUNK, count - off);
       PHE_TRY(launch_encrypt_comb(pk, d_m + off * (size_t)m_words, m_words, d_r ? d_r + off * r_words : nullptr, r_words,
-                                  d_ct + off * cw, c, s));
+                                  d_ct + off * cw, c, s, peers, n_peers, off));
     }
     return 0;
   }
@@ -1070,6 +1079,46 @@ int phe_encrypt_dev(const phe_pubkey* pk, const uint32_t* d_m, size_t count, con
   std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));
   return encrypt_dev_impl(pk, d_m, count, d_r, r_words, d_ct_out, (cudaStream_t)stream);
+}
+// DJN encrypt fused with the gather of BASELINE config 4: every ciphertext row is stored to d_ct_out and to the same row
+// of n_peers more buffers (the other ranks' gather buffers, opened through CUDA IPC and reachable over NVLink).
+int phe_encrypt_dev_multi(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
+                          uint32_t* d_ct_out, uint32_t* const* d_peer_out, int n_peers, void* stream) {
+  if (!pk || !d_m || !d_ct_out || (n_peers && !d_peer_out)) return fail("phe_encrypt_dev_multi: null argument");
+  if (n_peers < 0 || n_peers > NPAIR_MAX_PEERS) return fail("phe_encrypt_dev_multi: at most 15 peer buffers");
+  if (!pk->djn || !d_r) return fail("phe_encrypt_dev_multi: DJN keys with explicit obfuscator exponents only");
+  std::lock_guard<std::mutex> lk(pk->mu);
+  PHE_TRY(pk_ensure_device(pk));
+  return encrypt_dev_impl(pk, d_m, count, d_r, r_words, d_ct_out, (cudaStream_t)stream, 0, d_peer_out, n_peers);
+}
+// CUDA IPC for the gather buffers of the fused encrypt: export a buffer from phe_dev_alloc (a whole cudaMalloc block),
+// open it in another process of the node on that process's current device.
+int phe_ipc_export(const uint32_t* d_ptr, unsigned char handle_out[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!d_ptr || !handle_out) return fail("phe_ipc_export: null argument");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<uint32_t*>(d_ptr)));
+  std::memcpy(handle_out, &h, 64);
+  return 0;
+}
+int phe_ipc_open(const unsigned char handle[64], uint32_t** out) {
+  if (!handle || !out) return fail("phe_ipc_open: null argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  void* p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *out = static_cast<uint32_t*>(p);
+  return 0;
+}
+int phe_ipc_close(uint32_t* p) {
+  if (p) CUDA_TRY(cudaIpcCloseMemHandle(p));
+  return 0;
+}
+int phe_enable_peer_access(int peer_device) {
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("phe_enable_peer_access: ") + cudaGetErrorString(e)); }
+  return 0;
 }
 int phe_decrypt_dev(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m_out, void* stream) {
   if (!sk || !d_ct || !d_m_out) return fail("phe_decrypt_dev: null argument");

@@ -27,6 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--count", type=int, default=1 << 20)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--fused", action="store_true", help="the encrypt kernel stores every row into all ranks' gather buffers (CUDA IPC peer memory over NVLink) instead of an NCCL all-gather afterwards")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -45,6 +46,21 @@ def main():
     r = torch.from_numpy(r_np.view(np.int32)).to(dev)
     local_ct = torch.empty((hi - lo, 128), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    fused = args.fused and world > 1
+    if fused:
+        # every rank owns one full gather buffer; the others map it through CUDA IPC and write their rows into it
+        own = capi.DeviceBuffer(pk, args.count, 128)
+        full_buf = torch.as_tensor(own, device=dev)
+        full_buf.zero_()
+        torch.cuda.synchronize()
+        handles = [None] * world
+        dist.all_gather_object(handles, own.ipc_handle())
+        peer_ptrs = []
+        for r_, h in enumerate(handles):
+            if r_ != rank:
+                peer_ptrs.append(capi.ipc_open(h) + lo * 512)
+        torch.cuda.set_device(local)
+        dist.barrier()
 
     def once():
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -52,9 +68,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         e0.record()
-        pk.encrypt_dev(m.data_ptr(), hi - lo, r.data_ptr(), 32, local_ct.data_ptr(), stream)
-        e1.record()
-        full = gather_rows(local_ct, args.count) if world > 1 else local_ct
+        if fused:
+            pk.encrypt_dev_multi(m.data_ptr(), hi - lo, r.data_ptr(), 32, full_buf.data_ptr() + lo * 512, peer_ptrs, stream)
+            e1.record()
+            torch.cuda.synchronize()
+            dist.barrier()            # every rank's rows have landed in every buffer
+            full = full_buf
+        else:
+            pk.encrypt_dev(m.data_ptr(), hi - lo, r.data_ptr(), 32, local_ct.data_ptr(), stream)
+            e1.record()
+            full = gather_rows(local_ct, args.count) if world > 1 else local_ct
         e2.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e2), e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -76,11 +99,17 @@ def main():
         want = (1 + mi * n) * pow(hs, ri, n * n) % (n * n)
         got = int.from_bytes(full[lo + row].cpu().numpy().tobytes(), "little")
         ok = ok and (got == want)
+    if world > 1:   # every rank must hold the same full matrix: compare a checksum of all rows
+        chk = full.to(torch.int64).sum(dim=0)
+        ref = chk.clone()
+        dist.broadcast(ref, 0)
+        ok = ok and bool(torch.equal(chk, ref))
     flag = torch.tensor([1 if ok else 0], device=dev)
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"workload": "2048-bit DJN encrypt, batch=%d sharded over %d GPU(s) + all-gather of ciphertexts" % (args.count, world),
+        print(json.dumps({"workload": "2048-bit DJN encrypt, batch=%d sharded over %d GPU(s) + %s" % (args.count, world, "rows stored by the encrypt kernel into every rank's gather buffer (CUDA IPC peer memory)" if fused else "all-gather of ciphertexts"),
+                          "fused_peer_stores": bool(fused),
                           "n_gpus": world, "encrypt_ops_s": args.count / (best[0] * 1e-3), "ms_total": best[0], "ms_encrypt": best[1],
                           "gather_share": (best[0] - best[1]) / best[0], "gathered_bytes": args.count * 512,
                           "parity_spot_check": bool(flag.item())}))
