@@ -386,6 +386,9 @@ int do_encrypt_npair(const uint32_t* m, int m_words, const uint32_t* r, int r_wo
   using Env = EmuEnv<TPI>;
   constexpr int KP = phe::Shape<L, TPI>::KP;
   AlignedCopy cst(cst_e, (size_t)phe::NE_COUNT * KP), cb(comb, comb_doubles);
+  // two more destinations of every row, as the fused gather of config 4 uses them (peer buffers): must equal `out`
+  std::vector<uint32_t> peer_a((size_t)count * out_words, 0xdeadbeefu), peer_b((size_t)count * out_words, 0xdeadbeefu);
+  uint32_t* peer_ptrs[2] = {peer_a.data(), peer_b.data()};
   for (int i = 0; i < count; ++i) {
     NBufs<L, TPI> bufs;
     run_group<TPI>([&] {
@@ -393,9 +396,11 @@ int do_encrypt_npair(const uint32_t* m, int m_words, const uint32_t* r, int r_wo
       ctl.m_w = m + (size_t)i * m_words; ctl.m_words = m_words;
       ctl.r_w = r ? r + (size_t)i * r_words : nullptr; ctl.r_words = r_words; ctl.nwin = nwin; ctl.wb = wb;
       ctl.out_w = out + (size_t)i * out_words; ctl.out_words = out_words; ctl.cst = cst.p; ctl.comb = cb.p; ctl.sm = bufs.sm;
+      ctl.peers = peer_ptrs; ctl.n_peers = 2; ctl.peer_off = (size_t)i * out_words;
       phe::npair_run<L, TPI, Env>(ctl, cst.p, n0inv, d_top, bufs.sm);
     });
   }
+  if (std::memcmp(peer_a.data(), out, peer_a.size() * 4) || std::memcmp(peer_b.data(), out, peer_b.size() * 4)) return -3;
   return 0;
 }
 

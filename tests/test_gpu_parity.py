@@ -417,3 +417,30 @@ def test_npair_engine_and_n2_engine_agree(monkeypatch, bits):
                 # broadcast exponent
                 got = capi.array_to_ints(pk.mul(capi.ints_to_array(cts, 2 * nw), capi.ints_to_array(es[:1], 2)))
                 assert got == [pow(c, es[0], pk_o.nsquare) for c in cts]
+
+
+def test_encrypt_dev_multi_stores_every_row_to_all_buffers(key2048):
+    """phe_encrypt_dev_multi (the fused gather of BASELINE config 4): the encrypt kernel writes every row to the main
+    output and to each extra buffer -- here three buffers on the same GPU stand in for the peer-mapped ones."""
+    import torch
+    pk_o, sk_o, pk, sk = key2048
+    rng = np.random.default_rng(SEED + 5)
+    count = 1000
+    m_np = np.zeros((count, 64), dtype=np.uint32)
+    m_np[:, :2] = rng.integers(0, 1 << 32, size=(count, 2), dtype=np.uint64).astype(np.uint32)
+    r_np = rng.integers(0, 1 << 32, size=(count, 32), dtype=np.uint64).astype(np.uint32)
+    dev = torch.device("cuda", 0)
+    m = torch.from_numpy(m_np.view(np.int32)).to(dev)
+    r = torch.from_numpy(r_np.view(np.int32)).to(dev)
+    outs = [torch.zeros((count + 7, 128), dtype=torch.int32, device=dev) for _ in range(4)]
+    row0 = 7   # the caller points every buffer at its first row
+    pk.encrypt_dev_multi(m.data_ptr(), count, r.data_ptr(), 32, outs[0].data_ptr() + row0 * 512,
+                         [o.data_ptr() + row0 * 512 for o in outs[1:]], torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = pk.encrypt(m_np, r_np)
+    for o in outs:
+        got = o.cpu().numpy().view(np.uint32)
+        assert not got[:row0].any()
+        assert np.array_equal(got[row0:], want)
+    idx = [0, 1, count - 1]
+    assert capi.array_to_ints(want[idx]) == O.encrypt_batch(pk_o, capi.array_to_ints(m_np[idx]), capi.array_to_ints(r_np[idx]))
