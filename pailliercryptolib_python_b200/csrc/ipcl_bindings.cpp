@@ -360,12 +360,8 @@ struct CipherText : Packed {
     if (host_valid) return;
     Words& d = const_cast<Words&>(data);
     d.resize(words());
-    int rc;
-    {
-      py::gil_scoped_release nogil;
-      rc = phe_copy(d.data(), dev, words() * 4);
-    }
-    if (rc) throw_phe("ipclCipherText (device -> host)");
+    // the GIL stays held: two Python threads looking at the same batch must not both resize `data`
+    if (phe_copy(d.data(), dev, words() * 4)) throw_phe("ipclCipherText (device -> host)");
     host_valid = true;
   }
   const uint32_t* operand() const { return host_valid ? data.data() : dev; }   // host or device pointer for the C ABI
