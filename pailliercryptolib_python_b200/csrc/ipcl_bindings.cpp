@@ -690,6 +690,12 @@ PYBIND11_MODULE(ipcl_bindings, m) {
       .def(py::init([](const PubPtr& pk, const BigNumber& v) { return std::make_shared<CipherText>(pk, Packed::from_list({v})); }))
       .def(py::init([](const PubPtr& pk, const py::list& data) { return std::make_shared<CipherText>(pk, Packed::from_list(data.cast<std::vector<BigNumber>>())); }))
       .def(py::init([](const PubPtr& pk, const py::array_t<uint32_t, py::array::c_style | py::array::forcecast>& a) { return std::make_shared<CipherText>(pk, Packed::from_u32_array(a)); }))
+      // the reference's Python rebuilds a container from what __getitem__(slice) returned (ipcl_python.py:355-356);
+      // a slice is a container here, so this is the copy constructor under the same key
+      .def(py::init([](const PubPtr& pk, const CipherText& other) {
+        if (cmp(pk->n, other.pk->n) != 0) throw std::runtime_error("ipclCipherText: public key mismatch");
+        return std::make_shared<CipherText>(pk, H(other).chunk(0, other.count));
+      }))
       .def_static("from_packed", [](const PubPtr& pk, const py::array_t<uint32_t, py::array::c_style | py::array::forcecast>& a) { return std::make_shared<CipherText>(pk, Packed::from_matrix(a)); })
       .def("to_packed", [](const CipherText& s) { return H(s).to_matrix(s.stride); })
       .def("__repr__", [](const CipherText& s) { return "<ipclCipherText " + addr_tag(&s) + ">"; })
