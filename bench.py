@@ -10,7 +10,18 @@ the reference's fixed 2048-bit key (P, Q from bench/bench_ipcl_python.py:83-96),
   r = uniform 1024-bit obfuscator exponents, packed [N, 32] u32 (pinned -> deterministic ciphertexts)
 One step = encrypt the batch (ct = (1 + m n) hs^r mod n^2) then CRT-decrypt those ciphertexts; a step is
 2 N operations (N encrypts + N decrypts) and `value` = operations per second over all ranks.
-Under torchrun every rank runs the same batch on its own GPU (weak scaling, no data-path collective).
+Under torchrun every rank runs the same batch on its own GPU (weak scaling, no data-path collective in `value`).
+
+Beside the headline the same line carries:
+  e2e       the step through the host-buffer C ABI (pinned buffers, H2D / D2H inside)
+  e2e_api   the step through the Python API of the reference (PaillierPublicKey.encrypt(ndarray) ->
+            PaillierPrivateKey.decrypt -> Python floats; pageable input, library-drawn r)
+  roofline  dominant kernel: executed FP64 lane operations / measured DFMA rate (csrc/mont52.cuh runs on the FP64 pipe)
+  config3   (1 GPU) BASELINE configs[2]: 1 M HE add / HE mul, a sample of the outputs checked against the oracle
+  config5   (1 GPU) BASELINE configs[4]: 3072-bit key, 100 000 encrypt + decrypt, its own roofline
+  config4   (N > 1) BASELINE configs[3]: N x 2^20 encrypts sharded over the GPUs + NCCL all-gather of the ciphertexts,
+            and the fused form (the encrypt kernel stores every row into all ranks' buffers over NVLink)
+  comb      bytes and build time of the DJN fixed-base table (one-off per key, inside the warm-up)
 """
 import argparse
 import json
@@ -30,8 +41,6 @@ UNIT = "ops/s"
 SEED = 20240611
 
 # W(op) in 32x32->64 multiply-accumulates, SURVEY.md 8(d): MM(k) = 2k^2 + k, NMM(E) = E + ceil(E/5) + 32
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_dec_pair launch at N = 100 000 (ncu --set full, r01)
-TRAFFIC_K_DEC_PAIR = 7.48e9 + 2.10e9
 
 def _mm(k): return 2 * k * k + k
 def _nmm(e): return e + (e + 4) // 5 + 32
@@ -176,6 +185,58 @@ def run_reference(args):
     return 0
 
 
+def _passes_of_pair_program(prog):
+    """Reduction passes of one pair-engine program (csrc/paillier_items.cuh: PairOp): a square is 2, a multiplication 3."""
+    passes = 0
+    for ins in prog:
+        op, arg = ins & 0xFF, ins >> 8
+        passes += 2 * arg if op == 8 else 3 if op == 7 else 0
+    return passes
+
+
+def _dec_pair_products(capi, sk):
+    """Executed 52x52-bit limb products of one decrypt on the p-adic pair engine (both CRT halves), or None."""
+    pair = [capi.pair_block(sk, y) for y in (0, 1)]
+    if not pair[0]:
+        return None, None
+    L = pair[0]["L"]
+    passes = sum(_passes_of_pair_program(b["prog"]) for b in pair)
+    return passes * 2 * L * L, "%d reduction passes of 2*%d^2 limb products" % (passes, L)
+
+
+def _enc_npair_products(capi, pk):
+    """Executed limb products of one DJN encrypt on the n-adic pair engine with the comb table in use, or None."""
+    blk = capi.npair_block(pk)
+    if not blk or pk.comb_bits <= 0:
+        return None, None
+    K = blk["L"] * blk["TPI"]
+    nwin = -(-pk.randbits // pk.comb_bits)
+    passes = 3 * (nwin - 1) + 4            # nwin - 1 pair products, m*V0, leave-Montgomery (2 passes), v0 + v1 n
+    return passes * 2 * K * K, "%d passes of 2*%d^2 limb products (%d-bit comb, %d windows)" % (passes, K, pk.comb_bits, nwin)
+
+
+def _fp64_view(limb_products_per_op, ops, ms, fp64_peak, mix_peak, note):
+    """Roofline numbers of a kernel that ran `ops` operations in `ms`: 3 FP64 instructions (2 DFMA + 1 DADD) per limb
+    product against the measured DFMA rate, and limb products against the measured rate of the bare product mix."""
+    rate = limb_products_per_op * ops / (ms * 1e-3)
+    return {"executed": note, "limb_products_per_op": limb_products_per_op, "fp64_lane_ops_per_op": 3 * limb_products_per_op,
+            "achieved": 3 * rate / 1e12, "peak": fp64_peak / 1e12, "unit": "T FP64 lane-ops/s", "frac": 3 * rate / fp64_peak,
+            "product_mix": {"achieved": rate / 1e12, "peak": mix_peak / 1e12, "unit": "T limb-products/s", "frac": rate / mix_peak}}
+
+
+def _measured_traffic(kernel, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, only if a committed ncu capture of this
+    batch size exists (profiles/dram_traffic.json names the .csv it was read from); else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            for rec in json.load(f):
+                if rec["kernel"] == kernel and rec["batch"] == batch:
+                    return rec["dram_bytes_per_launch"], rec["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -233,9 +294,12 @@ def run_gpu(args):
         return float(t.item())
 
     # ---- device-resident timing --------------------------------------------------------------------------
+    t_w0 = time.perf_counter()
     for _ in range(args.warmup):
         step_dev()
     torch.cuda.synchronize()
+    warmup_s = time.perf_counter() - t_w0
+    comb_bytes, comb_build_ms = pk.comb_info      # the one-off table build happened inside the warm-up
     if not torch.equal(out_d, m_d):
         raise RuntimeError("round trip D(E(m)) != m on the GPU path")
     sampler = ClockSampler(local)
@@ -277,75 +341,83 @@ def run_gpu(args):
         raise RuntimeError("round trip D(E(m)) != m through the host C ABI")
     e2e = {"value": world * 2.0 * N / (e2e_ms * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(N * (64 + 32 + 128) * 4), "d2h_bytes_per_step": int(N * (128 + 64) * 4),
-           "ms_per_step": e2e_ms, "ms_each_step": e2e_each, "steps": e2e_steps, "api": "phe_encrypt + phe_decrypt (host buffers, pinned)"}
+           "ms_per_step": e2e_ms, "ms_each_step": e2e_each, "steps": e2e_steps,
+           "api": "phe_encrypt + phe_decrypt (host buffers, pinned; explicit r)"}
 
-    # ---- roofline of the dominant kernel (k_powm: the two CRT modexps of decrypt) -----------------------------
+    # ---- end to end through the Python API a caller of the reference uses ------------------------------------
+    e2e_api = _e2e_api(N, n, p, q, hs, world, max_over_ranks, barrier)
+
+    # ---- roofline of the dominant kernel: executed FP64 lane operations against the measured DFMA rate ---------
     peak = capi.int_pipe_peak(5)
     fp64_peak = capi.fp64_pipe_peak(5)
     mix_peak = capi.product_mix_peak(5)
     enc_kernel = "k_encrypt_npair" if ktimes["k_encrypt_npair"][1] else "k_encrypt_comb"
     comb_ms, comb_n = ktimes[enc_kernel]
     roofline = None
-    # dominant kernel: the two CRT halves of decrypt -- k_dec_pair (p-adic pair engine) for balanced keys, else k_powm
-    pair = [capi.pair_block(sk, y) for y in (0, 1)]
-    if pair[0] and ktimes["k_dec_pair"][1]:
-        dom_name, (dom_ms, dom_n) = "k_dec_pair<20> (decrypt: L_x(c^(x-1) mod x^2) h_x mod x, x = p, q in one launch, one ciphertext per lane, warp-granular units)", ktimes["k_dec_pair"]
-        Lp = pair[0]["L"]
-        passes = 0
-        for blk in pair:      # a square is 2 reduction passes, a multiplication 3; each pass = 2 L^2 limb products
-            for ins in blk["prog"]:
-                op, arg = ins & 0xFF, ins >> 8
-                passes += 2 * arg if op == 8 else 3 if op == 7 else 0
-        limb_products = passes * 2 * Lp * Lp
-        exec_note = "%d reduction passes of 2*%d^2 limb products" % (passes, Lp)
+    dec_products, dec_note = _dec_pair_products(capi, sk)
+    if dec_products and ktimes["k_dec_pair"][1]:
+        dom_key = "k_dec_pair"
+        dom_name = "k_dec_pair<20> (decrypt: L_x(c^(x-1) mod x^2) h_x mod x, x = p, q in one launch, one ciphertext per lane, warp-granular units)"
+        dom_ms, dom_n = ktimes["k_dec_pair"]
     else:
+        dom_key = "k_powm"
         dom_name, (dom_ms, dom_n) = "k_powm_prog<20,2> (decrypt: c^(p-1) mod p^2, c^(q-1) mod q^2)", ktimes["k_powm"]
         progs = [capi.host_powm_program(x - 1, 64) for x in (p, q)]
         mm = sum(sum(op >> 8 for op in pr[1:]) + sum(1 for op in pr[1:] if op & 0xFF != 0xFF) + 32 + 1 for pr in progs)
-        limb_products = mm * 2 * 40 * 40
-        exec_note = "%d Montgomery products of 2*40^2 limb products" % mm
+        dec_products, dec_note = mm * 2 * 40 * 40, "%d Montgomery products of 2*40^2 limb products" % mm
     if dom_n:
         per_launch_ms = dom_ms / dom_n
         ops_per_launch = N * args.steps / dom_n
-        achieved = W_DEC_2048 * ops_per_launch / (per_launch_ms * 1e-3)
-        prod_rate = limb_products * ops_per_launch / (per_launch_ms * 1e-3)
+        view = _fp64_view(dec_products, ops_per_launch, per_launch_ms, fp64_peak, mix_peak, dec_note)
+        traffic, traffic_src = _measured_traffic(dom_key, N)
         roofline = {
-            "bound": "int_pipe", "kernel": dom_name,
-            "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s", "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one k_dec_pair launch, ncu --set full, r01
-            # (profiles/r01_ncu_k_dec_pair_summary.txt): ~7 + 2 GB against 102 MB of algorithmic bytes -- the
-            # per-lane window tables (388 MB) do not fit the 126 MB L2; at ~70 GB/s it is 1 % of HBM bandwidth
-            "traffic": TRAFFIC_K_DEC_PAIR if (pair[0] and N == 100000) else None, "launch_ms": per_launch_ms, "launches": dom_n,
-            "peak_source": "measured live: phe_int_pipe_peak (IMAD.WIDE.U32 issue rate, all SMs)",
-            "algorithmic_mac32_per_op": W_DEC_2048,
-            "note": "algorithmic MAC32 of the reference algorithm (SURVEY 8d: two 2048-bit windowed modexps) against the "
-                    "integer-multiplier peak; the kernel runs 52-bit limb products on the FP64 pipe and the p-adic pair form "
-                    "needs half the products, hence frac > 1 -- fp64_pipe / product_mix count what is executed",
-            "share_of_step": dom_ms / ms_total,
-            # the pipe the kernel executes on: DFMA/DADD lane operations per second against the measured DFMA rate
-            "fp64_pipe": {"executed_fp64_per_op": 3 * limb_products, "achieved": 3 * prod_rate / 1e12, "peak": fp64_peak / 1e12,
-                          "unit": "T FP64 lane-ops/s", "frac": 3 * prod_rate / fp64_peak,
-                          "peak_source": "measured live: phe_fp64_pipe_peak (DFMA.RZ issue rate, all SMs)"},
+            # the path is arithmetic bound: its multiplier is the FP64 pipe (csrc/mont52.cuh), so that is
+            # the roofline: EXECUTED DFMA/DADD lane operations per second over the DFMA issue rate measured in this run
+            "bound": "fp64_pipe", "kernel": dom_name,
+            "achieved": view["achieved"], "peak": view["peak"], "unit": view["unit"], "frac": view["frac"],
+            "peak_source": "measured live: phe_fp64_pipe_peak (DFMA.RZ issue rate, all SMs)",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "launch_ms": per_launch_ms, "launches": dom_n, "share_of_step": dom_ms / ms_total,
+            "executed": view["executed"], "limb_products_per_op": view["limb_products_per_op"],
+            "fp64_lane_ops_per_op": view["fp64_lane_ops_per_op"],
             # the practical ceiling: the bare 2 DFMA + DADD + IADD3 + IADD3.X mix of one limb product
-            "product_mix": {"executed": exec_note, "limb_products_per_op": limb_products, "achieved": prod_rate / 1e12,
-                            "peak": mix_peak / 1e12, "unit": "T limb-products/s", "frac": prod_rate / mix_peak,
-                            "peak_source": "measured live: phe_product_mix_peak (same instruction mix, nothing else)"},
-            # HBM view of the same kernel (sanity counter: the path is arithmetic bound)
+            "product_mix": dict(view["product_mix"], peak_source="measured live: phe_product_mix_peak (same instruction mix, nothing else)"),
+            # the north_star's view: MAC32 of the reference's textbook algorithm per second against the
+            # measured IMAD.WIDE rate -- a speed-up over an integer-pipe implementation, NOT a roofline fraction
+            "textbook_mac32": {"algorithmic_mac32_per_op": W_DEC_2048,
+                               "achieved_tmac32_s": W_DEC_2048 * ops_per_launch / (per_launch_ms * 1e-3) / 1e12,
+                               "imad_wide_peak_tmac32_s": peak / 1e12,
+                               "speedup_vs_textbook_imad": W_DEC_2048 * ops_per_launch / (per_launch_ms * 1e-3) / peak},
+            # HBM view of the same kernel (sanity counter)
             "hbm": {"algorithmic_bytes_per_op": 512 + 2 * 128 + 256, "achieved_gbs": (512 + 2 * 128 + 256) * ops_per_launch / (per_launch_ms * 1e-3) / 1e9,
                     "peak_gbs": _measured_hbm()},
         }
     kernels = {k: {"ms_total": v[0], "launches": v[1]} for k, v in ktimes.items() if v[1]}
     if comb_n:
         kernels[enc_kernel]["encrypt_ops_s"] = N * args.steps / (comb_ms * 1e-3)
-        kernels[enc_kernel]["frac_of_int_pipe_peak_on_reference_work"] = W_ENC_DJN_2048 * N * args.steps / (comb_ms * 1e-3) / peak
+        enc_products, enc_note = _enc_npair_products(capi, pk) if enc_kernel == "k_encrypt_npair" else (None, None)
+        if enc_products:
+            kernels[enc_kernel]["fp64_pipe"] = _fp64_view(enc_products, N * args.steps / comb_n, comb_ms / comb_n, fp64_peak, mix_peak, enc_note)
+        kernels[enc_kernel]["speedup_vs_textbook_imad"] = W_ENC_DJN_2048 * N * args.steps / (comb_ms * 1e-3) / peak
     dec_ms = sum(ktimes[k][0] for k in ("k_dec_prep", "k_powm", "k_dec_tail", "k_dec_pair", "k_dec_crt"))
     if dec_ms:
         kernels["decrypt_ops_s"] = N * args.steps / (dec_ms * 1e-3)
 
-    # ---- secondary lines: HE add / HE mul (BASELINE configs[2] shapes, reduced batch unless --full) -----------
-    secondary = None
-    if not args.no_secondary:
-        secondary = _secondary(torch, capi, pk, dev, stream, args, peak)
+    # ---- BASELINE configs[2]: 1 M HE add / HE mul on one GPU, a sample of the outputs checked against the oracle ----
+    config3 = None
+    if world == 1 and not args.no_secondary:
+        config3 = _config3(torch, capi, pk, n, dev, stream, args, peak, fp64_peak, mix_peak)
+
+    # ---- BASELINE configs[4]: 3072-bit key, batch 100 000 on one GPU ----------------------------------------------
+    config5 = None
+    if world == 1 and not args.no_config5:
+        del flush
+        config5 = _config5(torch, capi, dev, stream, args, fp64_peak, mix_peak)
+
+    # ---- BASELINE configs[3]: encrypt sharded over the GPUs + gather of the ciphertext buffers --------------------
+    config4 = None
+    if world > 1 and not args.no_config4:
+        config4 = _config4(torch, dist, capi, pk, n, hs, dev, stream, rank, world, args)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -----------------------------------------------------------
     cpu_baseline = None
@@ -371,13 +443,47 @@ def run_gpu(args):
                        "l2": "flushed between timed iterations (256 MiB memset inside the timed region)",
                        "comb_bits": pk.comb_bits,
                        "comb_table": "fixed-base comb table of the DJN obfuscator hs, %d-bit digits, built once per key during warm-up (outside the timed region)" % pk.comb_bits},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": kernels, "secondary": secondary,
+            "e2e": e2e, "e2e_api": e2e_api, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "comb": {"comb_bits": pk.comb_bits, "comb_table_bytes": comb_bytes, "comb_build_ms": comb_build_ms,
+                     "warmup_s": warmup_s, "note": "one-off per key, inside the warm-up: the first %d-element encrypts run on a 12-bit table and promote the key to the wide one" % N},
+            "kernels": kernels, "config3": config3, "config4": config4, "config5": config5,
         }
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _e2e_api(N, n, p, q, hs, world, max_over_ranks, barrier):
+    """The call a user of the reference makes (ipcl_python.py:108-147, 219-245): PaillierPublicKey.encrypt(ndarray of
+    float64, pageable) -> PaillierEncryptedNumber -> PaillierPrivateKey.decrypt -> list of Python floats.  Obfuscator
+    exponents are drawn by the library (device ChaCha20), H2D / D2H and the fixed-point codec are inside the timing."""
+    import ipcl_python as L4
+    from ipcl_python.bindings.ipcl_bindings import ipclPublicKey
+    pub = L4.PaillierPublicKey(ipclPublicKey.create(L4.BNUtils.int2BN(n), 2048, L4.BNUtils.int2BN(hs), 1024))
+    pri = L4.PaillierPrivateKey(pub, p, q)
+    x = (np.arange(N, dtype=np.float64) + 11.0) * 1234.5678
+    for _ in range(2):       # the second call promotes this key object to its wide comb table
+        y = pri.decrypt(pub.encrypt(x))
+    barrier()
+    steps, each = 3, []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        ct = pub.encrypt(x)
+        t2 = time.perf_counter()
+        y = pri.decrypt(ct)
+        each.append([round((t2 - t1) * 1e3, 2), round((time.perf_counter() - t2) * 1e3, 2)])
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+    if not (len(y) == N and isinstance(y[0], float) and np.array_equal(np.asarray(y, dtype=np.float64), x)):
+        raise RuntimeError("Python API round trip decrypt(encrypt(x)) != x")
+    return {"value": world * 2.0 * N / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "ms_each_step_encrypt_decrypt": each,
+            "h2d_bytes_per_step": int(N * 2 * 4), "d2h_bytes_per_step": int(N * 64 * 4),
+            "api": "PaillierPublicKey.encrypt(float64 ndarray, pageable) -> PaillierPrivateKey.decrypt -> Python floats; "
+                   "r drawn by the library; the ciphertext batch stays in HBM between the two calls",
+            "round_trip_exact": True}
 
 
 def _measured_hbm():
@@ -388,8 +494,23 @@ def _measured_hbm():
         return 6650.0  # fallback stated in B200_PROFILING.md
 
 
-def _secondary(torch, capi, pk, dev, stream, args, peak):
-    """HE add (ct*ct mod n^2) and HE mul (ct^e, 53-bit e) throughput, device resident."""
+def _timed(torch, fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _config3(torch, capi, pk, n, dev, stream, args, peak, fp64_peak, mix_peak):
+    """HE add (ct*ct mod n^2) and HE mul (ct^e; 53-bit and 2048-bit e) throughput, device resident, batch 1 M
+    (BASELINE configs[2]); a seeded sample of the output rows is compared with the CPU oracle bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
     M = args.secondary_batch
     g = torch.Generator(device=dev)
     g.manual_seed(SEED)
@@ -401,33 +522,189 @@ def _secondary(torch, capi, pk, dev, stream, args, peak):
     e[:, 0] = torch.randint(0, 2**31 - 1, (M,), device=dev, dtype=torch.int32, generator=g)
     e[:, 1] = torch.randint(0, 2**20, (M,), device=dev, dtype=torch.int32, generator=g) | (1 << 20)
     out = torch.empty_like(a)
-    res = {"batch": M}
+    cores = os.cpu_count() or 1
+    S = min(M, args.check_rows)
+    rows = torch.from_numpy(np.random.Generator(np.random.PCG64(SEED)).choice(M, size=S, replace=False)).to(dev)
+    u32 = lambda t: np.ascontiguousarray(t.cpu().numpy().view(np.uint32))   # noqa: E731
+    res = {"batch": M, "checked_rows": S, "checker": "oracle/paillier_oracle.c (OpenSSL BIGNUM), %d pthreads" % cores}
 
-    def timed(fn, reps):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
-    ms = timed(lambda: pk.add_dev(a.data_ptr(), M, b.data_ptr(), M, out.data_ptr(), stream), 5)
+    ms = _timed(torch, lambda: pk.add_dev(a.data_ptr(), M, b.data_ptr(), M, out.data_ptr(), stream), 5)
     res["he_add_ops_s"] = M / (ms * 1e-3)
-    res["he_add_frac_int_pipe"] = W_ADD_2048 * M / (ms * 1e-3) / peak
+    res["he_add_ms"] = ms
     res["he_add_gbs"] = 3 * 512 * M / (ms * 1e-3) / 1e9
-    ms = timed(lambda: pk.mul_dev(a.data_ptr(), M, e.data_ptr(), 2, M, 53, out.data_ptr(), stream), 2)
+    res["he_add_frac_hbm"] = res["he_add_gbs"] / _measured_hbm()
+    res["he_add_fp64_pipe"] = _fp64_view(2 * 2 * 80 * 80, M, ms, fp64_peak, mix_peak, "2 Montgomery products of 2*80^2 limb products")
+    res["he_add_speedup_vs_textbook_imad"] = W_ADD_2048 * M / (ms * 1e-3) / peak
+    if not np.array_equal(u32(out[rows]), c_oracle.add(n, 64, u32(a[rows]), u32(b[rows]), threads=cores)):
+        raise RuntimeError("config 3: HE add differs from the oracle")
+    # broadcast form (ct + one ct): the second operand is brought into the Montgomery domain once
+    ms = _timed(torch, lambda: pk.add_dev(a.data_ptr(), M, b.data_ptr(), 1, out.data_ptr(), stream), 5)
+    res["he_add_broadcast_ops_s"] = M / (ms * 1e-3)
+    if not np.array_equal(u32(out[rows]), c_oracle.add(n, 64, u32(a[rows]), np.repeat(u32(b[:1]), S, axis=0), threads=cores)):
+        raise RuntimeError("config 3: broadcast HE add differs from the oracle")
+
+    ms = _timed(torch, lambda: pk.mul_dev(a.data_ptr(), M, e.data_ptr(), 2, M, 53, out.data_ptr(), stream), 2)
     res["he_mul53_ops_s"] = M / (ms * 1e-3)
-    res["he_mul53_frac_int_pipe"] = W_MUL53_2048 * M / (ms * 1e-3) / peak
+    res["he_mul53_ms"] = ms
+    res["he_mul53_speedup_vs_textbook_imad"] = W_MUL53_2048 * M / (ms * 1e-3) / peak
+    if not np.array_equal(u32(out[rows]), c_oracle.mul(n, 64, u32(a[rows]), u32(e[rows]), threads=cores)):
+        raise RuntimeError("config 3: HE mul (53-bit exponents) differs from the oracle")
     # full-width exponents (2048 bits, SURVEY 8d "mul (full)"): a tenth of the batch
     Mf = max(1, M // 10)
     ef = torch.randint(0, 2**31 - 1, (Mf, 64), device=dev, dtype=torch.int32, generator=g)
-    ms = timed(lambda: pk.mul_dev(a.data_ptr(), Mf, ef.data_ptr(), 64, Mf, 2048, out.data_ptr(), stream), 1)
+    ms = _timed(torch, lambda: pk.mul_dev(a.data_ptr(), Mf, ef.data_ptr(), 64, Mf, 2048, out.data_ptr(), stream), 1)
     res["he_mul2048_batch"] = Mf
     res["he_mul2048_ops_s"] = Mf / (ms * 1e-3)
+    Sf = min(Mf, max(1, S // 8))
+    if not np.array_equal(u32(out[:Sf]), c_oracle.mul(n, 64, u32(a[:Sf]), u32(ef[:Sf]), threads=cores)):
+        raise RuntimeError("config 3: HE mul (2048-bit exponents) differs from the oracle")
+    res["he_mul2048_checked_rows"] = Sf
+    res["bit_exact_vs_oracle"] = True
     return res
+
+
+def _config5(torch, capi, dev, stream, args, fp64_peak, mix_peak):
+    """BASELINE configs[4]: 3072-bit key (6144-bit n^2), batch 100 000 encrypt + decrypt on one GPU.  The reference
+    stops at 2048-bit keys (ipcl_python.py:29-30): parity is against the oracle (sampled rows) + the full round trip."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import paillier_oracle as O
+    bits, N = 3072, args.config5_batch
+    nw = bits // 32
+    pk_o, sk_o = O.seeded_keypair(bits, 77, djn=True)
+    pk = capi.PubKey(pk_o.n, bits, djn=True, hs=pk_o.hs)
+    sk = capi.PrivKey(pk, sk_o.p, sk_o.q)
+    rng = np.random.Generator(np.random.PCG64(SEED))
+    m_np = np.zeros((N, nw), dtype=np.uint32)
+    m_np[:, :2] = rng.integers(0, 1 << 32, size=(N, 2), dtype=np.uint64).astype(np.uint32)
+    m_np[:, 1] &= (1 << 21) - 1                      # 53-bit plaintexts (float64 mantissas), as configs[1]
+    r_np = rng.integers(0, 1 << 32, size=(N, nw // 2), dtype=np.uint64).astype(np.uint32)
+    m = torch.from_numpy(m_np.view(np.int32)).to(dev)
+    r = torch.from_numpy(r_np.view(np.int32)).to(dev)
+    ct = torch.empty((N, 2 * nw), dtype=torch.int32, device=dev)
+    out = torch.empty((N, nw), dtype=torch.int32, device=dev)
+
+    def step():
+        pk.encrypt_dev(m.data_ptr(), N, r.data_ptr(), nw // 2, ct.data_ptr(), stream)
+        sk.decrypt_dev(ct.data_ptr(), N, out.data_ptr(), stream)
+
+    for _ in range(2):      # the second pass runs on the wide comb table
+        step()
+    torch.cuda.synchronize()
+    comb_bytes, comb_build_ms = pk.comb_info
+    reps = 2
+    capi.timing_enable(True)
+    ms = _timed(torch, step, reps)
+    kt = capi.timing_read()
+    capi.timing_enable(False)
+    if not torch.equal(out, m):
+        raise RuntimeError("config 5: round trip D(E(m)) != m")
+    idx = [0, 1, N // 2, N - 1]
+    ct_h = ct[idx].cpu().numpy().view(np.uint32)
+    want = O.encrypt_batch(pk_o, capi.array_to_ints(m_np[idx]), capi.array_to_ints(r_np[idx]))
+    if capi.array_to_ints(ct_h) != want:
+        raise RuntimeError("config 5: ciphertexts differ from the oracle")
+    enc_ms, enc_n = kt["k_encrypt_npair"]
+    dec_ms, dec_n = kt["k_dec_pair"]
+    res = {"workload": "3072-bit seeded key (DJN), batch=%d encrypt+decrypt on 1 GPU (BASELINE configs[4])" % N,
+           "ops_s": 2 * N / (ms * 1e-3), "ms_per_step": ms, "comb_bits": pk.comb_bits, "comb_table_bytes": comb_bytes,
+           "comb_build_ms": comb_build_ms, "round_trip": True, "bit_exact_vs_oracle_rows": len(idx)}
+    if enc_n:
+        res["encrypt_ops_s"] = N / (enc_ms / enc_n * 1e-3)
+        res["ms_encrypt"] = enc_ms / enc_n
+        ep, en_ = _enc_npair_products(capi, pk)
+        if ep:
+            res["encrypt_fp64_pipe"] = _fp64_view(ep, N, enc_ms / enc_n, fp64_peak, mix_peak, en_)
+    if dec_n:
+        res["decrypt_ops_s"] = N / (dec_ms / dec_n * 1e-3)
+        res["ms_decrypt"] = dec_ms / dec_n
+        dp, dn = _dec_pair_products(capi, sk)
+        if dp:
+            view = _fp64_view(dp, N, dec_ms / dec_n, fp64_peak, mix_peak, dn)
+            res["roofline"] = {"bound": "fp64_pipe", "kernel": "k_dec_pair<30>", "achieved": view["achieved"], "peak": view["peak"],
+                               "unit": view["unit"], "frac": view["frac"], "executed": dn, "product_mix": view["product_mix"]}
+    return res
+
+
+def _config4(torch, dist, capi, pk, n, hs, dev, stream, rank, world, args):
+    """BASELINE configs[3]: world x 2^20 DJN encrypts sharded over the GPUs of the node, then every rank holds the whole
+    ciphertext matrix: (a) NCCL all-gather of the shards, (b) the encrypt kernel itself stores every row into all ranks'
+    buffers over NVLink (CUDA IPC peer memory).  CUDA events, max over ranks; checksum of the gathered matrix must agree
+    on every rank and sampled rows must equal the Python-int formula."""
+    from pailliercryptolib_python_b200.sharding import PeerGather, gather_rows, shard_bounds
+    count = world * args.config4_rows_per_gpu
+    lo, hi = shard_bounds(count, world, rank)
+    m_np, r_np = make_workload(hi - lo, seed=4321 + rank)      # every rank generates only its own rows
+    m = torch.from_numpy(m_np.view(np.int32)).to(dev)
+    r = torch.from_numpy(r_np.view(np.int32)).to(dev)
+    local_ct = torch.empty((hi - lo, 128), dtype=torch.int32, device=dev)
+
+    def maxr(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def check(full):
+        ok = True
+        for row in (0, hi - lo - 1):
+            mi = int.from_bytes(m_np[row].tobytes(), "little")
+            ri = int.from_bytes(r_np[row].tobytes(), "little")
+            want = (1 + mi * n) * pow(hs, ri, n * n) % (n * n)
+            ok = ok and int.from_bytes(full[lo + row].cpu().numpy().tobytes(), "little") == want
+        chk = full.to(torch.int64).sum(dim=0)
+        ref = chk.clone()
+        dist.broadcast(ref, 0)
+        ok = ok and bool(torch.equal(chk, ref))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
+    def run_nccl():
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        pk.encrypt_dev(m.data_ptr(), hi - lo, r.data_ptr(), 32, local_ct.data_ptr(), stream)
+        e1.record()
+        full = gather_rows(local_ct, count)
+        e2.record()
+        torch.cuda.synchronize()
+        return full, maxr([e0.elapsed_time(e2), e0.elapsed_time(e1), e1.elapsed_time(e2)])
+
+    out = {"workload": "2048-bit DJN encrypt, batch=%d sharded over %d GPUs + gather of the ciphertext buffers (BASELINE configs[3])" % (count, world),
+           "batch": count, "gathered_bytes": count * 512}
+    run_nccl()
+    best = None
+    for _ in range(2):
+        full, t = run_nccl()
+        if best is None or t[0] < best[0]:
+            best = t
+    out["nccl_all_gather"] = {"encrypt_ops_s": count / (best[0] * 1e-3), "ms_total": best[0], "ms_encrypt": best[1], "ms_gather": best[2],
+                              "gather_gbs_per_gpu": count * 512 * (world - 1) / world / (best[2] * 1e-3) / 1e9,
+                              "checksum_equal_on_all_ranks_and_rows_match_oracle": check(full)}
+    del full
+    pg = PeerGather(pk, count, dev)
+
+    def run_fused():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        pg.encrypt(m, r, stream)
+        e1.record()
+        full = pg.finish()
+        wall = (time.perf_counter() - t0) * 1e3     # includes the closing barrier: every row is in every buffer
+        return full, maxr([wall, e0.elapsed_time(e1)])
+
+    pg.full.zero_()
+    run_fused()
+    best = None
+    for _ in range(2):
+        pg.full.zero_()
+        full, t = run_fused()
+        if best is None or t[0] < best[0]:
+            best = t
+    out["fused_peer_stores"] = {"encrypt_ops_s": count / (best[0] * 1e-3), "ms_total": best[0], "ms_encrypt_kernel": best[1],
+                                "checksum_equal_on_all_ranks_and_rows_match_oracle": check(full)}
+    return out
 
 
 _JSON_OUT = None
@@ -460,7 +737,12 @@ def main():
     ap.add_argument("--secondary-batch", type=int, default=1000000)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE configs[2] (1 M HE add / HE mul)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the sharded encrypt + gather block (multi-GPU runs)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 3072-bit block (single-GPU runs)")
+    ap.add_argument("--config4-rows-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--config5-batch", type=int, default=100000)
+    ap.add_argument("--check-rows", type=int, default=1000, help="rows of the 1 M add / mul outputs compared with the oracle")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

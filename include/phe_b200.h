@@ -11,6 +11,10 @@
  *     last error on the calling thread (the pybind11 shim maps it to RuntimeError, as ipcl's ERROR_CHECK does);
  *   - *_dev variants take CUDA device pointers and a cudaStream_t (as void*), enqueue only, and never
  *     synchronise; the plain variants take host pointers and include H2D/D2H.
+ *   - stream rule: the scratch of a key (window tables, intermediates) is shared by all calls on that key.  Calls on
+ *     one key may come from any streams and threads: they are ordered on the GPU in the order they were made (each
+ *     call's stream waits on an event recorded after the previous call on that key; no host synchronisation), so they
+ *     never overlap each other.  Calls on different keys are independent and do overlap.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with an error.
  */
 #ifndef PHE_B200_H_
@@ -74,6 +78,8 @@ void phe_pubkey_destroy(phe_pubkey* pk);
  * variable PHE_COMB_BITS sets the default.  phe_pubkey_comb_bits returns the width in use (0 before a table exists). */
 int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits);
 int phe_pubkey_comb_bits(const phe_pubkey* pk);
+/* What the table in use costs: its bytes of device memory and the wall time of its build in ms (0, 0 before one exists). */
+int phe_pubkey_comb_info(const phe_pubkey* pk, unsigned long long* table_bytes, double* build_ms);
 int phe_pubkey_bits(const phe_pubkey* pk);
 int phe_pubkey_n_words(const phe_pubkey* pk);
 int phe_pubkey_is_djn(const phe_pubkey* pk);
@@ -91,7 +97,9 @@ int phe_privkey_get_p(const phe_privkey* sk, uint32_t* p_out);  /* n_words words
 int phe_privkey_get_q(const phe_privkey* sk, uint32_t* q_out);  /* n_words words, zero padded (PrivateKey::getQ) */
 
 /* ipcl::generateKeypair(n_length, enable_DJN) (ipcl_bindings.cpp:12-15): host prime search.
- * p, q = 3 (mod 4), top two bits set, gcd(p-1, q-1) = 2.  Outputs: n (bits/32 words), p, q (bits/64 words). */
+ * p, q = 3 (mod 4), top two bits set, gcd(p-1, q-1) = 2.  bits: a multiple of 4 in [200, 3072] (the reference's rule,
+ * 200 <= bits <= 2048 and bits % 4 == 0, with the upper limit lifted for BASELINE config 5).
+ * Outputs: n (ceil(bits / 32) words), p, q (ceil(bits / 64) words). */
 int phe_keygen(int bits, uint32_t* n_out, uint32_t* p_out, uint32_t* q_out);
 
 /* ---- the hot path, host buffers -------------------------------------------------------------------------- */
@@ -145,14 +153,18 @@ int phe_modexp(const uint32_t* base, const uint32_t* exp, const uint32_t* modulu
 
 /* ---- the hot path, device buffers (zero-copy chaining, multi-GPU gather) ----------------------------------- */
 
+/* make_secure == 0: ct = 1 + m n (d_r ignored).  make_secure != 0: ct = (1 + m n) * obf(r) with r = d_r (count x r_words,
+ * device memory) or, when d_r == NULL, drawn by the library exactly as phe_encrypt does (DJN: ChaCha20 keystream on the
+ * stream, keyed from getrandom(2); classic: host CSPRNG, uploaded).  Caller-supplied r must come from a CSPRNG; the
+ * explicit form exists for the parity tests. */
 int phe_encrypt_dev(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
-                    uint32_t* d_ct_out, void* stream);
+                    int make_secure, uint32_t* d_ct_out, void* stream);
 /* The same fused with the gather of ciphertext shards (BASELINE config 4): every row is also stored to the same row of
  * n_peers (<= 15) more buffers -- the other ranks' gather buffers, opened with CUDA IPC -- by the encrypt kernel itself,
  * so the transfer over NVLink overlaps the arithmetic.  d_ct_out and every d_peer_out[k] already point at this rank's
- * first row.  DJN keys, explicit r.  phe_enable_peer_access(dev) = cudaDeviceEnablePeerAccess on the current device. */
+ * first row.  DJN keys.  phe_enable_peer_access(dev) = cudaDeviceEnablePeerAccess on the current device. */
 int phe_encrypt_dev_multi(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
-                          uint32_t* d_ct_out, uint32_t* const* d_peer_out, int n_peers, void* stream);
+                          int make_secure, uint32_t* d_ct_out, uint32_t* const* d_peer_out, int n_peers, void* stream);
 int phe_enable_peer_access(int peer_device);
 /* CUDA IPC for those buffers: export a phe_dev_alloc block as a 64-byte handle; open it in another process of the node
  * (on its current device, peer access enabled lazily); close the mapping. */

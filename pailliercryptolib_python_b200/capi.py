@@ -21,7 +21,7 @@ SYMBOLS = [
     "phe_privkey_create", "phe_privkey_destroy", "phe_privkey_get_p", "phe_privkey_get_q", "phe_keygen",
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
-    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_dev_alloc", "phe_dev_free", "phe_copy", "phe_encrypt_dev_multi", "phe_enable_peer_access", "phe_ipc_export", "phe_ipc_open", "phe_ipc_close", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
+    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_pubkey_comb_info", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_dev_alloc", "phe_dev_free", "phe_copy", "phe_encrypt_dev_multi", "phe_enable_peer_access", "phe_ipc_export", "phe_ipc_open", "phe_ipc_close", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
     "phe_product_mix_peak",
 ]
@@ -161,6 +161,13 @@ class PubKey:
         return lib().phe_pubkey_comb_bits(self.h)
 
     @property
+    def comb_info(self):
+        """(bytes of device memory of the comb table in use, wall ms of its build); (0, 0.0) before one exists."""
+        b, ms = ctypes.c_ulonglong(), ctypes.c_double()
+        _check(lib().phe_pubkey_comb_info(self.h, ctypes.byref(b), ctypes.byref(ms)), "phe_pubkey_comb_info")
+        return int(b.value), float(ms.value)
+
+    @property
     def hs(self):
         out = np.zeros(2 * self.n_words, dtype=np.uint32)
         _check(lib().phe_pubkey_get_hs(self.h, _p(out)), "phe_pubkey_get_hs")
@@ -222,15 +229,17 @@ class PubKey:
         return out
 
     # ---- device-pointer ops (ints are raw CUDA pointers, e.g. torch.Tensor.data_ptr()) ------------------
-    def encrypt_dev(self, d_m, count, d_r, r_words, d_out, stream=0):
+    def encrypt_dev(self, d_m, count, d_r, r_words, d_out, stream=0, make_secure=True):
+        """make_secure with d_r None / 0: the library draws the obfuscator exponents itself (as the host call does)."""
         _check(lib().phe_encrypt_dev(self.h, _p(d_m), ctypes.c_size_t(count), _p(d_r) if d_r else None, r_words,
-                                     _p(d_out), ctypes.c_void_p(stream)), "phe_encrypt_dev")
+                                     int(bool(make_secure)), _p(d_out), ctypes.c_void_p(stream)), "phe_encrypt_dev")
 
-    def encrypt_dev_multi(self, d_m, count, d_r, r_words, d_out, peer_outs, stream=0):
+    def encrypt_dev_multi(self, d_m, count, d_r, r_words, d_out, peer_outs, stream=0, make_secure=True):
         """DJN encrypt whose rows also go to the buffers in peer_outs (device pointers, e.g. peer-mapped gather buffers)."""
         arr = (ctypes.c_void_p * max(1, len(peer_outs)))(*[ctypes.c_void_p(int(q)) for q in peer_outs])
-        _check(lib().phe_encrypt_dev_multi(self.h, _p(d_m), ctypes.c_size_t(count), _p(d_r), r_words, _p(d_out),
-                                           ctypes.cast(arr, ctypes.c_void_p), len(peer_outs), ctypes.c_void_p(stream)),
+        _check(lib().phe_encrypt_dev_multi(self.h, _p(d_m), ctypes.c_size_t(count), _p(d_r) if d_r else None, r_words,
+                                           int(bool(make_secure)), _p(d_out), ctypes.cast(arr, ctypes.c_void_p),
+                                           len(peer_outs), ctypes.c_void_p(stream)),
                "phe_encrypt_dev_multi")
 
     def add_dev(self, d_a, na, d_b, nb, d_out, stream=0):
@@ -283,9 +292,9 @@ def modexp(base, exp, modulus, words):
 
 
 def keygen(bits):
-    n = np.zeros(bits // 32, dtype=np.uint32)
-    p = np.zeros(bits // 64, dtype=np.uint32)
-    q = np.zeros(bits // 64, dtype=np.uint32)
+    n = np.zeros((bits + 31) // 32, dtype=np.uint32)
+    p = np.zeros((bits // 2 + 31) // 32, dtype=np.uint32)
+    q = np.zeros((bits // 2 + 31) // 32, dtype=np.uint32)
     _check(lib().phe_keygen(bits, _p(n), _p(p), _p(q)), "phe_keygen")
     return words_to_int(n), words_to_int(p), words_to_int(q)
 

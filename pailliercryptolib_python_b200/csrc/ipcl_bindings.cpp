@@ -517,9 +517,11 @@ PYBIND11_MODULE(ipcl_bindings, m) {
 
   py::class_<Keypair>(m, "ipclKeypair")
       .def_static("generate_keypair", [](int64_t n_length, bool enable_DJN) {
-        if (n_length < 64 || n_length > 3072 || n_length % 64) throw std::runtime_error("generate_keypair: n_length must be a multiple of 64 in [64, 3072]");
-        const int nw = (int)n_length / 32;
-        std::vector<uint32_t> n(nw), p(nw / 2), q(nw / 2);
+        // ipcl::generateKeypair: 200 <= n_length <= 2048, n_length % 4 == 0; here up to 3072
+        if (n_length < 200 || n_length > 3072 || n_length % 4)
+          throw std::runtime_error("generateKeyPair: modulus size in bits should belong to either 1Kb, 2Kb, 3Kb or 4Kb range only, key size exceed the range!!! (n_length must be a multiple of 4 in [200, 3072])");
+        const int nw = ((int)n_length + 31) / 32, pw = ((int)n_length / 2 + 31) / 32;
+        std::vector<uint32_t> n(nw), p(pw), q(pw);
         int rc;
         {
           py::gil_scoped_release nogil;

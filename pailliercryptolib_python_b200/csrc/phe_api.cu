@@ -3,6 +3,7 @@
 #include <sys/random.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -105,6 +106,8 @@ thread_local std::string t_err;
 int fail(const std::string& m) { t_err = m; return 1; }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 #define PHE_TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
+// joins the key's event chain for the rest of the scope (see StreamChain)
+#define KEY_CHAIN(key, stream) ChainScope chain_((key)->chain, (cudaStream_t)(stream)); if (chain_.rc) return chain_.rc
 
 // smallest shape whose capacity covers mod_bits + 8 (R >= 2^8 N keeps every Montgomery product < 2N)
 const ShapeOps* shape_for_bits(int mod_bits) {
@@ -196,8 +199,8 @@ struct DevBuf {
     // grow geometrically to avoid re-allocating on slowly increasing batch sizes
     size_t want = w + w / 8;
     cudaError_t e = cudaMalloc(&p, want * 4);
-    if (e != cudaSuccess) { e = cudaMalloc(&p, w * 4); want = w; }
-    if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, w * 4); want = w; }   // retry without the slack
+    if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
     words = want;
     return 0;
   }
@@ -205,11 +208,40 @@ struct DevBuf {
     if (w <= words) return 0;
     release();
     cudaError_t e = cudaMalloc(&p, w * 4);
-    if (e != cudaSuccess) { p = nullptr; return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
     words = w;
     return 0;
   }
   void release() { if (p) cudaFree(p); p = nullptr; words = 0; }
+};
+
+// The workspaces of a key (window tables, intermediates, scheduler counters) are shared by every call on that key.
+// The *_dev entry points only enqueue on the caller's stream, so two calls on different streams would overlap on the
+// GPU and overwrite each other's scratch.  Every call therefore joins a per-key event chain: before it touches the
+// scratch its stream waits for the event recorded after the previous call on the key, and it records a new one when
+// its own work is enqueued.  Calls on one key thus execute in the order they were made, whatever their streams (no
+// host synchronisation); calls on different keys stay independent.
+struct StreamChain {
+  cudaEvent_t ev = nullptr;
+  cudaStream_t last = nullptr;
+  bool used = false;
+  int enter(cudaStream_t s) {
+    if (used && s != last) CUDA_TRY(cudaStreamWaitEvent(s, ev, 0));
+    return 0;
+  }
+  int leave(cudaStream_t s) {
+    if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev, s));
+    last = s; used = true;
+    return 0;
+  }
+  void release() { if (ev) cudaEventDestroy(ev); ev = nullptr; used = false; }
+};
+// RAII over one call: enter() at construction (status in rc), leave() at scope exit
+struct ChainScope {
+  StreamChain& c; cudaStream_t s; int rc;
+  ChainScope(StreamChain& chain, cudaStream_t st) : c(chain), s(st), rc(chain.enter(st)) {}
+  ~ChainScope() { if (!rc) c.leave(s); }
 };
 
 int upload(DevBuf& b, const std::vector<uint32_t>& v) {
@@ -369,6 +401,8 @@ struct phe_pubkey {
   mutable DevBuf d_prog_n;                         // classic scheme: sliding-window program of the exponent n
   std::vector<uint32_t> h_prog_n;
   mutable std::mutex mu;
+  mutable StreamChain chain;       // orders the calls that share this key's scratch across streams
+  mutable double comb_build_ms = 0.0;   // wall time of the last comb-table build (phe_pubkey_comb_info)
   mutable bool dev_ready = false;  // device state (Montgomery block, comb table) is built on first compute call
 };
 
@@ -387,6 +421,7 @@ struct phe_privkey {
   uint64_t n0invs[3] = {0, 0, 0};
   mutable DevBuf ws_in, ws_out, ws_mont[2], ws_u[2], ws_tbl, ws_sched;
   mutable std::mutex mu;
+  mutable StreamChain chain;
   mutable bool dev_ready = false;
   std::vector<uint32_t> h_ctx[2], h_exp[2], h_prog[2], h_tail;   // host copies uploaded on first compute call
 };
@@ -445,6 +480,7 @@ int pk_ensure_comb(const phe_pubkey* pk, size_t count) {
     if (wb <= 8 || pk->comb_bits_wanted > 0) return fail("comb table: out of device memory");
     wb -= 2;
   }
+  const auto t_build0 = std::chrono::steady_clock::now();
   pk->comb_bits = wb;
   const_cast<phe_pubkey*>(pk)->nwin = (pk->randbits + wb - 1) / wb;
   std::vector<uint32_t> hsw(2 * (size_t)pk->n_words);
@@ -466,6 +502,7 @@ int pk_ensure_comb(const phe_pubkey* pk, size_t count) {
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   dhs.release();
   if (e != cudaSuccess) return fail(std::string("comb table build: ") + cudaGetErrorString(e));
+  pk->comb_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
   pk->comb_ready = true;
   return 0;
 }
@@ -630,7 +667,7 @@ int encrypt_dev_impl(const phe_pubkey* pk, const uint32_t* d_m, size_t count, co
   const int cw = 2 * pk->n_words;
   if (m_words <= 0) m_words = pk->n_words;   // stride of the plaintext rows
   if (count == 0) return 0;
-  if (!d_r || pk->djn) {
+  if (!d_r || pk->djn) {   // d_r == nullptr: make_secure = 0, ct = 1 + m n
     if (d_r) {
       PHE_TRY(pk_ensure_comb(pk, count));
       if ((size_t)r_words * 32 < (size_t)pk->randbits) return fail("phe_encrypt: r_words too small for randbits");
@@ -924,6 +961,7 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
 void phe_pubkey_destroy(phe_pubkey* pk) {
   if (!pk) return;
   for (DevBuf* b : {&pk->ws_inv, &pk->d_ctx, &pk->d_nctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
+  pk->chain.release();
   delete pk;
 }
 int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits) {
@@ -935,6 +973,12 @@ int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits) {
   return 0;
 }
 int phe_pubkey_comb_bits(const phe_pubkey* pk) { return pk ? pk->comb_bits : -1; }
+int phe_pubkey_comb_info(const phe_pubkey* pk, unsigned long long* table_bytes, double* build_ms) {
+  if (!pk) return fail("null");
+  if (table_bytes) *table_bytes = pk->comb_ready ? (unsigned long long)pk->d_comb.words * 4ull : 0ull;
+  if (build_ms) *build_ms = pk->comb_ready ? pk->comb_build_ms : 0.0;
+  return 0;
+}
 int phe_pubkey_bits(const phe_pubkey* pk) { return pk ? pk->bits : -1; }
 int phe_pubkey_n_words(const phe_pubkey* pk) { return pk ? pk->n_words : -1; }
 int phe_pubkey_is_djn(const phe_pubkey* pk) { return pk ? pk->djn : -1; }
@@ -1005,6 +1049,7 @@ void phe_privkey_destroy(phe_privkey* sk) {
   if (!sk) return;
   for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->d_pair_mod[0], &sk->d_pair_mod[1], &sk->d_pair_cst[0], &sk->d_pair_cst[1], &sk->d_pair_prog[0], &sk->d_pair_prog[1], &sk->ws_in, &sk->ws_out,
                     &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl, &sk->ws_sched}) b->release();
+  sk->chain.release();
   delete sk;
 }
 int phe_privkey_get_p(const phe_privkey* sk, uint32_t* o) { if (!sk || !o) return fail("null"); sk->p.to_words(o, sk->hw); return 0; }
@@ -1012,11 +1057,12 @@ int phe_privkey_get_q(const phe_privkey* sk, uint32_t* o) { if (!sk || !o) retur
 
 // ---- key generation (host) ---------------------------------------------------------------------------
 static bool probably_prime(const BN& c) {
-  static std::vector<uint32_t> small;
-  if (small.empty()) {
+  static const std::vector<uint32_t> small = [] {   // initialised once, thread-safe (keygen runs without the GIL)
+    std::vector<uint32_t> v;
     std::vector<bool> sieve(8192, true);
-    for (uint32_t i = 2; i < 8192; ++i) if (sieve[i]) { small.push_back(i); for (uint32_t j = i * i; j < 8192; j += i) sieve[j] = false; }
-  }
+    for (uint32_t i = 2; i < 8192; ++i) if (sieve[i]) { v.push_back(i); for (uint32_t j = i * i; j < 8192; j += i) sieve[j] = false; }
+    return v;
+  }();
   for (uint32_t sp : small) {
     uint64_t rem = 0;
     for (size_t i = c.w.size(); i-- > 0;) rem = ((rem << 32) | c.w[i]) % sp;
@@ -1056,7 +1102,8 @@ static BN random_prime_3mod4(int bits) {
 
 int phe_keygen(int bits, uint32_t* n_out, uint32_t* p_out, uint32_t* q_out) {
   try {
-    if (bits < 64 || bits > 3072 || (bits % 64) != 0) return fail("phe_keygen: bits must be a multiple of 64 in [64, 3072]");
+    // ipcl::generateKeypair accepts 200 <= bits <= 2048 with bits % 4 == 0; 3072 is config 5
+    if (bits < 200 || bits > 3072 || (bits % 4) != 0) return fail("phe_keygen: modulus bit length must be a multiple of 4 in [200, 3072]");
     if (!n_out || !p_out || !q_out) return fail("phe_keygen: null output");
     for (;;) {
       const BN p = random_prime_3mod4(bits / 2), q = random_prime_3mod4(bits / 2);
@@ -1064,31 +1111,51 @@ int phe_keygen(int bits, uint32_t* n_out, uint32_t* p_out, uint32_t* q_out) {
       if (!(hbn::gcd(hbn::sub(p, BN(1)), hbn::sub(q, BN(1))) == BN(2))) continue;
       const BN n = hbn::mul(p, q);
       if ((int)n.bits() != bits) continue;
-      n.to_words(n_out, bits / 32);
-      p.to_words(p_out, bits / 64);
-      q.to_words(q_out, bits / 64);
+      n.to_words(n_out, (bits + 31) / 32);
+      p.to_words(p_out, (bits / 2 + 31) / 32);
+      q.to_words(q_out, (bits / 2 + 31) / 32);
       return 0;
     }
   } catch (const std::exception& e) { return fail(std::string("phe_keygen: ") + e.what()); }
 }
 
 // ---- device-buffer entry points --------------------------------------------------------------------------
+// Obfuscator exponents for a device-path encrypt whose caller passed none: DJN keys draw them on the stream (ChaCha20,
+// as the host path does); classic keys draw r in [1, n-1] on the host and upload.  Result in pk->ws_r.
+static int draw_r_for_dev(const phe_pubkey* pk, size_t count, int* r_words, cudaStream_t s) {
+  if (pk->djn) return random_r_dev(pk, count, r_words, s);
+  std::vector<uint32_t> rgen;
+  PHE_TRY(make_r_host(pk, count, rgen, r_words));
+  PHE_TRY(pk->ws_r.ensure(rgen.size()));
+  CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, rgen.data(), rgen.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));   // rgen is a stack-lifetime staging buffer
+  return 0;
+}
+
 int phe_encrypt_dev(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
-                    uint32_t* d_ct_out, void* stream) {
+                    int make_secure, uint32_t* d_ct_out, void* stream) {
   if (!pk || !d_m || !d_ct_out) return fail("phe_encrypt_dev: null argument");
+  if (count == 0) return 0;
   std::lock_guard<std::mutex> lk(pk->mu);
-    PHE_TRY(pk_ensure_device(pk));
+  PHE_TRY(pk_ensure_device(pk));
+  KEY_CHAIN(pk, stream);
+  if (!make_secure) d_r = nullptr;
+  else if (!d_r) { PHE_TRY(draw_r_for_dev(pk, count, &r_words, (cudaStream_t)stream)); d_r = pk->ws_r.p; }
   return encrypt_dev_impl(pk, d_m, count, d_r, r_words, d_ct_out, (cudaStream_t)stream);
 }
 // DJN encrypt fused with the gather of BASELINE config 4: every ciphertext row is stored to d_ct_out and to the same row
 // of n_peers more buffers (the other ranks' gather buffers, opened through CUDA IPC and reachable over NVLink).
 int phe_encrypt_dev_multi(const phe_pubkey* pk, const uint32_t* d_m, size_t count, const uint32_t* d_r, int r_words,
-                          uint32_t* d_ct_out, uint32_t* const* d_peer_out, int n_peers, void* stream) {
+                          int make_secure, uint32_t* d_ct_out, uint32_t* const* d_peer_out, int n_peers, void* stream) {
   if (!pk || !d_m || !d_ct_out || (n_peers && !d_peer_out)) return fail("phe_encrypt_dev_multi: null argument");
   if (n_peers < 0 || n_peers > NPAIR_MAX_PEERS) return fail("phe_encrypt_dev_multi: at most 15 peer buffers");
-  if (!pk->djn || !d_r) return fail("phe_encrypt_dev_multi: DJN keys with explicit obfuscator exponents only");
+  if (!pk->djn) return fail("phe_encrypt_dev_multi: DJN keys only");
+  if (count == 0) return 0;
   std::lock_guard<std::mutex> lk(pk->mu);
   PHE_TRY(pk_ensure_device(pk));
+  KEY_CHAIN(pk, stream);
+  if (!make_secure) d_r = nullptr;
+  else if (!d_r) { PHE_TRY(draw_r_for_dev(pk, count, &r_words, (cudaStream_t)stream)); d_r = pk->ws_r.p; }
   return encrypt_dev_impl(pk, d_m, count, d_r, r_words, d_ct_out, (cudaStream_t)stream, 0, d_peer_out, n_peers);
 }
 // CUDA IPC for the gather buffers of the fused encrypt: export a buffer from phe_dev_alloc (a whole cudaMalloc block),
@@ -1125,6 +1192,7 @@ int phe_decrypt_dev(const phe_privkey* sk, const uint32_t* d_ct, size_t count, u
   if (count == 0) return 0;
   std::lock_guard<std::mutex> lk(sk->mu);
     PHE_TRY(sk_ensure_device(sk));
+  KEY_CHAIN(sk, stream);
   return decrypt_dev_impl(sk, d_ct, count, d_m_out, (cudaStream_t)stream);
 }
 int phe_add_dev(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint32_t* d_b, size_t nb, uint32_t* d_out,
@@ -1133,6 +1201,7 @@ int phe_add_dev(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint
   if (na == 0) return 0;
   std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));
+  KEY_CHAIN(pk, stream);
   return add_dev_impl(pk, d_a, na, d_b, nb, d_out, (cudaStream_t)stream);
 }
 int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
@@ -1141,6 +1210,7 @@ int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));
+  KEY_CHAIN(pk, stream);
   return mul_dev_impl(pk, d_ct, n, d_e, e_words, ne, exp_bits, d_out, (cudaStream_t)stream);
 }
 
@@ -1184,6 +1254,7 @@ int phe_encrypt_compact(const phe_pubkey* pk, const uint32_t* m, int m_words, si
     std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));
     CUDA_TRY(cudaSetDevice(pk->device));
+    KEY_CHAIN(pk, 0);
     const int cw = 2 * pk->n_words;
     std::vector<uint32_t> rgen;
     const bool device_r = make_secure && !r && pk->djn;   // DJN: r uniform in [0, 2^randbits), drawn on the device
@@ -1217,6 +1288,7 @@ int phe_obfuscate(const phe_pubkey* pk, uint32_t* ct, size_t count, const uint32
     std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));
     CUDA_TRY(cudaSetDevice(pk->device));
+    KEY_CHAIN(pk, 0);
     const int cw = 2 * pk->n_words;
     std::vector<uint32_t> rgen;
     if (!r && pk->djn) {
@@ -1243,6 +1315,7 @@ int phe_decrypt(const phe_privkey* sk, const uint32_t* ct, size_t count, uint32_
     std::lock_guard<std::mutex> lk(sk->mu);
     PHE_TRY(sk_ensure_device(sk));
     CUDA_TRY(cudaSetDevice(sk->pk->device));
+    KEY_CHAIN(sk, 0);
     const int hw = sk->hw, cw = 2 * hw;
     PHE_TRY(sk->ws_in.ensure(count * cw));
     PHE_TRY(sk->ws_out.ensure(count * hw));
@@ -1261,6 +1334,7 @@ int phe_add(const phe_pubkey* pk, const uint32_t* a, size_t na, const uint32_t* 
     std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));
     CUDA_TRY(cudaSetDevice(pk->device));
+    KEY_CHAIN(pk, 0);
     const int cw = 2 * pk->n_words;
     PHE_TRY(pk->ws_a.ensure(na * cw));
     PHE_TRY(pk->ws_b.ensure(nb * cw));
@@ -1283,6 +1357,7 @@ int phe_mul(const phe_pubkey* pk, const uint32_t* ct, size_t n, const uint32_t* 
     std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));
     CUDA_TRY(cudaSetDevice(pk->device));
+    KEY_CHAIN(pk, 0);
     const int cw = 2 * pk->n_words;
     const int ebits = max_bits_host(e, e_words, ne);
     PHE_TRY(pk->ws_a.ensure(n * cw));
@@ -1303,6 +1378,7 @@ int phe_invert(const phe_pubkey* pk, const uint32_t* ct, size_t count, uint32_t*
     std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));
     CUDA_TRY(cudaSetDevice(pk->device));
+    KEY_CHAIN(pk, 0);
     const int cw = 2 * pk->n_words;
     int rc = 0;
     for (size_t off = 0; off < count && !rc; off += CHUNK) {

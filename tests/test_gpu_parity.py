@@ -444,3 +444,79 @@ def test_encrypt_dev_multi_stores_every_row_to_all_buffers(key2048):
         assert np.array_equal(got[row0:], want)
     idx = [0, 1, count - 1]
     assert capi.array_to_ints(want[idx]) == O.encrypt_batch(pk_o, capi.array_to_ints(m_np[idx]), capi.array_to_ints(r_np[idx]))
+
+
+def test_two_streams_share_one_key(key2048):
+    """Stream rule of include/phe_b200.h: calls on one key may come from different (non-blocking) streams; the library
+    chains them with events so that they never overlap on the key's scratch.  Two different batches are decrypted and
+    multiplied concurrently from two streams; both must match the oracle."""
+    import torch
+    pk_o, sk_o, pk, sk = key2048
+    rng = random.Random(SEED + 30)
+    dev = torch.device("cuda", 0)
+    n_rows = 3000
+    batches = []
+    for b in range(2):
+        ms = [rng.getrandbits(53) + b for _ in range(n_rows)]
+        ct_np = np.zeros((n_rows, 128), dtype=np.uint32)
+        ct_np[:, :66] = capi.ints_to_array([1 + m * pk_o.n for m in ms], 66)     # raw ciphertexts 1 + m n
+        batches.append((ms, torch.from_numpy(ct_np.view(np.int32)).to(dev)))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    outs = [torch.empty((n_rows, 64), dtype=torch.int32, device=dev) for _ in range(2)]
+    prods = [torch.empty((n_rows, 128), dtype=torch.int32, device=dev) for _ in range(2)]
+    e = torch.from_numpy(capi.ints_to_array([3, 0], 2)[:1].view(np.int32).copy()).to(dev)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for b in (0, 1):
+            s = streams[b].cuda_stream
+            sk.decrypt_dev(batches[b][1].data_ptr(), n_rows, outs[b].data_ptr(), s)
+            pk.mul_dev(batches[b][1].data_ptr(), n_rows, e.data_ptr(), 2, 1, 2, prods[b].data_ptr(), s)
+    torch.cuda.synchronize()
+    for b in (0, 1):
+        ms = batches[b][0]
+        assert capi.array_to_ints(outs[b].cpu().numpy().view(np.uint32)[:, :2]) == ms
+        got = capi.array_to_ints(prods[b].cpu().numpy().view(np.uint32)[:16])
+        assert got == [pow(1 + m * pk_o.n, 3, pk_o.nsquare) for m in ms[:16]]
+
+
+def test_device_encrypt_draws_r_itself(key2048):
+    """phe_encrypt_dev(make_secure=1, d_r=NULL) draws the obfuscator exponents on the device, exactly as phe_encrypt does:
+    ciphertexts differ from the raw ones and from each other, and decrypt to the plaintexts; make_secure=0 is 1 + m n."""
+    import torch
+    pk_o, sk_o, pk, sk = key2048
+    dev = torch.device("cuda", 0)
+    ms = [5, 5, 7, 123456789]
+    m = torch.from_numpy(capi.ints_to_array(ms, 64).view(np.int32)).to(dev)
+    ct = torch.empty((4, 128), dtype=torch.int32, device=dev)
+    pk.encrypt_dev(m.data_ptr(), 4, None, 0, ct.data_ptr(), 0, make_secure=True)
+    torch.cuda.synchronize()
+    sec = capi.array_to_ints(ct.cpu().numpy().view(np.uint32))
+    assert sec[0] != sec[1] and all(c != 1 + v * pk_o.n for c, v in zip(sec, ms))
+    assert O.decrypt_batch(sk_o, sec) == ms
+    pk.encrypt_dev(m.data_ptr(), 4, None, 0, ct.data_ptr(), 0, make_secure=False)
+    torch.cuda.synchronize()
+    assert capi.array_to_ints(ct.cpu().numpy().view(np.uint32)) == [1 + v * pk_o.n for v in ms]
+
+
+@pytest.mark.parametrize("bits", [200, 1000, 1028, 2044])
+def test_reference_key_lengths(bits):
+    """The reference accepts any n_length % 4 == 0 in [200, 2048]: generate, encrypt with pinned r,
+    add, multiply, decrypt -- all against the oracle.  (Keys whose primes do not fill their words decrypt on the generic
+    Montgomery path instead of the p-adic pair engine.)"""
+    n, p, q = capi.keygen(bits)
+    assert n.bit_length() == bits and p * q == n
+    nw = (bits + 31) // 32
+    pk = capi.PubKey(n, bits, djn=True)
+    sk = capi.PrivKey(pk, p, q)
+    pk_o = O.PubKey(n, bits, True, pk.hs, bits // 2)
+    sk_o = O.PrivKey(pk_o, p, q)
+    rng = random.Random(SEED + bits)
+    ms = [0, 1, n - 1] + [rng.randrange(n) for _ in range(13)]
+    rs = [rng.getrandbits(bits // 2) for _ in ms]
+    ct = pk.encrypt(capi.ints_to_array(ms, nw), capi.ints_to_array(rs, (bits // 2 + 31) // 32))
+    assert capi.array_to_ints(ct) == O.encrypt_batch(pk_o, ms, rs)
+    assert capi.array_to_ints(sk.decrypt(ct)) == ms
+    a, b = capi.array_to_ints(ct[:8]), capi.array_to_ints(ct[8:])
+    assert capi.array_to_ints(pk.add(ct[:8], ct[8:])) == O.add_batch(pk_o, a, b)
+    e = [rng.getrandbits(53) for _ in range(8)]
+    assert capi.array_to_ints(pk.mul(ct[:8], capi.ints_to_array(e, 2))) == O.mul_batch(pk_o, a, e)
