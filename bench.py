@@ -345,7 +345,7 @@ def run_gpu(args):
            "api": "phe_encrypt + phe_decrypt (host buffers, pinned; explicit r)"}
 
     # ---- end to end through the Python API a caller of the reference uses ------------------------------------
-    e2e_api = _e2e_api(N, n, p, q, hs, world, max_over_ranks, barrier)
+    e2e_api = None if args.no_api else _e2e_api(N, n, p, q, hs, world, max_over_ranks, barrier)
 
     # ---- roofline of the dominant kernel: executed FP64 lane operations against the measured DFMA rate ---------
     peak = capi.int_pipe_peak(5)
@@ -738,6 +738,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE configs[2] (1 M HE add / HE mul)")
+    ap.add_argument("--no-api", action="store_true", help="skip the Python-API end-to-end leg")
     ap.add_argument("--no-config4", action="store_true", help="skip the sharded encrypt + gather block (multi-GPU runs)")
     ap.add_argument("--no-config5", action="store_true", help="skip the 3072-bit block (single-GPU runs)")
     ap.add_argument("--config4-rows-per-gpu", type=int, default=1 << 20)

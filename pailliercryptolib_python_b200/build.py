@@ -38,26 +38,30 @@ def _run(cmd):
     return r.stdout
 
 
-def build_lib(force=False, verbose=False):
+def build_lib(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: an A/B build of the kernels with extra -D flags into lib/libphe_b200_<variant>.so (selected at
+    run time with PHE_B200_LIB, see capi.py); the default build has neither."""
+    objdir = OBJDIR if not variant else OBJDIR + "_" + variant
+    lib = LIB if not variant else os.path.join(LIBDIR, "libphe_b200_%s.so" % variant)
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     jobs = []
     objs = []
     for src in CU_SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _newer(o, [s] + hdrs):
-            jobs.append([NVCC] + NVCC_FLAGS + ["-c", s, "-o", o])
+            jobs.append([NVCC] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", s, "-o", o])
     if jobs:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             for out in ex.map(_run, jobs):
                 if verbose and out.strip():
                     print(out)
-    if force or jobs or _newer(LIB, objs):
-        _run([NVCC, "-shared", "--cudart", "static", "-o", LIB] + objs)
-    return LIB
+    if force or jobs or _newer(lib, objs):
+        _run([NVCC, "-shared", "--cudart", "static", "-o", lib] + objs)
+    return lib
 
 
 def build_bindings(force=False):
@@ -86,4 +90,8 @@ def build_all(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_all(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:     # python -m pailliercryptolib_python_b200.build --variant u4 PHE52_U=4 ...
+        i = sys.argv.index("--variant")
+        print(build_lib(variant=sys.argv[i + 1], defines=sys.argv[i + 2:], verbose=True))
+    else:
+        print(build_all(force="--force" in sys.argv, verbose=True))

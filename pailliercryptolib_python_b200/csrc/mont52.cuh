@@ -132,6 +132,13 @@ struct DevPairEnv {
   static PHE_D uint32_t from_below(uint32_t) { return 0u; }
   static PHE_D bool any(bool p) { return p; }
   static PHE_D void sync() { __syncwarp(); }
+  // 8-byte asynchronous global -> shared copy (LDGSTS, no staging registers) and the matching wait: the table entry of
+  // the next multiplication is fetched under the squarings that precede it (paillier_items.cuh: item_dec_pair)
+  static PHE_D void cp_async8(void* dst_shared, const void* src_global) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_shared);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+  }
+  static PHE_D void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 };
 #endif
 

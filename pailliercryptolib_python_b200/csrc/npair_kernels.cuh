@@ -8,6 +8,15 @@
 
 namespace phe {
 
+// Resident CTAs per SM asked of ptxas (i.e. the register cap).  Shared memory allows two CTAs; at L = 20 two CTAs of
+// 255 registers is also what ptxas is given.  At L = 15 (3072-bit keys) the same bound made ptxas schedule
+// k_encrypt_npair one product chain at a time (ncu r02: wait 3.4 stalled warps per issue, issue slots 0.33 busy, every
+// DFMA of a row writing the same register); under the 168-register cap of three CTAs it interleaves the chains.
+#ifndef PHE_NPAIR_CTAS_L15
+#define PHE_NPAIR_CTAS_L15 3
+#endif
+template <int L> struct NPairCtas { static constexpr int V = (L == 15) ? PHE_NPAIR_CTAS_L15 : 2; };
+
 template <int L, int TPI> struct NKShape {
   static constexpr int KP = Shape<L, TPI>::KP;
   static constexpr int GPB = NT / TPI;
@@ -38,7 +47,7 @@ struct MulNPairArgs {
   double* tbl;            // [gridDim.x * GPB][1 << WIN][2 * KP]
 };
 
-template <int L, int TPI, int WIN> __global__ void __launch_bounds__(NT, 2) k_mul_npair(MulNPairArgs p) {
+template <int L, int TPI, int WIN> __global__ void __launch_bounds__(NT, NPairCtas<L>::V) k_mul_npair(MulNPairArgs p) {
   using Env = DevEnv<TPI>;
   using NS = NKShape<L, TPI>;
   extern __shared__ __align__(16) double smem[];
@@ -71,7 +80,7 @@ struct ProgNPairArgs {
   double* tbl;            // [gridDim.x * GPB][1 << (PROG_WS - 1)][2 * KP]
 };
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_powm_prog_npair(ProgNPairArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, NPairCtas<L>::V) k_powm_prog_npair(ProgNPairArgs p) {
   using Env = DevEnv<TPI>;
   using NS = NKShape<L, TPI>;
   extern __shared__ __align__(16) double smem[];
@@ -105,7 +114,7 @@ struct EncNPairArgs {
   int n_peers;
 };
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_encrypt_npair(const __grid_constant__ EncNPairArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, NPairCtas<L>::V) k_encrypt_npair(const __grid_constant__ EncNPairArgs p) {
   using Env = DevEnv<TPI>;
   using NS = NKShape<L, TPI>;
   extern __shared__ __align__(16) double smem[];
@@ -135,7 +144,7 @@ struct CombNPairArgs {
   NPairCtxArgs ctx;
 };
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_comb_bases_npair(CombNPairArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, NPairCtas<L>::V) k_comb_bases_npair(CombNPairArgs p) {
   using Env = DevEnv<TPI>;
   using NS = NKShape<L, TPI>;
   extern __shared__ __align__(16) double smem[];
@@ -148,7 +157,7 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_comb_bases_
   npair_run<L, TPI, Env>(ctl, smem, p.ctx.n0inv, p.ctx.d_top, sm);
 }
 
-template <int L, int TPI> __global__ void __launch_bounds__(NT, 2) k_comb_level_npair(CombNPairArgs p) {
+template <int L, int TPI> __global__ void __launch_bounds__(NT, NPairCtas<L>::V) k_comb_level_npair(CombNPairArgs p) {
   using Env = DevEnv<TPI>;
   using NS = NKShape<L, TPI>;
   extern __shared__ __align__(16) double smem[];

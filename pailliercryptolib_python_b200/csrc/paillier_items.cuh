@@ -660,6 +660,11 @@ template <int L, class PE> PHE_HD void col_copy(double* dst, const double* src) 
 #pragma unroll
   for (int j = 0; j < L; ++j) dst[j * PE::STRIDE] = src[j * PE::STRIDE];
 }
+// global -> shared column copy that does not pass through registers; completed by PE::cp_async_wait()
+template <int L, class PE> PHE_HD void col_copy_async(double* dst_shared, const double* src_global) {
+#pragma unroll
+  for (int j = 0; j < L; ++j) PE::cp_async8(dst_shared + j * PE::STRIDE, src_global + j * PE::STRIDE);
+}
 
 template <int L, class PE>
 PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* prog, uint32_t* out_w, int out_words,
@@ -671,6 +676,7 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
   for (int j = 0; j < L; ++j) x[j] = 0.0;
   int pc = 0, sub = 0, sqleft = 0;
   bool square = false;
+  bool y_pending = false;   // the table entry of the next PO_YT is already on its way into y0 / y1
 
 #pragma unroll 1
   for (;;) {
@@ -681,7 +687,21 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
         const uint32_t ins = prog[pc++];
         const uint32_t op = ins & 0xffu, arg = ins >> 8;
         if (op == PO_MUL) { square = false; break; }
-        if (op == PO_SQR) { square = true; sqleft = (int)arg; break; }
+        if (op == PO_SQR) {
+          square = true; sqleft = (int)arg;
+          // The program is the same for every lane and known ahead: if a multiplication by a table entry follows
+          // these squarings, start fetching the entry now (asynchronously, straight into shared memory: a square
+          // does not touch y0 / y1), so that its DRAM latency -- the per-lane tables do not fit the L2 -- is covered
+          // by the squarings instead of stalling the multiplication (ncu r01: long_scoreboard 0.34 per issue).
+          const uint32_t nxt = prog[pc];
+          if ((nxt & 0xffu) == PO_YT) {
+            const double* src = tbl + (size_t)(nxt >> 8) * 2 * L * ST;
+            col_copy_async<L, PE>(sm.y0, src);
+            col_copy_async<L, PE>(sm.y1, src + L * ST);
+            y_pending = true;
+          }
+          break;
+        }
         if (op == PO_END) { done = true; break; }
         if (op == PO_LOADC) {
           limbs_from_words<L, 1, PE>(x, c_w + arg * chunk_words, chunk_words);
@@ -693,9 +713,14 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
 #pragma unroll
           for (int j = 0; j < L; ++j) { sm.y0[j * ST] = src[j]; sm.y1[j * ST] = src[L + j]; }
         } else if (op == PO_YT) {
-          const double* src = tbl + (size_t)arg * 2 * L * ST;
-          col_copy<L, PE>(sm.y0, src);
-          col_copy<L, PE>(sm.y1, src + L * ST);
+          if (y_pending) {           // prefetched under the preceding squarings
+            PE::cp_async_wait();
+            y_pending = false;
+          } else {
+            const double* src = tbl + (size_t)arg * 2 * L * ST;
+            col_copy<L, PE>(sm.y0, src);
+            col_copy<L, PE>(sm.y1, src + L * ST);
+          }
         } else if (op == PO_YX) {
           col_copy<L, PE>(sm.y0, sm.xs0);
           col_copy<L, PE>(sm.y1, sm.x1);

@@ -259,6 +259,8 @@ struct EmuPairEnv {
   static uint32_t from_below(uint32_t) { return 0u; }
   static bool any(bool p) { return p; }
   static void sync() {}
+  static void cp_async8(void* dst, const void* src) { std::memcpy(dst, src, 8); }
+  static void cp_async_wait() {}
 };
 
 template <int L>
