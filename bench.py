@@ -185,23 +185,32 @@ def run_reference(args):
     return 0
 
 
-def _passes_of_pair_program(prog):
-    """Reduction passes of one pair-engine program (csrc/paillier_items.cuh: PairOp): a square is 2, a multiplication 3."""
-    passes = 0
+def _products_of_pair_program(prog, L):
+    """Executed 52x52-bit limb products of one pair-engine program (csrc/paillier_items.cuh: PairOp).  A reduction pass is
+    L^2 products for the multiplicand and L^2 for the modulus; a multiplication is 3 passes, a square 2."""
+    mul = 3 * 2 * L * L
+    sqr = 2 * 2 * L * L
+    muls = sqrs = 0
     for ins in prog:
         op, arg = ins & 0xFF, ins >> 8
-        passes += 2 * arg if op == 8 else 3 if op == 7 else 0
-    return passes
+        if op == 7:
+            muls += 1
+        elif op == 8:
+            sqrs += arg
+    return muls * mul + sqrs * sqr, muls, sqrs
 
 
 def _dec_pair_products(capi, sk):
-    """Executed 52x52-bit limb products of one decrypt on the p-adic pair engine (both CRT halves), or None."""
+    """Executed limb products of one decrypt on the p-adic pair engine (both CRT halves), or None."""
     pair = [capi.pair_block(sk, y) for y in (0, 1)]
     if not pair[0]:
         return None, None
     L = pair[0]["L"]
-    passes = sum(_passes_of_pair_program(b["prog"]) for b in pair)
-    return passes * 2 * L * L, "%d reduction passes of 2*%d^2 limb products" % (passes, L)
+    tot = muls = sqrs = 0
+    for b in pair:
+        t, m_, s_ = _products_of_pair_program(b["prog"], L)
+        tot, muls, sqrs = tot + t, muls + m_, sqrs + s_
+    return tot, "%d squares (2 passes) + %d multiplications (3 passes) of 2*%d^2 limb products per pass" % (sqrs, muls, L)
 
 
 def _enc_npair_products(capi, pk):

@@ -45,7 +45,8 @@ unsigned long long phe_kernel_launches(void);
 /* Measurement hooks (bench.py): with timing enabled every kernel launch is bracketed by a cudaEvent pair on
  * the stream it is launched on; phe_timing_read waits for the recorded events and returns the summed device
  * time and launch count of one kernel kind since the last phe_timing_enable.  Kinds: 0 k_modmul, 1 k_powm,
- * 2 k_dec_prep, 3 k_dec_tail, 4 k_encrypt_comb, 5 k_encrypt_finish, 6 k_comb_build, 7 k_dec_pair, 8 k_dec_crt. */
+ * 2 k_dec_prep, 3 k_dec_tail, 4 k_encrypt_comb, 5 k_encrypt_finish, 6 k_comb_build, 7 k_dec_pair, 8 k_dec_crt,
+ * 9 k_encrypt_npair, 10 k_mul_npair (and k_scale_npair), 11 k_rows_move. */
 int phe_timing_enable(int on);
 int phe_timing_read(int kind, double* ms_total, unsigned long long* launches);
 const char* phe_timing_kind_name(int kind);
@@ -177,6 +178,31 @@ int phe_add_dev(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uint
 /* exp_bits: upper bound on the bit length of every exponent (uniform loop count); 0 means e_words*32. */
 int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
                 int exp_bits, uint32_t* d_out, void* stream);
+
+/* ---- row operations on device-resident ciphertext matrices ------------------------------------------------------------
+ * What the reference's Python does around the hot path with per-element lists -- exponent alignment
+ * (ipcl_python.py:528-741), inversion of the ciphertexts that meet a negative plaintext (:272-276, 426-441, 470-479,
+ * 851-857), the operand maps of matmul (:777-808) and the add trees of sum / dot / matmul (:746-775, 810-880) -- as
+ * whole-batch operations on [rows, 2 n_words] matrices that stay in HBM.  Index and delta lists are HOST arrays
+ * (int64 row numbers); d_* are device pointers.  All of them enqueue on `stream` and return after the index lists
+ * have been consumed. */
+/* d_dst[i] = d_src[idx[i]] (i < n; idx[i] < src_rows; rows may repeat: a broadcast is a gather of zeros) */
+int phe_gather_rows_dev(const phe_pubkey* pk, const uint32_t* d_src, size_t src_rows, const long long* idx, size_t n,
+                        uint32_t* d_dst, void* stream);
+/* d_dst[idx[i]] = d_src[i] (i < n; idx[i] < dst_rows, distinct) */
+int phe_scatter_rows_dev(const phe_pubkey* pk, const uint32_t* d_src, const long long* idx, size_t n, uint32_t* d_dst,
+                         size_t dst_rows, void* stream);
+/* d_ct[idx[i]] <- d_ct[idx[i]] ^ (2^delta[i]) mod n^2 in place (distinct rows, delta >= 0 of any size): delta squarings
+ * each on the n-adic pair engine -- the reference's HE-mul by the plaintext BASE^delta of the exponent alignment. */
+int phe_scale_rows_dev(const phe_pubkey* pk, uint32_t* d_ct, size_t rows, const long long* idx, const int* delta, size_t n,
+                       void* stream);
+/* d_ct[idx[i]] <- d_ct[idx[i]]^-1 mod n^2 in place (Montgomery's trick on the gathered rows; fails if one of them is
+ * not invertible, leaving d_ct untouched) -- gmpy2.invert of ipcl_python.py:272-276. */
+int phe_invert_rows_dev(const phe_pubkey* pk, uint32_t* d_ct, size_t rows, const long long* idx, size_t n, void* stream);
+/* d_out[g] = HE-sum of the rows d_ct[g * width .. (g + 1) * width) = their product mod n^2 (g < groups): a log-depth tree
+ * with ONE Montgomery product per addition (the factors R^-1 the levels leave behind are repaid by one product with
+ * R^width at the root), one launch per level.  d_ct is not modified.  ipcl_python.py:810-827 (__padded_ct). */
+int phe_segsum_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t groups, size_t width, uint32_t* d_out, void* stream);
 
 /* The obfuscator exponents r of a DJN key, when the caller passes r = NULL, are drawn on the device from a ChaCha20
  * keystream (RFC 8439 block function) keyed with 256 + 96 fresh bits of getrandom(2) per call.  This exposes the

@@ -22,6 +22,7 @@ SYMBOLS = [
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
     "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_pubkey_comb_info", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_dev_alloc", "phe_dev_free", "phe_copy", "phe_encrypt_dev_multi", "phe_enable_peer_access", "phe_ipc_export", "phe_ipc_open", "phe_ipc_close", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
+    "phe_gather_rows_dev", "phe_scatter_rows_dev", "phe_scale_rows_dev", "phe_invert_rows_dev", "phe_segsum_dev",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
     "phe_product_mix_peak",
 ]
@@ -89,7 +90,7 @@ def kernel_launches():
 
 
 KERNEL_KINDS = ["k_modmul", "k_powm", "k_dec_prep", "k_dec_tail", "k_encrypt_comb", "k_encrypt_finish", "k_comb_build",
-                "k_dec_pair", "k_dec_crt", "k_encrypt_npair", "k_mul_npair"]
+                "k_dec_pair", "k_dec_crt", "k_encrypt_npair", "k_mul_npair", "k_rows_move"]
 
 
 def timing_enable(on=True):
@@ -241,6 +242,38 @@ class PubKey:
                                            int(bool(make_secure)), _p(d_out), ctypes.cast(arr, ctypes.c_void_p),
                                            len(peer_outs), ctypes.c_void_p(stream)),
                "phe_encrypt_dev_multi")
+
+    # ---- row operations on device matrices (index / delta lists are host arrays) ----------------------------------
+    @staticmethod
+    def _i64(a):
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))
+
+    def gather_rows_dev(self, d_src, src_rows, idx, d_dst, stream=0):
+        idx, ip = self._i64(idx)
+        _check(lib().phe_gather_rows_dev(self.h, _p(d_src), ctypes.c_size_t(src_rows), ip, ctypes.c_size_t(idx.size),
+                                         _p(d_dst), ctypes.c_void_p(stream)), "phe_gather_rows_dev")
+
+    def scatter_rows_dev(self, d_src, idx, d_dst, dst_rows, stream=0):
+        idx, ip = self._i64(idx)
+        _check(lib().phe_scatter_rows_dev(self.h, _p(d_src), ip, ctypes.c_size_t(idx.size), _p(d_dst),
+                                          ctypes.c_size_t(dst_rows), ctypes.c_void_p(stream)), "phe_scatter_rows_dev")
+
+    def scale_rows_dev(self, d_ct, rows, idx, delta, stream=0):
+        idx, ip = self._i64(idx)
+        delta = np.ascontiguousarray(delta, dtype=np.int32)
+        _check(lib().phe_scale_rows_dev(self.h, _p(d_ct), ctypes.c_size_t(rows), ip,
+                                        delta.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.c_size_t(idx.size),
+                                        ctypes.c_void_p(stream)), "phe_scale_rows_dev")
+
+    def invert_rows_dev(self, d_ct, rows, idx, stream=0):
+        idx, ip = self._i64(idx)
+        _check(lib().phe_invert_rows_dev(self.h, _p(d_ct), ctypes.c_size_t(rows), ip, ctypes.c_size_t(idx.size),
+                                         ctypes.c_void_p(stream)), "phe_invert_rows_dev")
+
+    def segsum_dev(self, d_ct, groups, width, d_out, stream=0):
+        _check(lib().phe_segsum_dev(self.h, _p(d_ct), ctypes.c_size_t(groups), ctypes.c_size_t(width), _p(d_out),
+                                    ctypes.c_void_p(stream)), "phe_segsum_dev")
 
     def add_dev(self, d_a, na, d_b, nb, d_out, stream=0):
         _check(lib().phe_add_dev(self.h, _p(d_a), ctypes.c_size_t(na), _p(d_b), ctypes.c_size_t(nb), _p(d_out),

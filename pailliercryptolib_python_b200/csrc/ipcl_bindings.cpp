@@ -365,6 +365,18 @@ struct CipherText : Packed {
     host_valid = true;
   }
   const uint32_t* operand() const { return host_valid ? data.data() : dev; }   // host or device pointer for the C ABI
+  bool on_device() const { return dev != nullptr; }
+  // device pointer of the batch, uploading it once if it only lives on the host (the row operations below work on HBM)
+  const uint32_t* device() const {
+    if (!dev) {
+      if (count == 0) throw std::runtime_error("ipclCipherText: empty container");
+      uint32_t* d = nullptr;
+      if (phe_dev_alloc(pk->h, words(), &d)) throw_phe("ipclCipherText (device allocation)");
+      if (phe_copy(d, data.data(), words() * 4)) { phe_dev_free(d); throw_phe("ipclCipherText (host -> device)"); }
+      dev = d;
+    }
+    return dev;
+  }
 };
 inline const CipherText& H(const CipherText& c) { c.sync_host(); return c; }
 
@@ -493,6 +505,89 @@ std::shared_ptr<CipherText> ct_mul(const CipherText& a, const PlainText& b) {
   }
   if (rc) { out.drop(); throw_phe("CipherText *"); }
   return out.finish();
+}
+
+// ---- row operations: the batch stays in HBM (include/phe_b200.h "row operations") ------------------------------------
+// What the reference's Python does with lists of BigNumber objects around + and * (ipcl_python.py:528-741 exponent
+// alignment, :272-276 inversion for negative plaintexts, :777-880 matmul operand maps and add trees); called by
+// pailliercryptolib_python_b200/ipcl_python.py, not part of the reference module.
+using IdxArray = py::array_t<long long, py::array::c_style | py::array::forcecast>;
+using DeltaArray = py::array_t<int, py::array::c_style | py::array::forcecast>;
+
+std::shared_ptr<CipherText> device_result(const PubPtr& pk, size_t n) {
+  uint32_t* d = nullptr;
+  if (phe_dev_alloc(pk->h, n * 2 * (size_t)pk->n_words, &d)) throw_phe("ipclCipherText (device allocation)");
+  return std::make_shared<CipherText>(pk, n, d);
+}
+
+// out[i] = a[idx[i]]
+std::shared_ptr<CipherText> ct_gather(const CipherText& a, const IdxArray& idx) {
+  const size_t n = (size_t)idx.size();
+  if (n == 0) throw std::runtime_error("ipclCipherText.gather: empty index list");
+  const uint32_t* src = a.device();
+  auto out = device_result(a.pk, n);
+  int rc;
+  {
+    py::gil_scoped_release nogil;
+    rc = phe_gather_rows_dev(a.pk->h, src, a.count, idx.data(), n, out->dev, nullptr);
+  }
+  if (rc) throw_phe("ipclCipherText.gather");
+  return out;
+}
+
+std::shared_ptr<CipherText> ct_device_copy(const CipherText& a) {
+  const uint32_t* src = a.device();
+  auto out = device_result(a.pk, a.count);
+  if (phe_copy(out->dev, src, a.words() * 4)) throw_phe("ipclCipherText (device copy)");
+  return out;
+}
+
+// copy of a with rows idx raised to 2^delta (exponent alignment)
+std::shared_ptr<CipherText> ct_scaled(const CipherText& a, const IdxArray& idx, const DeltaArray& delta) {
+  if (idx.size() != delta.size()) throw std::runtime_error("ipclCipherText.scale_rows: idx / delta size mismatch");
+  auto out = ct_device_copy(a);
+  int rc;
+  {
+    py::gil_scoped_release nogil;
+    rc = phe_scale_rows_dev(a.pk->h, out->dev, out->count, idx.data(), delta.data(), (size_t)idx.size(), nullptr);
+  }
+  if (rc) throw_phe("ipclCipherText.scale_rows");
+  return out;
+}
+
+// copy of a with rows idx inverted modulo n^2
+std::shared_ptr<CipherText> ct_inverted_rows(const CipherText& a, const IdxArray& idx) {
+  auto out = ct_device_copy(a);
+  int rc;
+  {
+    py::gil_scoped_release nogil;
+    rc = phe_invert_rows_dev(a.pk->h, out->dev, out->count, idx.data(), (size_t)idx.size(), nullptr);
+  }
+  if (rc) throw_phe("ipclCipherText.invert_rows");
+  return out;
+}
+
+// [groups * width] -> [groups]: HE-sum of every run of `width` rows
+std::shared_ptr<CipherText> ct_segsum(const CipherText& a, size_t groups, size_t width) {
+  if (groups == 0 || width == 0 || groups * width != a.count) throw std::runtime_error("ipclCipherText.segsum: groups * width != size");
+  const uint32_t* src = a.device();
+  auto out = device_result(a.pk, groups);
+  int rc;
+  {
+    py::gil_scoped_release nogil;
+    rc = phe_segsum_dev(a.pk->h, src, groups, width, out->dev, nullptr);
+  }
+  if (rc) throw_phe("ipclCipherText.segsum");
+  return out;
+}
+
+// rows [start, start + len) without leaving the device when the batch lives there
+std::shared_ptr<CipherText> ct_chunk(const CipherText& a, size_t start, size_t len) {
+  if (start + len > a.count) throw py::index_error("slice out of range");
+  if (!a.on_device() || len == 0) return std::make_shared<CipherText>(a.pk, H(a).chunk(start, len));
+  auto out = device_result(a.pk, len);
+  if (phe_copy(out->dev, a.dev + start * a.stride, len * a.stride * 4)) throw_phe("ipclCipherText (device slice)");
+  return out;
 }
 
 // ------------------------------------------------------------------------------------------------ context / hybrid
@@ -703,13 +798,19 @@ PYBIND11_MODULE(ipcl_bindings, m) {
       .def("__repr__", [](const CipherText& s) { return "<ipclCipherText " + addr_tag(&s) + ">"; })
       .def("__str__", [](const CipherText& s) { return "<ipclCipherText " + addr_tag(&s) + ">"; })
       .def("__getitem__", [](const CipherText& s, size_t i) { return std::make_shared<BigNumber>(H(s).element(i)); })
-      .def("__getitem__", [](const CipherText& s, const py::slice& sl) { size_t len; const size_t st = slice_bounds(s, sl, &len); return std::make_shared<CipherText>(s.pk, H(s).chunk(st, len)); })
+      .def("__getitem__", [](const CipherText& s, const py::slice& sl) { size_t len; const size_t st = slice_bounds(s, sl, &len); return ct_chunk(s, st, len); })
       .def("modinv", [](const CipherText& a) { return ct_modinv(a); })
+      .def("gather", &ct_gather, "out[i] = self[idx[i]] (rows may repeat); device resident")
+      .def("scale_rows", &ct_scaled, "copy of self with rows idx raised to 2^delta (exponent alignment); device resident")
+      .def("invert_rows", &ct_inverted_rows, "copy of self with rows idx inverted modulo n^2; device resident")
+      .def("segsum", &ct_segsum, "HE-sum of every run of `width` rows: [groups * width] -> [groups]; device resident")
+      .def_property_readonly("on_device", [](const CipherText& s) { return s.on_device(); })
+      .def_property_readonly("host_valid", [](const CipherText& s) { return s.host_valid; })
       .def("__add__", [](const CipherText& a, const CipherText& b) { return ct_add(a, b); })
       .def("__add__", [](const CipherText& a, const PlainText& b) { return ct_add(a, *encrypt(a.pk, b, false)); })
       .def("__mul__", [](const CipherText& a, const PlainText& b) { return ct_mul(a, b); })
       .def("__len__", [](const CipherText& s) { return s.count; })
-      .def("getCipherText", [](const CipherText& s, size_t i) { return std::make_shared<CipherText>(s.pk, H(s).chunk(i, 1)); })
+      .def("getCipherText", [](const CipherText& s, size_t i) { s.check(i); return ct_chunk(s, i, 1); })
       .def("rotate", [](const CipherText& s, int shift) { return std::make_shared<CipherText>(s.pk, H(s).rotated(shift)); })
       .def("getElementVec", [](const CipherText& s, size_t i) { return H(s).element_vec(i); })
       .def("getElementHex", [](const CipherText& s, size_t i) { return H(s).element_hex(i); })

@@ -117,6 +117,12 @@ template <int TPI> struct DevEnv {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_global) : "memory");
   }
   static PHE_D void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+  // bulk prefetch of `bytes` (a multiple of 16, 16-byte aligned) from global memory into the L2 by the TMA unit
+  // (cp.async.bulk.prefetch.L2: one instruction per entry, no registers, no shared memory): the comb-table entry of the
+  // next window of the DJN encrypt is pulled out of HBM while the current product runs (npair_items.cuh: NPairEncCtl)
+  static PHE_D void prefetch_l2(const void* src_global, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_global), "r"(bytes) : "memory");
+  }
 };
 #endif
 
@@ -217,9 +223,15 @@ PHE_HD void mac_span(uint64_t (&acc)[L], const X& x, double y, uint64_t& hprev, 
 // The row loop is unrolled U rows at a time (U divides L): inside a chunk column c of row u lives in
 // acc[(c + u) % L]; after the chunk the accumulators are rotated back by U places.  A fully unrolled L-row body
 // (77 KB at L = 20) misses the 32 KB L1.5 instruction cache on every pass -- ncu: no_instruction = 2.3 stalled
-// warps per issue -- so the body is kept under ~20 KB.
+// warps per issue -- so the body is kept under ~20 KB.  U = 4 at L = 20: r02, k_dec_pair<20> 119.9 ms against 120.6 at
+// U = 5 (profiles/r02_bench_u4_variant.json).
+// A symmetric (triangular) pass 1 of the pair square -- L (L + 1) / 2 instead of L^2 multiplicand products, bit-exact in
+// the emulator and on the GPU -- was built and measured in r02 and is NOT in here: its rows need per-block code next to
+// the general row loop (27 KB loop body, uniform branches between 4-product blocks) and k_dec_pair<20> went from 120.6
+// to 174.9 ms (ncu: no_instruction 1.2 and wait 1.15 stalled warps per issue, 3 % MORE executed instructions).
+// profiles/r02_tri_square_experiment.patch, r02_ncu_k_dec_pair_tri_square_summary.txt.
 #ifndef PHE52_U
-#define PHE52_U 5
+#define PHE52_U 4
 #endif
 // L = 30 (one-lane pair engine of 3072-bit keys): 5 rows are 300 products = 27 KB of code, 3 rows 16 KB
 template <int L> struct Unroll { static constexpr int U = (L > 24 && L % 3 == 0) ? 3 : (L % PHE52_U == 0) ? PHE52_U : (L % 5 == 0) ? 5 : (L % 4 == 0) ? 4 : (L % 3 == 0) ? 3 : (L % 2 == 0) ? 2 : 1; };

@@ -364,6 +364,59 @@ struct NPairPowmCtl {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Exponent alignment: out = c^(2^delta) mod n^2 = delta squarings (the reference multiplies by the plaintext BASE^delta
+// with a full modexp: ipcl_python.py:551-560, 602-606, 672-690).  Every lane group of a CTA runs max_delta squarings
+// (the shuffles of a warp must stay convergent); a group whose own delta is smaller keeps a copy of its value from
+// the moment it was reached (in y0 / y1, which a square does not touch) and takes it back at the end.  The host sorts
+// the rows by delta, so the squarings thrown away are few.
+// ------------------------------------------------------------------------------------------------
+template <int L, int TPI, class Env>
+struct NPairScaleCtl {
+  static constexpr int KP = Shape<L, TPI>::KP;
+  const uint32_t* c_w; int chunk_words;
+  int delta, max_delta;
+  uint32_t* out_w; int out_words;
+  const double* cst; NPairSmem sm;
+  int phase = 0, sq = 0;
+
+  PHE_HD int next(double (&x)[L], const double*& y0, const double*& y1) {
+#pragma unroll 1
+    for (;;) {
+      switch (phase) {
+        case 0: case 1:
+          npair_conv_step<L, TPI, Env>(phase, x, c_w, chunk_words, cst, sm, y0, y1);
+          ++phase;
+          return NK_X1Z;
+        case 2:
+          npair_conv_step<L, TPI, Env>(2, x, c_w, chunk_words, cst, sm, y0, y1);
+          phase = 3;
+          break;
+        case 3:
+          Env::sync();
+          if (sq == delta) {            // this group's result: park it (no shuffles in here: groups may diverge)
+            copy_entry<L, TPI, Env>(sm.y0, sm.xs0);
+            copy_entry<L, TPI, Env>(sm.y1, sm.x1);
+          }
+          Env::sync();
+          if (sq < max_delta) { ++sq; return NK_SQR; }
+          npair_load<L, TPI, Env>(x, sm.y0, sm);     // y0, y1 are adjacent: a pair entry
+          y0 = cst + NE_ONE * KP; y1 = nullptr;
+          phase = 4;
+          return NK_Y1Z;
+        case 4:
+          npair_canon_setup<L, TPI, Env>(x, cst, sm, nullptr);
+          y0 = cst + NE_N * KP;
+          phase = 5;
+          return NK_PLAIN;
+        default:
+          npair_store_words<L, TPI, Env>(out_w, out_words, x, sm);
+          return NK_DONE;
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Sliding-window exponentiation mod n^2 for an exponent SHARED by every item (classic obfuscator r^n; the program
 // format is item_powm_prog's, paillier_items.cuh): table of the odd powers T[k] = x^(2k+1), k < 2^(WS-1), as pair
 // entries in global memory.  Base: nchunks (1 or 2) chunks of chunk_words words.
@@ -478,6 +531,12 @@ struct NPairEncCtl {
   int phase = 0, j = 1;
 
   PHE_HD const double* entry(int win, uint32_t d) const { return comb + ((((size_t)win) << wb) + d) * 2 * KP; }
+  // The table is tens of GB of random 2 KP-double entries (640 B at 2048-bit keys): every fetch is a DRAM access.  The
+  // digits of r are known up front, so one lane of the group asks the TMA unit to bring the next entry into the L2
+  // (cp.async.bulk.prefetch.L2) a whole pair product (~10 us) before npair_set_y copies it.
+  PHE_HD void prefetch(int win) const {
+    if (Env::lane() == 0) Env::prefetch_l2(entry(win, get_bits(r_w, r_words, win * wb, wb)), (uint32_t)(2 * KP * sizeof(double)));
+  }
 
   PHE_HD int next(double (&x)[L], const double*& y0, const double*& y1) {
 #pragma unroll 1
@@ -500,10 +559,12 @@ struct NPairEncCtl {
             phase = 9;
             return NK_PLAIN;
           }
+          if (nwin > 1) prefetch(1);
           npair_load<L, TPI, Env>(x, entry(0, get_bits(r_w, r_words, 0, wb)), sm);
           phase = (nwin > 1) ? 1 : 2;
           break;
         case 1:
+          if (j + 1 < nwin) prefetch(j + 1);     // the entry of the next window: on its way out of HBM under this product
           npair_set_y<L, TPI, Env>(entry(j, get_bits(r_w, r_words, j * wb, wb)), sm);
           y0 = sm.y0; y1 = sm.y1;
           if (++j == nwin) phase = 2;

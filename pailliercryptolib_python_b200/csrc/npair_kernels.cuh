@@ -68,6 +68,37 @@ template <int L, int TPI, int WIN> __global__ void __launch_bounds__(NT, NPairCt
   }
 }
 
+// ---- exponent alignment in place: ct[idx[i]] <- ct[idx[i]]^(2^delta[i]), rows sorted by delta (descending) ---------
+struct ScaleNPairArgs {
+  uint32_t* ct;              // [rows][2 * chunk_words]
+  int chunk_words;
+  const long long* idx;      // [count] distinct rows
+  const int* delta;          // [count], non-increasing
+  int count;
+  NPairCtxArgs ctx;
+};
+
+template <int L, int TPI> __global__ void __launch_bounds__(NT, NPairCtas<L>::V) k_scale_npair(ScaleNPairArgs p) {
+  using Env = DevEnv<TPI>;
+  using NS = NKShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<NS::KP>(smem, p.ctx.entries, NE_COUNT);
+  const NPairSmem sm = npair_group_smem<L, TPI>(smem);
+  const int g = threadIdx.x / TPI;
+  const int cw = 2 * p.chunk_words;
+  for (int base = blockIdx.x * NS::GPB; base < p.count; base += gridDim.x * NS::GPB) {
+    const int want = base + g;
+    const int item = want < p.count ? want : p.count - 1;
+    uint32_t* row = p.ct + (size_t)p.idx[item] * cw;
+    NPairScaleCtl<L, TPI, Env> ctl;
+    ctl.c_w = row; ctl.chunk_words = p.chunk_words;
+    ctl.delta = p.delta[item]; ctl.max_delta = p.delta[base];     // sorted: the first row of the CTA's batch has the most
+    ctl.out_w = want < p.count ? row : nullptr; ctl.out_words = cw;
+    ctl.cst = smem; ctl.sm = sm;
+    npair_run<L, TPI, Env>(ctl, smem, p.ctx.n0inv, p.ctx.d_top, sm);
+  }
+}
+
 // ---- shared-exponent sliding-window modexp mod n^2 (classic obfuscator r^n) -----------------------------------------
 struct ProgNPairArgs {
   const uint32_t* c_w;    // [count][nchunks * chunk_words]

@@ -89,6 +89,32 @@ PHE_HD void item_modmul(const uint32_t* a_w, const uint32_t* b_w, uint32_t* out_
 }
 
 // ------------------------------------------------------------------------------------------------
+// One Montgomery product per element: out = a * b * R^-1 mod N (canonical words).  b is either words (converted here) or
+// a constant entry.  Three uses, all of them HE adds that cost ONE product instead of item_modmul's two:
+//   * broadcast add (other.size == 1): b = the single ciphertext times R, brought there once (b_entry = R^2 first);
+//   * the add tree of sum / dot / matmul (ipcl_python.py:810-827 rotate-and-add): the R^-1 of every level is left in
+//     and the root is multiplied by R^width once (a product of w numbers is w - 1 + 1 Montgomery products);
+//   * an element that only passes a tree level: b = R mod N (the product by the Montgomery one is the identity).
+// ------------------------------------------------------------------------------------------------
+template <int L, int TPI, class Env>
+PHE_HD void item_modmul1(const uint32_t* a_w, const uint32_t* b_w, const double* b_entry, uint32_t* out_w, int nwords,
+                         const double* n_entry, uint64_t n0inv, GroupSmem sm) {
+  double x[L];
+  // b_w may differ between the lane groups of a warp (a tree level mixes products and pass-through elements): only the
+  // loads are conditional, every group goes through the same synchronisation points
+  if (b_w) limbs_from_words<L, TPI, Env>(x, b_w, nwords);
+  else load_entry<L, TPI, Env>(x, b_entry);
+  Env::sync();
+  limbs_to_mem<L, TPI, Env>(sm.b0, x);
+  limbs_from_words<L, TPI, Env>(x, a_w, nwords);
+  Env::sync();
+  montmul<L, TPI, Env>(x, x, sm.b0, n_entry, n0inv);
+  uint64_t xi[L];
+  canonical_ints<L, TPI, Env>(xi, x, n_entry);
+  store_words<L, TPI, Env>(out_w, nwords, xi, sm.b1);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Batched modular inverse (Montgomery's trick), used for the negative-plaintext rule of HE-mul: the reference inverts
 // the ciphertext with gmpy2.invert element by element on the host (ipcl_python.py:272-276, 426-441, 470-479).
 // A lane group owns one block of consecutive elements c_first .. c_(first+cnt-1):
@@ -666,6 +692,16 @@ template <int L, class PE> PHE_HD void col_copy_async(double* dst_shared, const 
   for (int j = 0; j < L; ++j) PE::cp_async8(dst_shared + j * PE::STRIDE, src_global + j * PE::STRIDE);
 }
 
+// x <- 2 x as exact limbs (x < 2^(52 L - 1))
+template <int L> PHE_HD void pair_double(double (&x)[L]) {
+  uint64_t t[L];
+  ints_of<L>(t, x);
+#pragma unroll
+  for (int j = 0; j < L; ++j) t[j] <<= 1;
+  ripple<L>(t, 0u);
+  limbs_of<L>(x, t);
+}
+
 template <int L, class PE>
 PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* prog, uint32_t* out_w, int out_words,
                           const double* n, const double* dcon, uint64_t n0inv, const double* cst, double* tbl,
@@ -817,12 +853,7 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
     } else if (sub == 1) {
       ein = sm.e;
       if (square) {                    // a = 2 X0 (exact limbs again), b = X1
-        uint64_t t[L];
-        ints_of<L>(t, x);
-#pragma unroll
-        for (int j = 0; j < L; ++j) t[j] <<= 1;
-        ripple<L>(t, 0u);
-        limbs_of<L>(x, t);
+        pair_double<L>(x);
         b = sm.x1;
         rout = sm.x1;
       } else {

@@ -2,6 +2,7 @@
 // buffer management, launches.  There is no CPU fallback for the compute entry points.
 #include <sys/random.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -398,6 +399,7 @@ struct phe_pubkey {
   mutable bool comb_ready = false, comb_wide = false;
   mutable size_t comb_seen = 0;   // elements encrypted so far under the automatic width (promotion counter)
   mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_r, ws_tbl, ws_inv;  // op workspaces
+  mutable DevBuf ws_idx, ws_rows, ws_rows2, ws_tree[2], ws_ent; // row operations (alignment, inverse of rows, add trees)
   mutable DevBuf d_prog_n;                         // classic scheme: sliding-window program of the exponent n
   std::vector<uint32_t> h_prog_n;
   mutable std::mutex mu;
@@ -696,6 +698,22 @@ int add_dev_impl(const phe_pubkey* pk, const uint32_t* d_a, size_t na, const uin
                  cudaStream_t s) {
   if (nb != na && nb != 1) return fail("phe_add: size mismatch (b must have na or 1 elements)");
   const int cw = 2 * pk->n_words;
+  if (nb == 1 && na > 1) {
+    // broadcast: bring the single operand into the Montgomery domain once (b R mod n^2), then every element is ONE
+    // Montgomery product a[i] * (b R) * R^-1 instead of two
+    PHE_TRY(pk->ws_ent.ensure((size_t)cw));
+    Modmul1Args c{};
+    c.a = d_b; c.b_w = nullptr; c.b_stride = 0; c.b_entry = pk->ctx.entries + (size_t)ME_R2 * pk->ops->KP;
+    c.out = pk->ws_ent.p; c.nwords = cw; c.count = 1; c.ctx = pk->ctx;
+    CUDA_TRY(pk->ops->modmul1(c, s));
+    for (size_t off = 0; off < na; off += CHUNK) {
+      Modmul1Args a{};
+      a.a = d_a + off * cw; a.b_w = pk->ws_ent.p; a.b_stride = 0; a.b_entry = nullptr;
+      a.out = d_out + off * cw; a.nwords = cw; a.count = (int)std::min(CHUNK, na - off); a.ctx = pk->ctx;
+      CUDA_TRY(pk->ops->modmul1(a, s));
+    }
+    return 0;
+  }
   for (size_t off = 0; off < na; off += CHUNK) {
     const int c = (int)std::min(CHUNK, na - off);
     const bool bc = (nb == 1 && na != 1);
@@ -787,6 +805,138 @@ int invert_dev_impl(const phe_pubkey* pk, const uint32_t* d_a, size_t count, uin
       CUDA_TRY(cudaMemcpyAsync(dsts[k], W + l.out_pad, l.count * cw * 4, cudaMemcpyDeviceToDevice, s));
   }
   CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ---- row operations on device-resident ciphertext matrices ----------------------------------------------------------
+// host index list -> device (int64), in the key's index workspace at word offset `at`
+int upload_idx(const phe_pubkey* pk, const long long* idx, size_t n, size_t rows_limit, size_t at, cudaStream_t s) {
+  for (size_t i = 0; i < n; ++i)
+    if (idx[i] < 0 || (rows_limit && (size_t)idx[i] >= rows_limit)) return fail("row index out of range");
+  PHE_TRY(pk->ws_idx.ensure(at + 2 * n + 2));
+  CUDA_TRY(cudaMemcpyAsync(pk->ws_idx.p + at, idx, n * 8, cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int move_rows_impl(const phe_pubkey* pk, const uint32_t* d_src, const long long* idx, size_t n, size_t rows_limit,
+                   uint32_t* d_dst, int scatter, cudaStream_t s) {
+  if (n == 0) return 0;
+  PHE_TRY(upload_idx(pk, idx, n, rows_limit, 0, s));
+  CUDA_TRY(rows_move(d_src, d_dst, reinterpret_cast<const long long*>(pk->ws_idx.p), (long long)n, 2 * pk->n_words, scatter, s));
+  CUDA_TRY(cudaStreamSynchronize(s));   // idx may be a temporary of the caller (pageable copy)
+  return 0;
+}
+
+int mul_dev_impl(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint32_t* d_e, int e_words, size_t ne,
+                 int exp_bits, uint32_t* d_out, cudaStream_t s);
+
+// ct[idx[i]] <- ct[idx[i]]^(2^delta[i]) in place (distinct rows)
+int scale_rows_impl(const phe_pubkey* pk, uint32_t* d_ct, size_t rows, const long long* idx, const int* delta, size_t n,
+                    cudaStream_t s) {
+  if (n == 0) return 0;
+  const int cw = 2 * pk->n_words;
+  std::vector<size_t> order(n);
+  for (size_t i = 0; i < n; ++i) { order[i] = i; if (delta[i] < 0) return fail("phe_scale_rows: negative delta"); }
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return delta[a] > delta[b]; });
+  std::vector<long long> sidx(n);
+  std::vector<int> sdelta(n);
+  for (size_t i = 0; i < n; ++i) { sidx[i] = idx[order[i]]; sdelta[i] = delta[order[i]]; }
+  {   // distinct rows: two lane groups must not work on one row
+    std::vector<long long> chk(sidx);
+    std::sort(chk.begin(), chk.end());
+    if (std::adjacent_find(chk.begin(), chk.end()) != chk.end()) return fail("phe_scale_rows: duplicate row index");
+  }
+  const size_t dat = 2 * n + 2;
+  PHE_TRY(pk->ws_idx.ensure(dat + n));        // both lists: a later ensure() would move the indices already uploaded
+  PHE_TRY(upload_idx(pk, sidx.data(), n, rows, 0, s));
+  CUDA_TRY(cudaMemcpyAsync(pk->ws_idx.p + dat, sdelta.data(), n * 4, cudaMemcpyHostToDevice, s));
+  const long long* d_idx = reinterpret_cast<const long long*>(pk->ws_idx.p);
+  const int* d_delta = reinterpret_cast<const int*>(pk->ws_idx.p + dat);
+  if (pk->use_npair) {
+    for (size_t off = 0; off < n; off += CHUNK) {
+      ScaleNPairArgs a{};
+      a.ct = d_ct; a.chunk_words = pk->n_words; a.idx = d_idx + off; a.delta = d_delta + off;
+      a.count = (int)std::min(CHUNK, n - off); a.ctx = pk->nctx;
+      CUDA_TRY(pk->nops->scale_npair(a, s));
+    }
+  } else {   // n^2 Montgomery engine: gather, raise to the plaintext 2^delta, scatter
+    const int ew = sdelta[0] / 32 + 1;
+    std::vector<uint32_t> e(n * (size_t)ew, 0u);
+    for (size_t i = 0; i < n; ++i) e[i * ew + sdelta[i] / 32] = 1u << (sdelta[i] % 32);
+    PHE_TRY(pk->ws_rows.ensure(n * cw));
+    PHE_TRY(pk->ws_rows2.ensure(n * cw));
+    PHE_TRY(pk->ws_d.ensure(n * (size_t)ew));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_d.p, e.data(), e.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(rows_move(d_ct, pk->ws_rows.p, d_idx, (long long)n, cw, 0, s));
+    PHE_TRY(mul_dev_impl(pk, pk->ws_rows.p, n, pk->ws_d.p, ew, n, sdelta[0] + 1, pk->ws_rows2.p, s));
+    CUDA_TRY(rows_move(pk->ws_rows2.p, d_ct, d_idx, (long long)n, cw, 1, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));   // sidx / sdelta are stack-lifetime staging buffers
+  return 0;
+}
+
+int invert_dev_impl(const phe_pubkey* pk, const uint32_t* d_a, size_t count, uint32_t* d_out, cudaStream_t s);
+
+// ct[idx[i]] <- ct[idx[i]]^-1 mod n^2 in place
+int invert_rows_impl(const phe_pubkey* pk, uint32_t* d_ct, size_t rows, const long long* idx, size_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int cw = 2 * pk->n_words;
+  PHE_TRY(upload_idx(pk, idx, n, rows, 0, s));
+  const long long* d_idx = reinterpret_cast<const long long*>(pk->ws_idx.p);
+  for (size_t off = 0; off < n; off += CHUNK) {
+    const size_t c = std::min(CHUNK, n - off);
+    PHE_TRY(pk->ws_rows.ensure(c * cw));
+    PHE_TRY(pk->ws_rows2.ensure(c * cw));
+    CUDA_TRY(rows_move(d_ct, pk->ws_rows.p, d_idx + off, (long long)c, cw, 0, s));
+    PHE_TRY(invert_dev_impl(pk, pk->ws_rows.p, c, pk->ws_rows2.p, s));
+    CUDA_TRY(rows_move(pk->ws_rows2.p, d_ct, d_idx + off, (long long)c, cw, 1, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// out[g] = prod_j ct[g * width + j] mod n^2: a tree of one-product levels, the R^-1 factors repaid at the root
+int segsum_impl(const phe_pubkey* pk, const uint32_t* d_ct, size_t groups, size_t width, uint32_t* d_out, cudaStream_t s) {
+  if (groups == 0) return 0;
+  if (width == 0) return fail("phe_segsum: width must be >= 1");
+  const int cw = 2 * pk->n_words;
+  if (groups > (size_t)1 << 30 || width > (size_t)1 << 30 || groups * ((width + 1) / 2) > (size_t)1 << 31)
+    return fail("phe_segsum: too many rows for one call");
+  if (width == 1) {
+    CUDA_TRY(cudaMemcpyAsync(d_out, d_ct, groups * cw * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  const ShapeOps* o = pk->ops;
+  const size_t half_rows = groups * ((width + 1) / 2);
+  PHE_TRY(pk->ws_tree[0].ensure(half_rows * cw));
+  if (width > 2) PHE_TRY(pk->ws_tree[1].ensure(groups * (((width + 1) / 2 + 1) / 2) * cw));
+  const uint32_t* cur = d_ct;
+  size_t w = width;
+  int flip = 0;
+  while (w > 1) {
+    TreeLevelArgs a{};
+    a.src = cur; a.dst = pk->ws_tree[flip].p; a.nwords = cw; a.groups = (int)groups; a.w = (int)w; a.ctx = pk->ctx;
+    CUDA_TRY(o->tree_level(a, s));
+    cur = pk->ws_tree[flip].p;
+    flip ^= 1;
+    w = w / 2 + (w & 1);
+  }
+  // root: width - 1 products left R^-(width - 1) behind; one more product by R^width mod n^2 repays them
+  const BN Rm = hbn::mod(hbn::shl(BN(1), o->capacity_bits), pk->nsq);
+  std::vector<uint32_t> ww(2, 0u);
+  ww[0] = (uint32_t)(width & 0xffffffffu); ww[1] = (uint32_t)((uint64_t)width >> 32);
+  const BN Rw = hbn::modexp(Rm, BN::from_words(ww.data(), 2), pk->nsq);
+  std::vector<uint32_t> ent(EW(o));
+  to_entry(Rw, o, ent.data());
+  PHE_TRY(pk->ws_ent.ensure(EW(o) + 2 * (size_t)cw));
+  uint32_t* d_ent = pk->ws_ent.p + 2 * (size_t)cw;   // (the first rows of ws_ent serve the broadcast add)
+  d_ent += ((4 - (reinterpret_cast<uintptr_t>(d_ent) / 4) % 4) % 4);   // 16-byte aligned
+  CUDA_TRY(cudaMemcpyAsync(d_ent, ent.data(), ent.size() * 4, cudaMemcpyHostToDevice, s));
+  Modmul1Args f{};
+  f.a = cur; f.b_w = nullptr; f.b_stride = 0; f.b_entry = reinterpret_cast<const double*>(d_ent);
+  f.out = d_out; f.nwords = cw; f.count = (int)groups; f.ctx = pk->ctx;
+  CUDA_TRY(o->modmul1(f, s));
+  CUDA_TRY(cudaStreamSynchronize(s));   // ent is a stack-lifetime staging buffer
   return 0;
 }
 
@@ -911,7 +1061,7 @@ int phe_timing_read(int kind, double* ms_total, unsigned long long* launches) {
 const char* phe_timing_kind_name(int kind) {
   static const char* names[KK_COUNT] = {"k_modmul", "k_powm", "k_dec_prep", "k_dec_tail", "k_encrypt_comb",
                                         "k_encrypt_finish", "k_comb_build", "k_dec_pair", "k_dec_crt", "k_encrypt_npair",
-                                        "k_mul_npair"};
+                                        "k_mul_npair", "k_rows_move"};
   return (kind >= 0 && kind < KK_COUNT) ? names[kind] : nullptr;
 }
 
@@ -960,7 +1110,7 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
 
 void phe_pubkey_destroy(phe_pubkey* pk) {
   if (!pk) return;
-  for (DevBuf* b : {&pk->ws_inv, &pk->d_ctx, &pk->d_nctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
+  for (DevBuf* b : {&pk->ws_idx, &pk->ws_rows, &pk->ws_rows2, &pk->ws_tree[0], &pk->ws_tree[1], &pk->ws_ent, &pk->ws_inv, &pk->d_ctx, &pk->d_nctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
   pk->chain.release();
   delete pk;
 }
@@ -1212,6 +1362,52 @@ int phe_mul_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uint
     PHE_TRY(pk_ensure_device(pk));
   KEY_CHAIN(pk, stream);
   return mul_dev_impl(pk, d_ct, n, d_e, e_words, ne, exp_bits, d_out, (cudaStream_t)stream);
+}
+
+// ---- row operations (device-resident ciphertext matrices; index lists are host arrays) ------------------------------
+int phe_gather_rows_dev(const phe_pubkey* pk, const uint32_t* d_src, size_t src_rows, const long long* idx, size_t n,
+                        uint32_t* d_dst, void* stream) {
+  if (!pk || !d_src || !d_dst || (n && !idx)) return fail("phe_gather_rows_dev: null argument");
+  std::lock_guard<std::mutex> lk(pk->mu);
+  PHE_TRY(pk_ensure_device(pk));
+  KEY_CHAIN(pk, stream);
+  return move_rows_impl(pk, d_src, idx, n, src_rows, d_dst, 0, (cudaStream_t)stream);
+}
+int phe_scatter_rows_dev(const phe_pubkey* pk, const uint32_t* d_src, const long long* idx, size_t n, uint32_t* d_dst,
+                         size_t dst_rows, void* stream) {
+  if (!pk || !d_src || !d_dst || (n && !idx)) return fail("phe_scatter_rows_dev: null argument");
+  std::lock_guard<std::mutex> lk(pk->mu);
+  PHE_TRY(pk_ensure_device(pk));
+  KEY_CHAIN(pk, stream);
+  return move_rows_impl(pk, d_src, idx, n, dst_rows, d_dst, 1, (cudaStream_t)stream);
+}
+int phe_scale_rows_dev(const phe_pubkey* pk, uint32_t* d_ct, size_t rows, const long long* idx, const int* delta, size_t n,
+                       void* stream) {
+  if (!pk || !d_ct || (n && (!idx || !delta))) return fail("phe_scale_rows_dev: null argument");
+  try {
+    std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
+    KEY_CHAIN(pk, stream);
+    return scale_rows_impl(pk, d_ct, rows, idx, delta, n, (cudaStream_t)stream);
+  } catch (const std::exception& e) { return fail(std::string("phe_scale_rows_dev: ") + e.what()); }
+}
+int phe_invert_rows_dev(const phe_pubkey* pk, uint32_t* d_ct, size_t rows, const long long* idx, size_t n, void* stream) {
+  if (!pk || !d_ct || (n && !idx)) return fail("phe_invert_rows_dev: null argument");
+  try {
+    std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
+    KEY_CHAIN(pk, stream);
+    return invert_rows_impl(pk, d_ct, rows, idx, n, (cudaStream_t)stream);
+  } catch (const std::exception& e) { return fail(std::string("phe_invert_rows_dev: ") + e.what()); }
+}
+int phe_segsum_dev(const phe_pubkey* pk, const uint32_t* d_ct, size_t groups, size_t width, uint32_t* d_out, void* stream) {
+  if (!pk || !d_ct || !d_out) return fail("phe_segsum_dev: null argument");
+  try {
+    std::lock_guard<std::mutex> lk(pk->mu);
+    PHE_TRY(pk_ensure_device(pk));
+    KEY_CHAIN(pk, stream);
+    return segsum_impl(pk, d_ct, groups, width, d_out, (cudaStream_t)stream);
+  } catch (const std::exception& e) { return fail(std::string("phe_segsum_dev: ") + e.what()); }
 }
 
 // ---- device memory for callers that keep ciphertexts resident between calls (the pybind11 shim) -----------------

@@ -79,6 +79,61 @@ __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_modmul(const uint32_t* __
   }
 }
 
+// ---- one-product HE add: broadcast second operand, constant second operand -----------------------------------------
+// out[i] = a[i] * b * R^-1 mod N with b = b_w[i * b_stride] (words; b_stride = 0: one row for all) or the constant
+// entry b_entry (global memory, KP doubles).  See item_modmul1.
+struct Modmul1Args {
+  const uint32_t* a; const uint32_t* b_w; size_t b_stride; const double* b_entry;
+  uint32_t* out; int nwords, count;
+  MontCtxArgs ctx;
+};
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_modmul1(Modmul1Args p) {
+  using Env = DevEnv<TPI>;
+  using KS = KShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<KS::KP>(smem, p.ctx.entries, ME_COUNT);
+  GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
+  const int g = threadIdx.x / TPI;
+  for (int base = blockIdx.x * KS::GPB; base < p.count; base += gridDim.x * KS::GPB) {
+    const int want = base + g;
+    const int item = want < p.count ? want : p.count - 1;
+    item_modmul1<L, TPI, Env>(p.a + (size_t)item * p.nwords, p.b_w ? p.b_w + (size_t)item * p.b_stride : nullptr, p.b_entry,
+                              want < p.count ? p.out + (size_t)item * p.nwords : nullptr, p.nwords, smem + ME_N * KS::KP,
+                              p.ctx.n0inv, sm);
+  }
+}
+
+// ---- one level of the add tree of sum / dot / matmul (ipcl_python.py:746-930; __padded_ct :810-827) ---------------
+// src: [groups][w] rows, dst: [groups][wout] rows, wout = half + (w & 1), half = w / 2:
+//   dst[g][j] = src[g][j] * src[g][j + half] * R^-1   (j < half);   dst[g][half] = src[g][2 half]   (w odd: carried over
+// as a product by the Montgomery one, so that every lane group of a warp runs the same product)
+struct TreeLevelArgs {
+  const uint32_t* src; uint32_t* dst;
+  int nwords, groups, w;
+  MontCtxArgs ctx;
+};
+template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k_tree_level(TreeLevelArgs p) {
+  using Env = DevEnv<TPI>;
+  using KS = KShape<L, TPI>;
+  extern __shared__ __align__(16) double smem[];
+  stage_entries<KS::KP>(smem, p.ctx.entries, ME_COUNT);
+  GroupSmem sm = group_smem<L, TPI>(smem, ME_COUNT);
+  const int g = threadIdx.x / TPI;
+  const int half = p.w / 2, wout = half + (p.w & 1);
+  const long long count = (long long)p.groups * wout;
+  for (long long base = (long long)blockIdx.x * KS::GPB; base < count; base += (long long)gridDim.x * KS::GPB) {
+    const long long want = base + g;
+    const long long item = want < count ? want : count - 1;
+    const long long grp = item / wout;
+    const int j = (int)(item - grp * wout);
+    const uint32_t* row = p.src + (size_t)grp * p.w * p.nwords;
+    const bool pass = (j == half);     // the odd element of this level
+    item_modmul1<L, TPI, Env>(row + (size_t)(pass ? 2 * half : j) * p.nwords, pass ? nullptr : row + (size_t)(j + half) * p.nwords,
+                              smem + ME_ONEM * KS::KP, want < count ? p.dst + (size_t)item * p.nwords : nullptr, p.nwords,
+                              smem + ME_N * KS::KP, p.ctx.n0inv, sm);
+  }
+}
+
 // ---- batched modular inverse (Montgomery's trick): one block of `block` consecutive elements per lane group --------
 struct InvArgs {
   const uint32_t* c_w;     // [count][nwords]

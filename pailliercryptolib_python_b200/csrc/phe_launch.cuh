@@ -215,6 +215,31 @@ template <int L, int TPI> struct Launch {
     const int grid = grid_for(k_powm_prog_npair<L, TPI>, NS::smem_bytes(), count, NS::GPB, 1);
     return (size_t)grid * NS::GPB * ((size_t)2 * NS::KP << (PROG_WS - 1)) * 2;
   }
+  static cudaError_t modmul1(const Modmul1Args& p, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const int grid = grid_for(k_modmul1<L, TPI>, smem, p.count, KS::GPB, 1);
+    { TimedLaunch tl_(KK_MODMUL, s);
+    k_modmul1<L, TPI><<<grid, NT, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+  }
+  static cudaError_t tree_level(const TreeLevelArgs& p, cudaStream_t s) {
+    const size_t smem = KS::smem_bytes(ME_COUNT);
+    const long long items = (long long)p.groups * (p.w / 2 + (p.w & 1));
+    const int grid = grid_for(k_tree_level<L, TPI>, smem, (int)std::min<long long>(items, 1 << 30), KS::GPB, 1);
+    { TimedLaunch tl_(KK_MODMUL, s);
+    k_tree_level<L, TPI><<<grid, NT, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+  }
+  static cudaError_t scale_npair(const ScaleNPairArgs& p, cudaStream_t s) {
+    const size_t smem = NS::smem_bytes();
+    const int grid = grid_for(k_scale_npair<L, TPI>, smem, p.count, NS::GPB, 1);
+    { TimedLaunch tl_(KK_MUL_NPAIR, s);
+    k_scale_npair<L, TPI><<<grid, NT, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+  }
   static cudaError_t comb_build_npair(const CombNPairArgs& p0, cudaStream_t s) {
     const size_t smem = NS::smem_bytes();
     cudaFuncSetAttribute(k_comb_bases_npair<L, TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -239,7 +264,7 @@ template <int L, int TPI> struct Launch {
     return ShapeOps{L, TPI, KS::KP, KS::GPB, LW * L * TPI, &modmul, &powm, &powm_tbl_words, &powm_prog, &powm_prog_tbl_words, &dec_prep, &dec_tail, &dec_crt, &inv_block, &resident_groups,
                     &encrypt_comb, &encrypt_finish, &comb_build,
                     &mul_npair, &mul_npair_tbl_words, &encrypt_npair, &comb_build_npair, &powm_prog_npair,
-                    &powm_prog_npair_tbl_words};
+                    &powm_prog_npair_tbl_words, &modmul1, &tree_level, &scale_npair};
   }
 };
 

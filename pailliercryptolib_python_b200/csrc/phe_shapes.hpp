@@ -22,6 +22,9 @@ struct MulNPairArgs;
 struct EncNPairArgs;
 struct CombNPairArgs;
 struct ProgNPairArgs;
+struct Modmul1Args;
+struct TreeLevelArgs;
+struct ScaleNPairArgs;
 
 struct ShapeOps {
   int L, TPI, KP, GPB;   // KP: doubles per padded entry
@@ -48,7 +51,14 @@ struct ShapeOps {
   cudaError_t (*comb_build_npair)(const CombNPairArgs& p, cudaStream_t s);
   cudaError_t (*powm_prog_npair)(const ProgNPairArgs& p, cudaStream_t s);
   size_t (*powm_prog_npair_tbl_words)(int count);
+  // one-product HE adds (broadcast / constant second operand), add-tree levels, exponent alignment by squarings
+  cudaError_t (*modmul1)(const Modmul1Args& p, cudaStream_t s);
+  cudaError_t (*tree_level)(const TreeLevelArgs& p, cudaStream_t s);
+  cudaError_t (*scale_npair)(const ScaleNPairArgs& p, cudaStream_t s);
 };
+// dst[i] = src[idx[i]] (scatter == 0) or dst[idx[i]] = src[i]; rows of `words` u32 words (a multiple of 4)
+cudaError_t rows_move(const uint32_t* src, uint32_t* dst, const long long* idx, long long n, int words, int scatter,
+                      cudaStream_t s);
 
 const ShapeOps* shape_ops(int L, int TPI);   // nullptr if not built
 
@@ -64,7 +74,7 @@ void count_launch();
 
 // Per-kernel-kind device timing (phe_timing_* in the C ABI): when enabled every launch is bracketed by a
 // cudaEvent pair on its own stream.  Off by default (no events recorded).
-enum KernelKind { KK_MODMUL = 0, KK_POWM, KK_DEC_PREP, KK_DEC_TAIL, KK_ENC_COMB, KK_ENC_FINISH, KK_COMB_BUILD, KK_DEC_PAIR, KK_DEC_CRT, KK_ENC_NPAIR, KK_MUL_NPAIR, KK_COUNT };
+enum KernelKind { KK_MODMUL = 0, KK_POWM, KK_DEC_PREP, KK_DEC_TAIL, KK_ENC_COMB, KK_ENC_FINISH, KK_COMB_BUILD, KK_DEC_PAIR, KK_DEC_CRT, KK_ENC_NPAIR, KK_MUL_NPAIR, KK_ROWS, KK_COUNT };
 void timing_begin(int kind, cudaStream_t s);
 void timing_end(int kind, cudaStream_t s);
 struct TimedLaunch {   // RAII: brackets one kernel launch, counts it

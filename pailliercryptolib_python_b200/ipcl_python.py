@@ -7,12 +7,14 @@ What is different underneath (B200-first, not a translation):
     and its exponents as an int64 vector; every operator is a handful of whole-batch calls into libphe_b200.so
     (encrypt / decrypt / modmul / modexp kernels), never a Python loop over ipclBigNumber objects;
   * the fixed-point codec is vectorised (fixedpoint.encode_array / decode_array);
-  * exponent alignment gathers the rows that need scaling, raises them to 2^delta in one batched HE-mul and scatters
-    them back with numpy indexing (reference: ipcl_python.py:528-741, per-element lists);
+  * ciphertext batches stay in HBM from encrypt to decrypt: exponent alignment squares the rows that need scaling in
+    place of a device copy (phe_scale_rows_dev; reference: ipcl_python.py:528-741, per-element lists), matmul gathers
+    its operands by index on the device (phe_gather_rows_dev; :777-808), only exponents -- host metadata -- are looked at
+    on the host;
   * negative plaintext factors still invert the ciphertext first (ipcl_python.py:272-276, 426-441, 470-479) so results
-    are bit-identical to the reference's; the inverses are computed in one batched device call (phe_invert);
-  * sum()/dot()/@ reduce with a log-depth tree of batched HE-adds; sum() works for any length (the reference's passes
-    a list where it needs a ciphertext container, ipcl_python.py:752-755).
+    are bit-identical to the reference's; the rows concerned are inverted on the device (phe_invert_rows_dev);
+  * sum()/dot()/@ reduce with a log-depth tree of one-product HE-adds in one device call (phe_segsum_dev); sum() works
+    for any length (the reference's passes a list where it needs a ciphertext container, ipcl_python.py:752-755).
 """
 from typing import Optional, Tuple, Union
 
@@ -268,30 +270,25 @@ class PaillierEncryptedNumber:
         x_ct, y_ct, expo = self.__align_exponent(self.__ct, self.__expo, other.ciphertext(), other.__expo)
         return self._wrap(x_ct + y_ct, expo)
 
-    def _scale_rows(self, packed: np.ndarray, rows: np.ndarray, deltas: np.ndarray) -> None:
-        """packed[rows] <- packed[rows] ^ (2^delta) mod n^2, one batched HE-mul (the reference multiplies by the
-        plaintext BASE^delta: ipcl_python.py:551-560, 602-606)."""
+    @staticmethod
+    def _scale_rows(ct: ipclCipherText, rows: np.ndarray, deltas: np.ndarray) -> ipclCipherText:
+        """ct with ct[rows] <- ct[rows] ^ (2^delta) mod n^2: delta squarings per row on the device, the batch never
+        leaves HBM (the reference multiplies by the plaintext BASE^delta element by element: ipcl_python.py:551-560,
+        602-606).  Any delta works (the reference's modExp has no exponent-size limit either)."""
         if rows.size == 0:
-            return
-        words = int(deltas.max()) // 32 + 1
-        factors = np.zeros((rows.size, words), dtype=np.uint32)
-        factors[np.arange(rows.size), deltas // 32] = np.uint32(1) << (deltas % 32).astype(np.uint32)
-        sub = ipclCipherText.from_packed(self.public_key.pubkey, np.ascontiguousarray(packed[rows]))
-        packed[rows] = (sub * ipclPlainText.from_packed(factors)).to_packed()
+            return ct
+        return ct.scale_rows(np.ascontiguousarray(rows, dtype=np.int64), np.ascontiguousarray(deltas, dtype=np.int32))
 
     def increase_exponent_to(self, x_ct: ipclCipherText, x_expo, exponent: int) -> ipclCipherText:
         """Raise every element whose exponent is below `exponent` (ipcl_python.py:528-568)."""
         diff = int(exponent) - np.asarray(x_expo, dtype=np.int64)
         rows = np.nonzero(diff > 0)[0]
-        if rows.size == 0:
-            return x_ct
-        packed = x_ct.to_packed()
-        self._scale_rows(packed, rows, diff[rows])
-        return ipclCipherText.from_packed(self.public_key.pubkey, packed)
+        return self._scale_rows(x_ct, rows, diff[rows])
 
     def __align_exponent(self, x_ct, x_expo, y_ct, y_expo):
         """Bring both operands to max(exponent) per element; y may be a single broadcast ciphertext
-        (ipcl_python.py:570-741)."""
+        (ipcl_python.py:570-741).  Row selection happens on the host (exponents are host metadata), the rows
+        themselves are scaled in place of a device copy."""
         x_expo = np.asarray(x_expo, dtype=np.int64)
         y_expo = np.asarray(y_expo, dtype=np.int64)
         count = len(x_ct)
@@ -299,43 +296,39 @@ class PaillierEncryptedNumber:
         out_expo = np.maximum(x_expo, y_bcast)
         x_rows = np.nonzero(x_expo < y_bcast)[0]
         y_rows = np.nonzero(y_bcast < x_expo)[0]
-        if x_rows.size:
-            xp = x_ct.to_packed()
-            self._scale_rows(xp, x_rows, (y_bcast - x_expo)[x_rows])
-            x_ct = ipclCipherText.from_packed(self.public_key.pubkey, xp)
+        x_ct = self._scale_rows(x_ct, x_rows, (y_bcast - x_expo)[x_rows])
         if y_rows.size:
-            yp = y_ct.to_packed()
-            if len(y_ct) == 1 and count > 1:
-                yp = np.repeat(yp, count, axis=0)
-            self._scale_rows(yp, y_rows, (x_expo - y_bcast)[y_rows])
-            y_ct = ipclCipherText.from_packed(self.public_key.pubkey, yp)
+            if len(y_ct) == 1 and count > 1:      # the broadcast operand needs different factors per row: expand it
+                y_ct = y_ct.gather(np.zeros(count, dtype=np.int64))
+            y_ct = self._scale_rows(y_ct, y_rows, (x_expo - y_bcast)[y_rows])
         return x_ct, y_ct, out_expo
 
     # ---- homomorphic multiply by plaintext ---------------------------------------------------------------------------
-    def __invert_rows(self, packed: np.ndarray, rows: np.ndarray) -> None:
-        """packed[rows] <- inverses modulo n^2, one batched device call (Montgomery's trick); the reference calls
-        gmpy2.invert per element (ipcl_python.py:272-276)."""
+    def __invert_rows(self, ct: ipclCipherText, rows: np.ndarray) -> ipclCipherText:
+        """ct with ct[rows] <- inverses modulo n^2, one batched device call (Montgomery's trick on the gathered rows);
+        the reference calls gmpy2.invert per element (ipcl_python.py:272-276)."""
         if rows.size == 0:
-            return
-        sub = ipclCipherText.from_packed(self.public_key.pubkey, np.ascontiguousarray(packed[rows]))
+            return ct
         try:
-            packed[rows] = sub.modinv().to_packed()
+            if rows.size == len(ct):
+                return ct.modinv()
+            return ct.invert_rows(np.ascontiguousarray(rows, dtype=np.int64))
         except RuntimeError:
             # some element shares a factor with n: reproduce the element-wise error of the reference's gmpy2.invert
             nsq = self.public_key.nsquare
+            packed = ct.to_packed()
             vals = _limbs_to_ints(packed[rows])
             try:
                 packed[rows] = _ints_to_limbs([pow(v, -1, nsq) for v in vals], packed.shape[1])
             except ValueError as e:
                 raise ZeroDivisionError("invert() no inverse exists") from e
+            return ipclCipherText.from_packed(self.public_key.pubkey, packed)
 
-    def _mul_encoded(self, packed, pt_limbs: np.ndarray, ct_expo, pt_expo):
+    def _mul_encoded(self, ct: ipclCipherText, pt_limbs: np.ndarray, ct_expo, pt_expo):
         """ct[i] ^ pt[i] with the reference's negative-plaintext rule: if pt >= n - max_int use (ct^-1)^(n - pt) so the
-        exponent stays short (ipcl_python.py:426-441, 470-479).  pt_limbs: [N or 1, n_words].  `packed` is the limb
-        matrix of the ciphertexts (modified in place) or an ipclCipherText, which stays on the device unless some
-        plaintext is negative."""
+        exponent stays short (ipcl_python.py:426-441, 470-479).  pt_limbs: [N or 1, n_words] (host: plaintexts start
+        there).  The ciphertext batch stays on the device: the rows that meet a negative plaintext are inverted there."""
         pk = self.public_key
-        is_ct = isinstance(packed, ipclCipherText)
         n_l = _ints_to_limbs([pk.n], pk.n_words)[0]
         thr = _ints_to_limbs([pk.n - pk.max_int], pk.n_words)[0]
         # lexicographic compare pt >= thr from the top word down
@@ -350,22 +343,19 @@ class PaillierEncryptedNumber:
                 break
         neg = np.nonzero(ge)[0]
         if neg.size:
-            if is_ct:
-                packed, is_ct = packed.to_packed(), False
             pt_limbs = pt_limbs.copy()
             borrow = np.zeros(neg.size, dtype=np.int64)
             for j in range(pk.n_words):
                 v = np.int64(int(n_l[j])) - pt_limbs[neg, j].astype(np.int64) - borrow
                 borrow = (v < 0).astype(np.int64)
                 pt_limbs[neg, j] = (v & 0xFFFFFFFF).astype(np.uint32)
-            if pt_limbs.shape[0] == 1 and packed.shape[0] > 1:
-                self.__invert_rows(packed, np.arange(packed.shape[0]))
+            if pt_limbs.shape[0] == 1 and len(ct) > 1:
+                ct = self.__invert_rows(ct, np.arange(len(ct)))
             else:
-                self.__invert_rows(packed, neg)
+                ct = self.__invert_rows(ct, neg)
         used = pk.n_words
         while used > 1 and not pt_limbs[:, used - 1].any():
             used -= 1
-        ct = packed if is_ct else ipclCipherText.from_packed(pk.pubkey, packed)
         res = ct * ipclPlainText.from_packed(np.ascontiguousarray(pt_limbs[:, :used]))
         return res, np.asarray(ct_expo, dtype=np.int64) + np.asarray(pt_expo, dtype=np.int64)
 
@@ -389,25 +379,13 @@ class PaillierEncryptedNumber:
         return self * (1.0 / other)
 
     # ---- reductions ---------------------------------------------------------------------------------------------------
-    def _tree_sum(self, packed: np.ndarray, groups: int, width: int) -> np.ndarray:
-        """packed: [groups * width, cw] (row-major groups).  Returns [groups, cw]: the HE-sum of every group, by a
-        log-depth tree of batched HE-adds (ipcl_python.py:810-827 does the same with rotate-and-add)."""
-        pk = self.public_key
-        cw = packed.shape[1]
-        cur = packed.reshape(groups, width, cw)
-        while cur.shape[1] > 1:
-            w = cur.shape[1]
-            half = w // 2
-            a = ipclCipherText.from_packed(pk.pubkey, np.ascontiguousarray(cur[:, :half].reshape(-1, cw)))
-            b = ipclCipherText.from_packed(pk.pubkey, np.ascontiguousarray(cur[:, half:2 * half].reshape(-1, cw)))
-            s = (a + b).to_packed().reshape(groups, half, cw)
-            cur = np.concatenate([s, cur[:, 2 * half:]], axis=1) if w % 2 else s
-        return cur.reshape(groups, cw)
-
     def sum(self) -> "PaillierEncryptedNumber":
+        """HE-sum of all elements: exponents aligned to the largest, then a log-depth tree of one-product additions on
+        the device (phe_segsum_dev).  Works for any length; the reference's own sum() passes a list where it needs a
+        ciphertext container (ipcl_python.py:752-755), its working form is the rotate-and-add tree of :810-827."""
         top = int(self.__expo.max())
-        aligned = self.increase_exponent_to(self.__ct, self.__expo, top).to_packed()
-        return self._wrap(self._tree_sum(aligned, 1, len(self)), [top])
+        aligned = self.increase_exponent_to(self.__ct, self.__expo, top)
+        return self._wrap(aligned.segsum(1, len(self)), [top])
 
     def mean(self) -> "PaillierEncryptedNumber":
         return self.sum() / len(self)
@@ -429,14 +407,14 @@ class PaillierEncryptedNumber:
             idx_self = (ii * n + ll).reshape(-1)
             pts = other[ll, jj].reshape(-1) if other.ndim == 2 else other[ll].reshape(-1)
         pt_limbs, pt_expo = encode_array(pts, pk.n, pk.max_int, pk.n_words)
-        prod, expo = self._mul_encoded(self.packed()[idx_self], pt_limbs, self.__expo[idx_self], pt_expo)
+        operands = self.__ct.gather(np.ascontiguousarray(idx_self, dtype=np.int64))       # device gather by the index map
+        prod, expo = self._mul_encoded(operands, pt_limbs, self.__expo[idx_self], pt_expo)
         expo = expo.reshape(m * k, n)
         top = expo.max(axis=1)
-        packed = prod.to_packed()
         delta = (top[:, None] - expo).reshape(-1)
         rows = np.nonzero(delta > 0)[0]
-        self._scale_rows(packed, rows, delta[rows])
-        return self._wrap(self._tree_sum(packed, m * k, n), top)
+        prod = self._scale_rows(prod, rows, delta[rows])
+        return self._wrap(prod.segsum(m * k, n), top)
 
     def __matmul__(self, other) -> "PaillierEncryptedNumber":
         if len(self) % len(other) != 0:

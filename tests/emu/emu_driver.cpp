@@ -65,6 +65,7 @@ template <int TPI> struct EmuEnv {
   static void sync() { if (TPI > 1) t_ex->bar.arrive_and_wait(); }
   static void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
   static void cp_async_wait() {}
+  static void prefetch_l2(const void*, uint32_t) {}
 };
 
 template <int TPI> void run_group(const std::function<void()>& body) {
@@ -103,6 +104,25 @@ int do_modmul(const uint32_t* a, const uint32_t* b, uint32_t* out, int nwords, i
     run_group<TPI>([&] {
       phe::item_modmul<L, TPI, Env>(a + (size_t)i * nwords, b + (size_t)i * nwords, out + (size_t)i * nwords, nwords,
                                     ne.p, n0inv, r2.p, bufs.sm);
+    });
+  }
+  return 0;
+}
+
+// one-product HE add: b as words (b_w) or as a constant entry (b_e)
+template <int L, int TPI>
+int do_modmul1(const uint32_t* a, const uint32_t* b_w, const double* b_e, uint32_t* out, int nwords, int count,
+               const double* n_e, uint64_t n0inv) {
+  using Env = EmuEnv<TPI>;
+  constexpr int KP = phe::Shape<L, TPI>::KP;
+  AlignedCopy ne(n_e, KP);
+  std::vector<double> zero(KP, 0.0);
+  AlignedCopy be(b_e ? b_e : zero.data(), KP);
+  for (int i = 0; i < count; ++i) {
+    Bufs<L, TPI> bufs;
+    run_group<TPI>([&] {
+      phe::item_modmul1<L, TPI, Env>(a + (size_t)i * nwords, b_w ? b_w + (size_t)i * nwords : nullptr, b_e ? be.p : nullptr,
+                                     out + (size_t)i * nwords, nwords, ne.p, n0inv, bufs.sm);
     });
   }
   return 0;
@@ -327,6 +347,27 @@ int do_mul_npair(const uint32_t* c, int chunk_words, const uint32_t* e, int e_wo
   return 0;
 }
 
+// exponent alignment: out = c^(2^delta); every item runs max_delta squarings and keeps the value it had after its own
+template <int L, int TPI>
+int do_scale_npair(const uint32_t* c, int chunk_words, const int* delta, int max_delta, uint32_t* out, int count,
+                   const double* cst_e, uint64_t n0inv, uint64_t d_top) {
+  using Env = EmuEnv<TPI>;
+  constexpr int KP = phe::Shape<L, TPI>::KP;
+  AlignedCopy cst(cst_e, (size_t)phe::NE_COUNT * KP);
+  const int cw = 2 * chunk_words;
+  for (int i = 0; i < count; ++i) {
+    NBufs<L, TPI> bufs;
+    run_group<TPI>([&] {
+      phe::NPairScaleCtl<L, TPI, Env> ctl;
+      ctl.c_w = c + (size_t)i * cw; ctl.chunk_words = chunk_words;
+      ctl.delta = delta[i]; ctl.max_delta = max_delta;
+      ctl.out_w = out + (size_t)i * cw; ctl.out_words = cw; ctl.cst = cst.p; ctl.sm = bufs.sm;
+      phe::npair_run<L, TPI, Env>(ctl, cst.p, n0inv, d_top, bufs.sm);
+    });
+  }
+  return 0;
+}
+
 template <int L, int TPI>
 int do_powm_prog_npair(const uint32_t* c, int chunk_words, int nchunks, const uint32_t* prog, int nprog, uint32_t* out,
                        int out_words, int count, const double* cst_e, uint64_t n0inv, uint64_t d_top) {
@@ -425,6 +466,16 @@ extern "C" {
 int emu_modmul(int shape, const uint32_t* a, const uint32_t* b, uint32_t* out, int nwords, int count,
                const double* n_e, uint64_t n0inv, const double* r2_e) {
   DISPATCH_SHAPE((do_modmul<L, TPI>(a, b, out, nwords, count, n_e, n0inv, r2_e)));
+}
+
+int emu_modmul1(int shape, const uint32_t* a, const uint32_t* b_w, const double* b_e, uint32_t* out, int nwords, int count,
+                const double* n_e, uint64_t n0inv) {
+  DISPATCH_SHAPE((do_modmul1<L, TPI>(a, b_w, b_e, out, nwords, count, n_e, n0inv)));
+}
+
+int emu_scale_npair(int shape, const uint32_t* c, int chunk_words, const int* delta, int max_delta, uint32_t* out, int count,
+                    const double* cst, uint64_t n0inv, uint64_t d_top) {
+  DISPATCH_SHAPE((do_scale_npair<L, TPI>(c, chunk_words, delta, max_delta, out, count, cst, n0inv, d_top)));
 }
 
 int emu_powm(int shape, int win, const uint32_t* base, int base_words, const double* base_mont, const uint32_t* e,

@@ -37,6 +37,63 @@ def test_modmul(emu, L, TPI, bits):
         assert from_words(out) == [x * y % N for x, y in zip(a, b)]
 
 
+@pytest.mark.parametrize("L,TPI,bits", [(20, 2, 2048), (20, 4, 4096), (15, 8, 6144)])
+def test_modmul_one_product(emu, L, TPI, bits):
+    """item_modmul1: a * b * R^-1 with b as words or as a constant entry -- the broadcast add (b = other * R), a level of
+    the add tree (the R^-1 stay in, the root repays them with R^width) and the pass-through by the Montgomery one."""
+    rng = random.Random(bits + 7 * TPI)
+    nw = bits // 32
+    N = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+    mc = mont_consts(N, L, TPI)
+    R, Rinv = mc["R"], pow(mc["R"], -1, N)
+    a = [0, 1, N - 1] + [rng.randrange(N) for _ in range(5)]
+    b = [N - 1, 5, N - 1] + [rng.randrange(N) for _ in range(5)]
+    aw, bw = to_words(a, nw), to_words(b, nw)
+    out = np.zeros_like(aw)
+    assert emu.emu_modmul1(shape_id(L, TPI), P(aw), P(bw), None, P(out), nw, len(a), PD(mc["n"]), U64(mc["n0inv"])) == 0
+    assert from_words(out) == [x * y * Rinv % N for x, y in zip(a, b)]
+    # constant entry: b = R^2 brings a into the Montgomery domain; b = R mod N is the identity
+    assert emu.emu_modmul1(shape_id(L, TPI), P(aw), None, PD(mc["r2"]), P(out), nw, len(a), PD(mc["n"]), U64(mc["n0inv"])) == 0
+    assert from_words(out) == [x * R % N for x in a]
+    assert emu.emu_modmul1(shape_id(L, TPI), P(aw), None, PD(mc["oneM"]), P(out), nw, len(a), PD(mc["n"]), U64(mc["n0inv"])) == 0
+    assert from_words(out) == a
+    # a whole tree in Python on top of the emulated product: 5 leaves, root repaid with R^5
+    leaves = [rng.randrange(N) for _ in range(5)]
+
+    def prod1(x, y=None, entry=None):
+        o = np.zeros((1, nw), dtype=np.uint32)
+        assert emu.emu_modmul1(shape_id(L, TPI), P(to_words([x], nw)), P(to_words([y], nw)) if y is not None else None,
+                               PD(entry) if entry is not None else None, P(o), nw, 1, PD(mc["n"]), U64(mc["n0inv"])) == 0
+        return from_words(o)[0]
+    from emu_util import to_entry
+    l1 = [prod1(leaves[0], leaves[2]), prod1(leaves[1], leaves[3]), prod1(leaves[4], entry=mc["oneM"])]
+    l2 = [prod1(l1[0], l1[1]), prod1(l1[2], entry=mc["oneM"])]
+    root = prod1(l2[0], l2[1])
+    want = 1
+    for v in leaves:
+        want = want * v % N
+    assert prod1(root, entry=to_entry(pow(R, 5, N), L, TPI)) == want
+
+
+@pytest.mark.parametrize("L,TPI,bits", [(20, 1, 1024), (20, 2, 2048), (15, 4, 3072)])
+def test_npair_scale_rows(emu, L, TPI, bits):
+    """NPairScaleCtl: c^(2^delta) by delta squarings; a lane group whose delta is below the batch maximum keeps the value
+    it had after its own delta (exponent alignment, ipcl_python.py:551-560)."""
+    rng = random.Random(bits * 5 + 1)
+    nw = bits // 32
+    n = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+    n2 = n * n
+    nc = npair_consts(n, L, TPI, nw)
+    base = [rng.randrange(n2) for _ in range(4)] + [1, n2 - 1, n + 1]
+    delta = np.array([9, 0, 3, 9, 5, 1, 8], dtype=np.int32)
+    cw = to_words(base, 2 * nw)
+    out = np.zeros_like(cw)
+    rc = emu.emu_scale_npair(shape_id(L, TPI), P(cw), nw, delta.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), 9, P(out),
+                             len(base), PD(nc["cst"]), U64(nc["n0inv"]), U64(nc["d_top"]))
+    assert rc == 0
+    assert from_words(out) == [pow(b, 1 << int(d), n2) for b, d in zip(base, delta)]
+
+
 @pytest.mark.parametrize("L,TPI,bits,win,ebits", [(20, 1, 1024, 5, 300), (20, 2, 2048, 5, 1024), (20, 4, 4096, 3, 53),
                                                    (20, 4, 4096, 1, 7), (20, 2, 2048, 3, 1), (15, 4, 3072, 5, 100)])
 def test_powm_per_item_exponent(emu, L, TPI, bits, win, ebits):

@@ -520,3 +520,102 @@ def test_reference_key_lengths(bits):
     assert capi.array_to_ints(pk.add(ct[:8], ct[8:])) == O.add_batch(pk_o, a, b)
     e = [rng.getrandbits(53) for _ in range(8)]
     assert capi.array_to_ints(pk.mul(ct[:8], capi.ints_to_array(e, 2))) == O.mul_batch(pk_o, a, e)
+
+
+def _dev(arr):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(arr).view(np.int32)).to("cuda:0")
+
+
+def _host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize("engine", ["npair", "n2"])
+def test_row_operations_on_device(key2048, engine, monkeypatch):
+    """phe_gather_rows_dev / phe_scatter_rows_dev / phe_scale_rows_dev / phe_invert_rows_dev / phe_segsum_dev and the
+    one-product broadcast add, against Python ints (both engines for the scaling)."""
+    import torch
+    pk_o, sk_o, pk, sk = key2048
+    if engine == "n2":
+        monkeypatch.setenv("PHE_NO_NPAIR_ENGINE", "1")
+        pk = capi.PubKey(pk_o.n, 2048, djn=True, hs=pk_o.hs)
+    n2 = pk_o.nsquare
+    rng = random.Random(SEED + 40)
+    rows = 37
+    vals = _rand_cts(pk_o, rng, rows)
+    d = _dev(capi.ints_to_array(vals, 128))
+    # gather (with repeats: a broadcast) and scatter
+    idx = [5, 5, 0, 36, 7, 5]
+    g = torch.zeros((len(idx), 128), dtype=torch.int32, device="cuda:0")
+    pk.gather_rows_dev(d.data_ptr(), rows, idx, g.data_ptr())
+    assert capi.array_to_ints(_host(g)) == [vals[i] for i in idx]
+    tgt = d.clone()
+    sidx = [3, 30, 1]
+    pk.scatter_rows_dev(g.data_ptr(), sidx, tgt.data_ptr(), rows)   # first three rows of g
+    want = list(vals)
+    for k, i in enumerate(sidx):
+        want[i] = vals[idx[k]]
+    assert capi.array_to_ints(_host(tgt)) == want
+    with pytest.raises(RuntimeError, match="out of range"):
+        pk.gather_rows_dev(d.data_ptr(), rows, [0, rows], g.data_ptr())
+    # exponent alignment in place: unsorted deltas, zero, and one beyond 32 * n_words bits
+    work = d.clone()
+    sc_idx = [2, 11, 36, 0, 17, 9]
+    deltas = [3, 0, 2100 if engine == "npair" else 70, 53, 1, 53]
+    pk.scale_rows_dev(work.data_ptr(), rows, sc_idx, deltas)
+    want = list(vals)
+    for i, dl in zip(sc_idx, deltas):
+        want[i] = pow(vals[i], 1 << dl, n2)
+    assert capi.array_to_ints(_host(work)) == want
+    with pytest.raises(RuntimeError, match="duplicate"):
+        pk.scale_rows_dev(work.data_ptr(), rows, [1, 1], [1, 2])
+    # inverse of a subset of rows in place
+    work = d.clone()
+    inv_idx = [0, 4, 8, 36, 20]
+    pk.invert_rows_dev(work.data_ptr(), rows, inv_idx)
+    want = list(vals)
+    for i in inv_idx:
+        want[i] = pow(vals[i], -1, n2)
+    assert capi.array_to_ints(_host(work)) == want
+    # add trees: every width up to 9, then a long one; groups > 1
+    for groups, width in [(1, 1), (3, 1), (1, 2), (4, 2), (2, 3), (5, 5), (1, 7), (3, 8), (4, 9), (1, 37)]:
+        use = vals[: groups * width] if groups * width <= rows else [vals[i % rows] for i in range(groups * width)]
+        src = _dev(capi.ints_to_array(use, 128))
+        out = torch.empty((groups, 128), dtype=torch.int32, device="cuda:0")
+        pk.segsum_dev(src.data_ptr(), groups, width, out.data_ptr())
+        want = []
+        for gi in range(groups):
+            acc = 1
+            for v in use[gi * width:(gi + 1) * width]:
+                acc = acc * v % n2
+            want.append(acc)
+        assert capi.array_to_ints(_host(out)) == want, (groups, width)
+    # broadcast add: one product per element
+    out = torch.empty_like(d)
+    pk.add_dev(d.data_ptr(), rows, d[7:8].contiguous().data_ptr(), 1, out.data_ptr())
+    assert capi.array_to_ints(_host(out)) == [v * vals[7] % n2 for v in vals]
+
+
+def test_segsum_large(key2048):
+    """100 000 rows into one sum, and a 64 x 64 block of 64-wide sums, against products of Python ints."""
+    import torch
+    pk_o, sk_o, pk, sk = key2048
+    n2 = pk_o.nsquare
+    rng = random.Random(SEED + 41)
+    base = _rand_cts(pk_o, rng, 64)
+    rows = 100000
+    src = _dev(capi.ints_to_array(base, 128))[torch.arange(rows, device="cuda:0") % 64].contiguous()
+    out = torch.empty((1, 128), dtype=torch.int32, device="cuda:0")
+    pk.segsum_dev(src.data_ptr(), 1, rows, out.data_ptr())
+    want = 1
+    for j, v in enumerate(base):
+        want = want * pow(v, rows // 64 + (1 if j < rows % 64 else 0), n2) % n2
+    assert capi.array_to_ints(_host(out)) == [want]
+    out = torch.empty((64 * 24, 128), dtype=torch.int32, device="cuda:0")
+    pk.segsum_dev(src.data_ptr(), 64 * 24, 64, out.data_ptr())        # every group of 64 = the same 64 values
+    tot = 1
+    for v in base:
+        tot = tot * v % n2
+    got = capi.array_to_ints(_host(out[:3])) + capi.array_to_ints(_host(out[-1:]))
+    assert got == [tot] * 4
