@@ -76,7 +76,11 @@ void phe_pubkey_destroy(phe_pubkey* pk);
  * 20 bits for a 2048-bit key).  Automatic: a 12-bit table at first, promoted to the widest one that fits a quarter of
  * the free device memory (at most 20 bits / 40 GB) once the key has encrypted 32768 elements.  A pinned width takes
  * effect at the next table build (the first obfuscated encrypt, or immediately if the width changes).  The environment
- * variable PHE_COMB_BITS sets the default.  phe_pubkey_comb_bits returns the width in use (0 before a table exists). */
+ * variable PHE_COMB_BITS sets the default.  phe_pubkey_comb_bits returns the width in use (0 before a table exists).
+ * Tables are shared and budgeted across keys: all phe_pubkey objects of one key (same n, hs, randbits, device) use ONE
+ * table per width (a second object neither builds nor holds another copy; the table is freed with its last user), and
+ * the automatic width keeps the tables of all keys on a device within 60 % of its memory (PHE_COMB_BUDGET_GB changes
+ * that), so a process with many keys gets narrower tables for the later ones by rule rather than by running out. */
 int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits);
 int phe_pubkey_comb_bits(const phe_pubkey* pk);
 /* What the table in use costs: its bytes of device memory and the wall time of its build in ms (0, 0 before one exists). */

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -381,6 +382,31 @@ int window_for_bits(int ebits) { return ebits <= 8 ? 1 : (ebits <= 160 ? 3 : 5);
 
 }  // namespace
 
+// Fixed-base comb table of a DJN key in device memory.  Tables are shared: every phe_pubkey object of the same key
+// (same n, hs, randbits, engine, device) and digit width points at ONE table through a process-wide registry, so
+// unpickling a key twice -- or holding it once through the C ABI and once through the Python classes -- does not build
+// or hold the 35 GB twice.  The table lives as long as some key object uses it.
+struct CombTable {
+  DevBuf buf;
+  int wb = 0, nwin = 0, device = 0;
+  double build_ms = 0.0;
+  size_t bytes = 0;
+  ~CombTable() { buf.release(); }
+};
+namespace {
+std::mutex g_comb_mu;
+std::map<std::string, std::weak_ptr<CombTable>> g_comb_reg;
+// bytes of comb tables alive on `device` (caller holds g_comb_mu)
+size_t comb_live_bytes(int device) {
+  size_t tot = 0;
+  for (auto it = g_comb_reg.begin(); it != g_comb_reg.end();) {
+    if (auto t = it->second.lock()) { if (t->device == device) tot += t->bytes; ++it; }
+    else it = g_comb_reg.erase(it);
+  }
+  return tot;
+}
+}  // namespace
+
 struct phe_pubkey {
   int bits = 0, n_words = 0, djn = 0, randbits = 0, device = 0;
   BN n, nsq, hs;
@@ -391,12 +417,11 @@ struct phe_pubkey {
   mutable DevBuf d_nctx;
   std::vector<uint32_t> h_nctx;
   mutable MontCtxArgs ctx{};
-  mutable DevBuf d_ctx, d_comb;
+  mutable DevBuf d_ctx;
   std::vector<uint32_t> h_ctx;    // Montgomery block, uploaded lazily
-  int nwin = 0;
-  mutable int comb_bits = 0;      // digit width of the comb table once built (0: not built yet)
+  mutable std::shared_ptr<CombTable> comb;   // the (shared) fixed-base table once built
   int comb_bits_wanted = 0;       // 0: choose from the free device memory
-  mutable bool comb_ready = false, comb_wide = false;
+  mutable bool comb_wide = false;
   mutable size_t comb_seen = 0;   // elements encrypted so far under the automatic width (promotion counter)
   mutable DevBuf ws_a, ws_b, ws_c, ws_d, ws_r, ws_tbl, ws_inv;  // op workspaces
   mutable DevBuf ws_idx, ws_rows, ws_rows2, ws_tree[2], ws_ent; // row operations (alignment, inverse of rows, add trees)
@@ -404,7 +429,6 @@ struct phe_pubkey {
   std::vector<uint32_t> h_prog_n;
   mutable std::mutex mu;
   mutable StreamChain chain;       // orders the calls that share this key's scratch across streams
-  mutable double comb_build_ms = 0.0;   // wall time of the last comb-table build (phe_pubkey_comb_info)
   mutable bool dev_ready = false;  // device state (Montgomery block, comb table) is built on first compute call
 };
 
@@ -451,62 +475,90 @@ int pk_ensure_device(const phe_pubkey* pk) {
 // 2048-bit key (52 + 2 products, ~0.2 s to build) on an idle 180 GB B200, 2.7 GB at wb = 16 (64 + 2 products, 15 ms).
 // A key starts on a small table (wb = 12: 225 MB, < 1 ms) and is promoted to the wide one once it has encrypted
 // COMB_PROMOTE elements, so that a caller with a handful of values never waits for (or holds) the large table.
-// PHE_COMB_BITS or phe_pubkey_set_comb_bits pin the width.
+// Budget across keys: the automatic width is the widest whose table fits a quarter of the free memory, 40 GB, AND keeps
+// the tables of ALL keys on the device within the comb budget (60 % of the device memory, PHE_COMB_BUDGET_GB to
+// change): a process with many keys gets narrower tables for the later ones by rule, not by allocation failure.
+// PHE_COMB_BITS or phe_pubkey_set_comb_bits pin the width (no budget check then).
 constexpr size_t COMB_PROMOTE = 32768;
+std::string comb_key(const phe_pubkey* pk, int wb) {
+  std::string k;
+  auto put = [&](const void* p, size_t n) { k.append(static_cast<const char*>(p), n); };
+  const int hdr[5] = {pk->device, pk->use_npair ? 1 : 0, pk->randbits, wb, pk->n_words};
+  put(hdr, sizeof(hdr));
+  std::vector<uint32_t> w(2 * (size_t)pk->n_words);
+  pk->n.to_words(w.data(), pk->n_words); put(w.data(), (size_t)pk->n_words * 4);
+  pk->hs.to_words(w.data(), w.size()); put(w.data(), w.size() * 4);
+  return k;
+}
 int pk_ensure_comb(const phe_pubkey* pk, size_t count) {
   if (!pk->djn) return fail("comb table requested for a non-DJN key");
   int wb = pk->comb_bits_wanted;
   if (wb <= 0) { const char* e = getenv("PHE_COMB_BITS"); if (e) wb = atoi(e); }
   const size_t entry_bytes = pk->use_npair ? 2 * EW(pk->nops) * 4 : EW(pk->ops) * 4;
   auto table_bytes = [&](int w) { return (size_t)((pk->randbits + w - 1) / w) * ((size_t)1 << w) * entry_bytes; };
-  if (wb > 0) {
-    if (pk->comb_ready) return 0;
+  std::lock_guard<std::mutex> reg_lock(g_comb_mu);
+  const bool pinned = wb > 0;
+  if (pinned) {
+    if (pk->comb) return 0;
   } else {
     pk->comb_seen += count;
     const bool wide = pk->comb_seen >= COMB_PROMOTE;
-    if (pk->comb_ready && (pk->comb_wide || !wide)) return 0;
+    if (pk->comb && (pk->comb_wide || !wide)) return 0;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    if (pk->comb_ready) free_b += table_bytes(pk->comb_bits);   // the current table is released first
+    size_t budget = total_b / 10 * 6;
+    if (const char* e = getenv("PHE_COMB_BUDGET_GB")) budget = (size_t)(atof(e) * 1073741824.0);
+    size_t live = comb_live_bytes(pk->device);
+    if (pk->comb && pk->comb.use_count() == 1) { free_b += pk->comb->bytes; live -= pk->comb->bytes; }   // released first
     wb = wide ? 20 : 12;
-    while (wb > 8 && (table_bytes(wb) > free_b / 4 || table_bytes(wb) > ((size_t)40 << 30))) wb -= 2;
+    auto shared_already = [&](int w) { auto it = g_comb_reg.find(comb_key(pk, w)); return it != g_comb_reg.end() && !it->second.expired(); };
+    while (wb > 8 && !shared_already(wb) &&
+           (table_bytes(wb) > free_b / 4 || table_bytes(wb) > ((size_t)40 << 30) || live + table_bytes(wb) > budget)) wb -= 2;
     if (wide) pk->comb_wide = true;
-    if (pk->comb_ready && wb <= pk->comb_bits) return 0;
-    if (pk->comb_ready) { CUDA_TRY(cudaDeviceSynchronize()); pk->d_comb.release(); pk->comb_ready = false; }
+    if (pk->comb && wb <= pk->comb->wb) return 0;
+    if (pk->comb) { CUDA_TRY(cudaDeviceSynchronize()); pk->comb.reset(); }
   }
   if (wb < 1) wb = 1;
   if (wb > 22) wb = 22;
-  // an allocation that fails (fragmented or shared device) falls back to narrower tables instead of failing the encrypt
-  while (pk->d_comb.ensure_exact(table_bytes(wb) / 4) != 0) {
-    cudaGetLastError();
-    if (wb <= 8 || pk->comb_bits_wanted > 0) return fail("comb table: out of device memory");
-    wb -= 2;
+  for (;;) {
+    {   // another key object of the same key already holds this table: share it
+      auto it = g_comb_reg.find(comb_key(pk, wb));
+      if (it != g_comb_reg.end()) if (auto t = it->second.lock()) { pk->comb = t; return 0; }
+    }
+    auto t = std::make_shared<CombTable>();
+    // an allocation that fails (fragmented or shared device) falls back to narrower tables instead of failing the encrypt
+    if (t->buf.ensure_exact(table_bytes(wb) / 4) != 0) {
+      cudaGetLastError();
+      if (wb <= 8 || pinned) return fail("comb table: out of device memory");
+      wb -= 2;
+      continue;
+    }
+    const auto t_build0 = std::chrono::steady_clock::now();
+    t->wb = wb; t->nwin = (pk->randbits + wb - 1) / wb; t->device = pk->device; t->bytes = table_bytes(wb);
+    std::vector<uint32_t> hsw(2 * (size_t)pk->n_words);
+    pk->hs.to_words(hsw.data(), hsw.size());
+    DevBuf dhs;
+    PHE_TRY(upload(dhs, hsw));
+    cudaError_t e;
+    if (pk->use_npair) {
+      CombNPairArgs ca{};
+      ca.hs_w = dhs.p; ca.chunk_words = pk->n_words; ca.nwin = t->nwin; ca.wb = wb;
+      ca.comb = reinterpret_cast<double*>(t->buf.p); ca.ctx = pk->nctx;
+      e = pk->nops->comb_build_npair(ca, 0);
+    } else {
+      CombArgs ca{};
+      ca.hs_w = dhs.p; ca.hs_words = 2 * pk->n_words; ca.nwin = t->nwin; ca.wb = wb;
+      ca.comb = reinterpret_cast<double*>(t->buf.p); ca.ctx = pk->ctx;
+      e = pk->ops->comb_build(ca, 0);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    dhs.release();
+    if (e != cudaSuccess) return fail(std::string("comb table build: ") + cudaGetErrorString(e));
+    t->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
+    g_comb_reg[comb_key(pk, wb)] = t;
+    pk->comb = t;
+    return 0;
   }
-  const auto t_build0 = std::chrono::steady_clock::now();
-  pk->comb_bits = wb;
-  const_cast<phe_pubkey*>(pk)->nwin = (pk->randbits + wb - 1) / wb;
-  std::vector<uint32_t> hsw(2 * (size_t)pk->n_words);
-  pk->hs.to_words(hsw.data(), hsw.size());
-  DevBuf dhs;
-  PHE_TRY(upload(dhs, hsw));
-  cudaError_t e;
-  if (pk->use_npair) {
-    CombNPairArgs ca{};
-    ca.hs_w = dhs.p; ca.chunk_words = pk->n_words; ca.nwin = pk->nwin; ca.wb = wb;
-    ca.comb = reinterpret_cast<double*>(pk->d_comb.p); ca.ctx = pk->nctx;
-    e = pk->nops->comb_build_npair(ca, 0);
-  } else {
-    CombArgs ca{};
-    ca.hs_w = dhs.p; ca.hs_words = 2 * pk->n_words; ca.nwin = pk->nwin; ca.wb = wb;
-    ca.comb = reinterpret_cast<double*>(pk->d_comb.p); ca.ctx = pk->ctx;
-    e = pk->ops->comb_build(ca, 0);
-  }
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  dhs.release();
-  if (e != cudaSuccess) return fail(std::string("comb table build: ") + cudaGetErrorString(e));
-  pk->comb_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
-  pk->comb_ready = true;
-  return 0;
 }
 
 int sk_ensure_device(const phe_privkey* sk) {
@@ -570,16 +622,18 @@ int launch_encrypt_comb(const phe_pubkey* pk, const uint32_t* m_w, int m_words, 
     EncNPairArgs a{};
     a.n_peers = n_peers;
     for (int k = 0; k < n_peers; ++k) a.peer_out[k] = peers[k] + peer_row0 * cw;
-    a.m_w = m_w; a.m_words = m_words; a.r_w = r_w; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
+    a.m_w = m_w; a.m_words = m_words; a.r_w = r_w; a.r_words = r_words;
+    a.nwin = pk->comb ? pk->comb->nwin : 0; a.wb = pk->comb ? pk->comb->wb : 0;
     a.out_w = out_w; a.out_words = cw; a.count = count; a.ctx = pk->nctx;
-    a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
+    a.comb = pk->comb ? reinterpret_cast<const double*>(pk->comb->buf.p) : nullptr;
     CUDA_TRY(pk->nops->encrypt_npair(a, s));
     return 0;
   }
   EncCombArgs a{};
-  a.m_w = m_w; a.m_words = m_words; a.r_w = r_w; a.r_words = r_words; a.nwin = pk->nwin; a.wb = pk->comb_bits;
+  a.m_w = m_w; a.m_words = m_words; a.r_w = r_w; a.r_words = r_words;
+  a.nwin = pk->comb ? pk->comb->nwin : 0; a.wb = pk->comb ? pk->comb->wb : 0;
   a.out_w = out_w; a.out_words = cw; a.count = count; a.ctx = pk->ctx;
-  a.comb = reinterpret_cast<const double*>(pk->d_comb.p);
+  a.comb = pk->comb ? reinterpret_cast<const double*>(pk->comb->buf.p) : nullptr;
   CUDA_TRY(pk->ops->encrypt_comb(a, s));
   return 0;
 }
@@ -1110,23 +1164,24 @@ int phe_pubkey_create(const uint32_t* n, int n_words, int bits, int djn, const u
 
 void phe_pubkey_destroy(phe_pubkey* pk) {
   if (!pk) return;
-  for (DevBuf* b : {&pk->ws_idx, &pk->ws_rows, &pk->ws_rows2, &pk->ws_tree[0], &pk->ws_tree[1], &pk->ws_ent, &pk->ws_inv, &pk->d_ctx, &pk->d_nctx, &pk->d_comb, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
+  for (DevBuf* b : {&pk->ws_idx, &pk->ws_rows, &pk->ws_rows2, &pk->ws_tree[0], &pk->ws_tree[1], &pk->ws_ent, &pk->ws_inv, &pk->d_ctx, &pk->d_nctx, &pk->d_prog_n, &pk->ws_r, &pk->ws_a, &pk->ws_b, &pk->ws_c, &pk->ws_d, &pk->ws_tbl}) b->release();
   pk->chain.release();
+  { std::lock_guard<std::mutex> rl(g_comb_mu); pk->comb.reset(); }
   delete pk;
 }
 int phe_pubkey_set_comb_bits(phe_pubkey* pk, int bits) {
   if (!pk) return fail("null");
   if (bits < 0 || bits > 22) return fail("phe_pubkey_set_comb_bits: bits must be in [0, 22] (0 = automatic)");
   std::lock_guard<std::mutex> lk(pk->mu);
-  if (pk->comb_ready && bits != pk->comb_bits) { pk->d_comb.release(); pk->comb_ready = false; }
+  if (pk->comb && bits != pk->comb->wb) { cudaDeviceSynchronize(); std::lock_guard<std::mutex> rl(g_comb_mu); pk->comb.reset(); }
   pk->comb_bits_wanted = bits;
   return 0;
 }
-int phe_pubkey_comb_bits(const phe_pubkey* pk) { return pk ? pk->comb_bits : -1; }
+int phe_pubkey_comb_bits(const phe_pubkey* pk) { return pk ? (pk->comb ? pk->comb->wb : 0) : -1; }
 int phe_pubkey_comb_info(const phe_pubkey* pk, unsigned long long* table_bytes, double* build_ms) {
   if (!pk) return fail("null");
-  if (table_bytes) *table_bytes = pk->comb_ready ? (unsigned long long)pk->d_comb.words * 4ull : 0ull;
-  if (build_ms) *build_ms = pk->comb_ready ? pk->comb_build_ms : 0.0;
+  if (table_bytes) *table_bytes = pk->comb ? (unsigned long long)pk->comb->bytes : 0ull;
+  if (build_ms) *build_ms = pk->comb ? pk->comb->build_ms : 0.0;
   return 0;
 }
 int phe_pubkey_bits(const phe_pubkey* pk) { return pk ? pk->bits : -1; }

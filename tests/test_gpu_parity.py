@@ -619,3 +619,27 @@ def test_segsum_large(key2048):
         tot = tot * v % n2
     got = capi.array_to_ints(_host(out[:3])) + capi.array_to_ints(_host(out[-1:]))
     assert got == [tot] * 4
+
+
+def test_comb_table_is_shared_between_objects_of_one_key(key2048):
+    """Two phe_pubkey objects of the same key use one fixed-base table: the second neither builds nor holds a copy."""
+    pk_o, sk_o, pk, sk = key2048
+    rng = random.Random(SEED + 50)
+    ms = [rng.getrandbits(53) for _ in range(64)]
+    rs = [rng.getrandbits(1024) for _ in ms]
+    m, r = capi.ints_to_array(ms, 64), capi.ints_to_array(rs, 32)
+    a = capi.PubKey(pk_o.n, 2048, djn=True, hs=pk_o.hs)
+    a.set_comb_bits(14)
+    want = a.encrypt(m, r)                                  # builds the 14-bit table (1 + 13 build launches + encrypt)
+    assert a.comb_bits == 14 and a.comb_info[0] > 0
+    b = capi.PubKey(pk_o.n, 2048, djn=True, hs=pk_o.hs)
+    b.set_comb_bits(14)
+    before = capi.kernel_launches()
+    got = b.encrypt(m, r)
+    assert capi.kernel_launches() - before == 1             # the encrypt kernel only: no table build
+    assert np.array_equal(got, want) and b.comb_info == a.comb_info
+    del a                                                   # the table stays alive through b
+    assert np.array_equal(b.encrypt(m, r), want)
+    c = capi.PubKey(pk_o.n, 2048, djn=True, hs=pk_o.hs + 0)  # a different width is a different table
+    c.set_comb_bits(9)
+    assert np.array_equal(c.encrypt(m, r), want) and c.comb_info[0] != b.comb_info[0]
