@@ -136,6 +136,15 @@ int phe_obfuscate(const phe_pubkey* pk, uint32_t* ct_inout, size_t count, const 
  *   ct: count x 2*n_words.  m_out: count x n_words. */
 int phe_decrypt(const phe_privkey* sk, const uint32_t* ct, size_t count, uint32_t* m_out);
 
+/* phe_decrypt followed, on the device, by the classification half of the reference's FixedPointNumber.decode
+ * (bindings/fixedpoint.py:97-115), for callers that decode fixed-point numbers: per element the signed mantissa when it
+ * fits 63 bits and a class byte -- 0: the plaintext m itself is < 2^63 (mantissa = m); 1: n - m < 2^63, a negative value
+ * (mantissa = -(n - m)); 2: neither (mantissa 0; the plaintext words of exactly those rows are written to
+ * m_rows_out[i * n_words ..], a host buffer of count x n_words words, if it is not NULL).  9 bytes per element cross
+ * PCIe instead of 4 n_words, and the host never scans the words.  mant_out: count int64, cls_out: count bytes (host). */
+int phe_decrypt_mantissas(const phe_privkey* sk, const uint32_t* ct, size_t count, long long* mant_out,
+                          unsigned char* cls_out, uint32_t* m_rows_out);
+
 /* ipcl::CipherText::operator+(CipherText) -> raw_add (ipcl_bindings_classes.cpp:318-321):
  *   out[i] = a[i] * b[i] mod n^2; nb is na or 1 (broadcast). */
 int phe_add(const phe_pubkey* pk, const uint32_t* a, size_t na, const uint32_t* b, size_t nb, uint32_t* out);

@@ -22,7 +22,7 @@ SYMBOLS = [
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
     "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_pubkey_comb_info", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_dev_alloc", "phe_dev_free", "phe_copy", "phe_encrypt_dev_multi", "phe_enable_peer_access", "phe_ipc_export", "phe_ipc_open", "phe_ipc_close", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
-    "phe_gather_rows_dev", "phe_scatter_rows_dev", "phe_scale_rows_dev", "phe_invert_rows_dev", "phe_segsum_dev",
+    "phe_decrypt_mantissas", "phe_gather_rows_dev", "phe_scatter_rows_dev", "phe_scale_rows_dev", "phe_invert_rows_dev", "phe_segsum_dev",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
     "phe_product_mix_peak",
 ]
@@ -308,6 +308,18 @@ class PrivKey:
         assert out.shape == (ct.shape[0], self.pk.n_words)
         _check(lib().phe_decrypt(self.h, _p(ct), ctypes.c_size_t(ct.shape[0]), _p(out)), "phe_decrypt")
         return out
+
+    def decrypt_mantissas(self, ct):
+        """(mant int64 [N], cls uint8 [N], rows uint32 [N, n_words]): see phe_decrypt_mantissas; rows is only filled where
+        cls == 2."""
+        ct = np.ascontiguousarray(ct, dtype=np.uint32).reshape(-1, 2 * self.pk.n_words)
+        mant = np.empty(ct.shape[0], dtype=np.int64)
+        cls = np.empty(ct.shape[0], dtype=np.uint8)
+        rows = np.zeros((ct.shape[0], self.pk.n_words), dtype=np.uint32)
+        _check(lib().phe_decrypt_mantissas(self.h, _p(ct), ctypes.c_size_t(ct.shape[0]),
+                                           mant.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+                                           cls.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)), _p(rows)), "phe_decrypt_mantissas")
+        return mant, cls, rows
 
     def decrypt_dev(self, d_ct, count, d_out, stream=0):
         _check(lib().phe_decrypt_dev(self.h, _p(d_ct), ctypes.c_size_t(count), _p(d_out), ctypes.c_void_p(stream)),

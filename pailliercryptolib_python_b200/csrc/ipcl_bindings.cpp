@@ -447,6 +447,24 @@ struct PrivateKey {
   }
   PrivateKey(const PrivateKey&) = delete;
   ~PrivateKey() { phe_privkey_destroy(h); }
+  // decrypt + classification of the plaintexts on the device (phe_decrypt_mantissas): (mantissas, classes, words) as
+  // numpy arrays; `words` is only meaningful in the rows of class 2
+  py::tuple decrypt_mantissas(const CipherText& ct) const {
+    if (cmp(ct.pk->n, pk->n) != 0) throw std::runtime_error("decrypt: public key mismatch");
+    py::array_t<long long> mant((py::ssize_t)ct.count);
+    py::array_t<unsigned char> cls((py::ssize_t)ct.count);
+    py::array_t<uint32_t> rows({(py::ssize_t)ct.count, (py::ssize_t)pk->n_words});
+    long long* mp = mant.mutable_data();
+    unsigned char* cp = cls.mutable_data();
+    uint32_t* rp = rows.mutable_data();
+    int rc;
+    {
+      py::gil_scoped_release nogil;
+      rc = phe_decrypt_mantissas(h, ct.operand(), ct.count, mp, cp, rp);
+    }
+    if (rc) throw_phe("decrypt");
+    return py::make_tuple(mant, cls, rows);
+  }
   PlainText decrypt(const CipherText& ct) const {
     if (cmp(ct.pk->n, pk->n) != 0) throw std::runtime_error("decrypt: public key mismatch");
     Packed out;
@@ -740,6 +758,8 @@ PYBIND11_MODULE(ipcl_bindings, m) {
       .def_property_readonly("public_key", [](const PrivateKey& s) { return s.pk; })
       .def("decrypt", [](const PrivateKey& s, const CipherText& ct) { return s.decrypt(ct); })
       .def("decrypt_tolist", [](const PrivateKey& s, const CipherText& ct) { return s.decrypt(ct).texts(); })
+      .def("decrypt_mantissas", [](const PrivateKey& s, const CipherText& ct) { return s.decrypt_mantissas(ct); },
+           "decrypt and classify on the device: (int64 mantissas, uint8 classes 0 positive / 1 negative / 2 see words, uint32 words)")
       .def(py::pickle(
           [](const PrivateKey& s) { return py::make_tuple(to_bytes(s.pk->n), to_bytes(s.p), to_bytes(s.q), pubkey_state(*s.pk)); },
           [](py::tuple t) {

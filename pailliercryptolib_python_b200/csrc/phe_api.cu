@@ -445,7 +445,7 @@ struct phe_privkey {
   int ebits[2] = {0, 0};
   int hw = 0;  // words of x^2 (= n_words)
   uint64_t n0invs[3] = {0, 0, 0};
-  mutable DevBuf ws_in, ws_out, ws_mont[2], ws_u[2], ws_tbl, ws_sched;
+  mutable DevBuf ws_in, ws_out, ws_mont[2], ws_u[2], ws_tbl, ws_sched, ws_cls, d_n;
   mutable std::mutex mu;
   mutable StreamChain chain;
   mutable bool dev_ready = false;
@@ -1253,7 +1253,7 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
 void phe_privkey_destroy(phe_privkey* sk) {
   if (!sk) return;
   for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->d_pair_mod[0], &sk->d_pair_mod[1], &sk->d_pair_cst[0], &sk->d_pair_cst[1], &sk->d_pair_prog[0], &sk->d_pair_prog[1], &sk->ws_in, &sk->ws_out,
-                    &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl, &sk->ws_sched}) b->release();
+                    &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl, &sk->ws_sched, &sk->ws_cls, &sk->d_n}) b->release();
   sk->chain.release();
   delete sk;
 }
@@ -1575,6 +1575,45 @@ int phe_decrypt(const phe_privkey* sk, const uint32_t* ct, size_t count, uint32_
     CUDA_TRY(cudaMemcpy(m_out, sk->ws_out.p, count * hw * 4, cudaMemcpyDefault));
     return 0;
   } catch (const std::exception& e) { return fail(std::string("phe_decrypt: ") + e.what()); }
+}
+
+// decrypt + the classification half of the fixed-point decode (see include/phe_b200.h)
+int phe_decrypt_mantissas(const phe_privkey* sk, const uint32_t* ct, size_t count, long long* mant_out,
+                          unsigned char* cls_out, uint32_t* m_rows_out) {
+  try {
+    if (!sk || !ct || !mant_out || !cls_out) return fail("phe_decrypt_mantissas: null argument");
+    if (count == 0) return 0;
+    std::lock_guard<std::mutex> lk(sk->mu);
+    PHE_TRY(sk_ensure_device(sk));
+    CUDA_TRY(cudaSetDevice(sk->pk->device));
+    KEY_CHAIN(sk, 0);
+    const int hw = sk->hw, cw = 2 * hw;
+    PHE_TRY(sk->ws_in.ensure(count * cw));
+    PHE_TRY(sk->ws_out.ensure(count * hw));
+    PHE_TRY(sk->ws_cls.ensure(count * 2 + (count + 3) / 4 + 4));     // int64 mantissas, then the class bytes
+    if (!sk->d_n.p) {
+      std::vector<uint32_t> nw(hw);
+      sk->pk->n.to_words(nw.data(), hw);
+      PHE_TRY(upload(sk->d_n, nw));
+    }
+    CUDA_TRY(cudaMemcpyAsync(sk->ws_in.p, ct, count * cw * 4, cudaMemcpyDefault, 0));
+    PHE_TRY(decrypt_dev_impl(sk, sk->ws_in.p, count, sk->ws_out.p, 0));
+    long long* d_mant = reinterpret_cast<long long*>(sk->ws_cls.p);
+    unsigned char* d_cls = reinterpret_cast<unsigned char*>(sk->ws_cls.p + count * 2);
+    CUDA_TRY(classify_plain(sk->ws_out.p, sk->d_n.p, hw, (long long)count, d_mant, d_cls, 0));
+    CUDA_TRY(cudaMemcpyAsync(mant_out, d_mant, count * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpy(cls_out, d_cls, count, cudaMemcpyDeviceToHost));
+    if (m_rows_out) {   // the rows the host has to decode from their words: usually none
+      for (size_t i = 0; i < count; ++i)
+        if (cls_out[i] == 2) {
+          size_t j = i;
+          while (j + 1 < count && cls_out[j + 1] == 2) ++j;         // one copy per run of such rows
+          CUDA_TRY(cudaMemcpy(m_rows_out + i * hw, sk->ws_out.p + i * hw, (j - i + 1) * (size_t)hw * 4, cudaMemcpyDeviceToHost));
+          i = j;
+        }
+    }
+    return 0;
+  } catch (const std::exception& e) { return fail(std::string("phe_decrypt_mantissas: ") + e.what()); }
 }
 
 int phe_add(const phe_pubkey* pk, const uint32_t* a, size_t na, const uint32_t* b, size_t nb, uint32_t* out) {

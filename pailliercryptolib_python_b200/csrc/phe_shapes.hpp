@@ -69,6 +69,9 @@ struct PairOps {
   size_t (*tbl_words)(int count, int slots);   // table scratch (u32 words) for a launch
 };
 const PairOps* pair_ops(int L);   // nullptr if not built
+// per plaintext row: signed 63-bit mantissa and class (0 positive, 1 negative = -(n - m), 2 neither); see pair_shapes.cu
+cudaError_t classify_plain(const uint32_t* m, const uint32_t* n, int nw, long long count, long long* mant, unsigned char* cls,
+                           cudaStream_t s);
 unsigned long long launch_counter();          // kernels launched by this library so far
 void count_launch();
 

@@ -297,6 +297,64 @@ def decode_array(limbs, exponents, n, max_int):
     return out.tolist()
 
 
+def classify_plain(limbs, n):
+    """What phe_decrypt_mantissas computes on the device, in numpy (the CPU tests' stand-in for it): per row the signed
+    mantissa when the plaintext m or n - m fits 63 bits, and the class 0 (positive) / 1 (negative) / 2 (neither)."""
+    limbs = np.ascontiguousarray(limbs, dtype=np.uint32)
+    count, words = limbs.shape
+    n_l = _n_limbs(n, words)
+    mant = np.zeros(count, dtype=np.int64)
+    cls = np.full(count, 2, dtype=np.uint8)
+    hi_zero = ~limbs[:, 2:].any(axis=1) if words > 2 else np.ones(count, dtype=bool)
+    w1 = limbs[:, 1] if words > 1 else np.zeros(count, dtype=np.uint32)
+    pos = hi_zero & (w1 < 0x80000000)
+    mant[pos] = limbs[pos, 0].astype(np.int64) | (w1[pos].astype(np.int64) << 32)
+    cls[pos] = 0
+    d = np.empty_like(limbs)
+    borrow = np.zeros(count, dtype=np.int64)
+    for j in range(words):
+        v = np.int64(int(n_l[j])) - limbs[:, j].astype(np.int64) - borrow
+        borrow = (v < 0).astype(np.int64)
+        d[:, j] = (v & 0xFFFFFFFF).astype(np.uint32)
+    d1 = d[:, 1] if words > 1 else np.zeros(count, dtype=np.uint32)
+    neg = ~pos & (borrow == 0) & (~d[:, 2:].any(axis=1) if words > 2 else True) & (d1 < 0x80000000)
+    mant[neg] = -(d[neg, 0].astype(np.int64) | (d1[neg].astype(np.int64) << 32))
+    cls[neg] = 1
+    return mant, cls
+
+
+def decode_mantissas(mant, cls, rows, exponents, n, max_int):
+    """decode_array for plaintexts that were classified on the device (phe_decrypt_mantissas): mant / cls as above, rows
+    the plaintext words (only read where cls == 2).  Same values and Python types as FixedPointNumber(...).decode()."""
+    mant = np.asarray(mant, dtype=np.int64)
+    cls = np.asarray(cls, dtype=np.uint8)
+    expo = np.asarray(exponents, dtype=np.int64)
+    count = mant.shape[0]
+    fast = (cls < 2) & (np.abs(mant) <= min(max_int, (1 << 63) - 1))
+    as_float = fast & (expo > 0) & (expo < 1100)
+    if as_float.all():      # the usual batch: one multiplication, Python floats straight from tolist()
+        return (mant.astype(np.float64) * np.ldexp(1.0, -expo)).tolist()
+    as_int = fast & (expo == 0)
+    if as_int.all():
+        return mant.tolist()
+    out = np.empty(count, dtype=object)      # object-array assignment stores Python ints / floats, not numpy scalars
+    if as_int.any():
+        out[as_int] = mant[as_int]
+    if as_float.any():
+        out[as_float] = mant[as_float].astype(np.float64) * np.ldexp(1.0, (-expo[as_float]).astype(np.int64))
+    rest = np.nonzero(~(as_int | as_float))[0]
+    if rest.size:
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        words = rows.shape[1]
+        for i in rest:
+            if cls[i] == 2:
+                enc = int.from_bytes(rows[i].tobytes(), "little")
+            else:
+                enc = int(mant[i]) if cls[i] == 0 else n + int(mant[i])
+            out[i] = FixedPointNumber(enc, int(expo[i]), n, max_int).decode()
+    return out.tolist()
+
+
 class FixedPointEndec(object):
     """Array/scalar encoder-decoder with a fixed precision (the reference's class of the same name,
     fixedpoint.py:304-367, minus its dependency on the FATE session tables)."""

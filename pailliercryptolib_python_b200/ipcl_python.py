@@ -28,7 +28,7 @@ from .bindings.ipcl_bindings import (
     ipclPrivateKey,
     ipclPublicKey,
 )
-from .fixedpoint import FixedPointNumber, decode_array, encode_array
+from .fixedpoint import FixedPointNumber, decode_mantissas, encode_array
 
 _NUMBER = (int, float, np.integer, np.floating)
 
@@ -158,8 +158,12 @@ class PaillierPrivateKey:
 
     def decrypt(self, encrypted_number: "PaillierEncryptedNumber"):
         """Decrypt and decode: list of ints/floats, or a single value for a length-1 ciphertext (ipcl_python.py:219-245)."""
-        limbs = self._decrypt_packed(encrypted_number, "PailierPrivateKey.decrypt")
-        vals = decode_array(limbs, encrypted_number.exponent(), self.__n, self.__max_int)
+        if encrypted_number.public_key.n != self.__n:
+            raise ValueError("PailierPrivateKey.decrypt: Public key mismatch")
+        # the plaintexts are classified on the device (sign, 63-bit mantissa): 9 bytes per element come back instead of
+        # 4 n_words, and only rows that are neither small positive nor small negative are decoded from their words
+        mant, cls, rows = self.prikey.decrypt_mantissas(encrypted_number.ciphertext())
+        vals = decode_mantissas(mant, cls, rows, encrypted_number._expo_array(), self.__n, self.__max_int)
         return vals if len(encrypted_number) > 1 else vals[0]
 
 
@@ -211,6 +215,9 @@ class PaillierEncryptedNumber:
         if not 0 <= idx < self.__length:
             raise IndexError("ciphertext: idx out of range")
         return self.__ct[idx]
+
+    def _expo_array(self) -> np.ndarray:
+        return self.__expo
 
     def exponent(self, idx: Optional[int] = None):
         if idx is None:

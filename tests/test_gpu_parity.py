@@ -643,3 +643,26 @@ def test_comb_table_is_shared_between_objects_of_one_key(key2048):
     c = capi.PubKey(pk_o.n, 2048, djn=True, hs=pk_o.hs + 0)  # a different width is a different table
     c.set_comb_bits(9)
     assert np.array_equal(c.encrypt(m, r), want) and c.comb_info[0] != b.comb_info[0]
+
+
+def test_decrypt_mantissas_classification(key2048):
+    """phe_decrypt_mantissas: decrypt + per-row sign / 63-bit mantissa on the device, against the numpy restatement
+    (fixedpoint.classify_plain) and the plaintexts themselves."""
+    from pailliercryptolib_python_b200.fixedpoint import classify_plain
+    pk_o, sk_o, pk, sk = key2048
+    n = pk_o.n
+    rng = random.Random(SEED + 60)
+    ms = [0, 1, (1 << 63) - 1, 1 << 63, n - 1, n - (1 << 63) + 1, n - (1 << 63), n - (1 << 63) - 1, n // 2, n // 3]
+    ms += [rng.getrandbits(53) for _ in range(40)] + [n - rng.getrandbits(60) - 1 for _ in range(40)] + [rng.randrange(n) for _ in range(10)]
+    ct = capi.ints_to_array([1 + m * n for m in ms], 128)        # raw ciphertexts: decrypt gives ms back
+    mant, cls, rows = sk.decrypt_mantissas(ct)
+    want_mant, want_cls = classify_plain(capi.ints_to_array(ms, 64), n)
+    assert np.array_equal(cls, want_cls) and np.array_equal(mant, want_mant)
+    for i, m in enumerate(ms):
+        if cls[i] == 0:
+            assert int(mant[i]) == m
+        elif cls[i] == 1:
+            assert n + int(mant[i]) == m
+        else:
+            assert capi.words_to_int(rows[i]) == m
+    assert sorted(set(cls.tolist())) == [0, 1, 2]
