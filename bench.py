@@ -487,12 +487,51 @@ def _e2e_api(N, n, p, q, hs, world, max_over_ranks, barrier):
     ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
     if not (len(y) == N and isinstance(y[0], float) and np.array_equal(np.asarray(y, dtype=np.float64), x)):
         raise RuntimeError("Python API round trip decrypt(encrypt(x)) != x")
-    return {"value": world * 2.0 * N / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+    ops = _api_ops(pub, pri, ct, x) if world == 1 else None
+    return {"value": world * 2.0 * N / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "ops": ops,
             "ms_each_step_encrypt_decrypt": each,
             "h2d_bytes_per_step": int(N * 2 * 4), "d2h_bytes_per_step": int(N * 64 * 4),
             "api": "PaillierPublicKey.encrypt(float64 ndarray, pageable) -> PaillierPrivateKey.decrypt -> Python floats; "
                    "r drawn by the library; the ciphertext batch stays in HBM between the two calls",
             "round_trip_exact": True}
+
+
+def _api_ops(pub, pri, ct, x):
+    """Wall ms (median of 3, after one warm-up call) of the operators a caller chains between encrypt and decrypt, on the
+    100 000-element batch: they run on the device-resident batch, results checked by decrypting."""
+    N = len(x)
+    rs = np.random.RandomState(3)
+    mixed = (rs.rand(N) - 0.5) * 10.0 ** rs.randint(-4, 5, size=N)       # exponents differ row by row
+    signed = np.where(np.arange(N) % 2 == 0, -2.5, 3.0)
+    ct_m = pub.encrypt(mixed)
+    a64 = pub.encrypt(rs.rand(64 * 64))
+    b64 = rs.rand(64, 64) - 0.5
+    out = {}
+
+    def timed(name, fn):
+        res = fn()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            res = fn()
+            res.ciphertext().wait()                # operators enqueue; wait for the result (nothing is copied)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        out[name] = round(float(np.median(ts)), 2)
+        return res
+
+    s = timed("add_mixed_exponents_ms", lambda: ct + ct_m)
+    p = timed("mul_mixed_sign_ms", lambda: ct * signed)
+    tot = timed("sum_ms", lambda: ct.sum())
+    mm = timed("matmul_64x64_by_64x64_ms", lambda: a64 @ b64)
+    ok = (np.allclose(np.asarray(pri.decrypt(s), dtype=float), x + mixed, rtol=1e-12)
+          and np.allclose(np.asarray(pri.decrypt(p), dtype=float), x * signed)
+          and abs(pri.decrypt(tot) - x.sum()) <= 1e-9 * abs(x.sum())
+          and np.allclose(np.asarray(pri.decrypt(mm), dtype=float).reshape(64, 64), np.asarray(pri.decrypt(a64)).reshape(64, 64) @ b64, rtol=1e-9, atol=1e-12))
+    if not ok:
+        raise RuntimeError("Python API operators: decrypted results differ from numpy")
+    out["count"] = N
+    out["results_checked_by_decrypt"] = True
+    return out
 
 
 def _measured_hbm():

@@ -112,7 +112,11 @@ int phe_keygen(int bits, uint32_t* n_out, uint32_t* p_out, uint32_t* q_out);
  * key's device (unified virtual addressing: the copies inside are cudaMemcpyDefault), so a caller can leave results
  * in HBM between calls; with a device output the call returns once the work is enqueued on the default stream.  The
  * exponents of phe_mul and explicit obfuscator exponents r are read on the host and must be host pointers. */
-int phe_dev_alloc(const phe_pubkey* pk, size_t words, uint32_t** out);   /* cudaMalloc on the key's device */
+/* Device memory on the key's device.  Freed blocks are cached (by device and rounded size, at most 16 GB per process)
+ * and handed out again once everything enqueued on the default stream -- and on the blocking streams it orders with --
+ * before the free has finished; a block must not be freed while work on a NON-BLOCKING stream still uses it (stricter
+ * than cudaFree, which waits for the whole device).  Every block is a whole cudaMalloc allocation (phe_ipc_export). */
+int phe_dev_alloc(const phe_pubkey* pk, size_t words, uint32_t** out);
 int phe_dev_free(uint32_t* p);
 int phe_copy(void* dst, const void* src, size_t bytes);                  /* host or device on either side; synchronous */
 

@@ -824,6 +824,9 @@ PYBIND11_MODULE(ipcl_bindings, m) {
       .def("scale_rows", &ct_scaled, "copy of self with rows idx raised to 2^delta (exponent alignment); device resident")
       .def("invert_rows", &ct_inverted_rows, "copy of self with rows idx inverted modulo n^2; device resident")
       .def("segsum", &ct_segsum, "HE-sum of every run of `width` rows: [groups * width] -> [groups]; device resident")
+      .def("wait", [](const CipherText& s) {   // block until the batch has been computed (results are enqueued, not awaited)
+        if (s.dev && s.count) { uint32_t w; py::gil_scoped_release nogil; if (phe_copy(&w, s.dev, 4)) throw_phe("ipclCipherText.wait"); }
+      })
       .def_property_readonly("on_device", [](const CipherText& s) { return s.on_device(); })
       .def_property_readonly("host_valid", [](const CipherText& s) { return s.host_valid; })
       .def("__add__", [](const CipherText& a, const CipherText& b) { return ct_add(a, b); })

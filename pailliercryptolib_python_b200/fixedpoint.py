@@ -177,6 +177,46 @@ def _sub_from_modulus(n_limbs, mag_lo, mag_hi, rows):
     return out
 
 
+def encode_signed_array(values, max_int):
+    """The vector path of encode_array without the reduction modulo n: (|mantissa| as [N, 2] uint32 limbs, sign flags,
+    exponents), or None when the input needs the scalar codec (object arrays, big Python ints, mixed lists).  The
+    encoding is mantissa mod n, i.e. n - |mantissa| for the flagged rows -- HE mul wants exactly the magnitude and the
+    sign (ipcl_python.py:426-441: a negative plaintext is n - pt with the ciphertext inverted), so building the n_words-wide
+    n - |mantissa| on the host only to subtract it from n again is skipped."""
+    if isinstance(values, np.ndarray):
+        arr = values
+    else:
+        values = list(values)
+        if values and all(type(v) is float or isinstance(v, np.floating) for v in values):
+            arr = np.asarray(values, dtype=np.float64)
+        elif values and all(type(v) is int and -(1 << 63) <= v < (1 << 63) for v in values):
+            arr = np.asarray(values, dtype=np.int64)
+        else:
+            return None
+    if arr.ndim != 1:
+        raise ValueError("encode_array: need a 1-D sequence")
+    if arr.dtype in (np.float64, np.float32, np.float16) and max_int >= (1 << 53):
+        x = arr.astype(np.float64)
+        if not np.isfinite(x).all():
+            raise ValueError("encode_array: non-finite input")
+        x = np.where(np.abs(x) < 1e-200, 0.0, x)
+        mant, ex = np.frexp(x)
+        expo = np.where(x == 0.0, 0, 53 - ex).astype(np.int64)
+        mag = np.abs(np.round(np.ldexp(mant, 53))).astype(np.uint64)
+        neg = (x < 0) & (mag > 0)
+    elif arr.dtype in (np.int64, np.int32, np.int16) and max_int >= (1 << 63):
+        x = arr.astype(np.int64)
+        expo = np.zeros(arr.shape[0], dtype=np.int64)
+        neg = x < 0
+        mag = np.where(neg, -(x + 1), x).astype(np.uint64) + neg.astype(np.uint64)
+    else:
+        return None
+    limbs = np.empty((arr.shape[0], 2), dtype=np.uint32)
+    limbs[:, 0] = (mag & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    limbs[:, 1] = (mag >> np.uint64(32)).astype(np.uint32)
+    return limbs, neg, expo
+
+
 def encode_array(values, n, max_int, words, compact=False):
     """Vectorised FixedPointNumber.encode over a 1-D array: returns (limbs [N, words] uint32, exponents [N] int64).
 

@@ -28,7 +28,7 @@ from .bindings.ipcl_bindings import (
     ipclPrivateKey,
     ipclPublicKey,
 )
-from .fixedpoint import FixedPointNumber, decode_mantissas, encode_array
+from .fixedpoint import FixedPointNumber, decode_mantissas, encode_array, encode_signed_array
 
 _NUMBER = (int, float, np.integer, np.floating)
 
@@ -366,15 +366,29 @@ class PaillierEncryptedNumber:
         res = ct * ipclPlainText.from_packed(np.ascontiguousarray(pt_limbs[:, :used]))
         return res, np.asarray(ct_expo, dtype=np.int64) + np.asarray(pt_expo, dtype=np.int64)
 
-    def __mul__(self, other) -> "PaillierEncryptedNumber":
+    def _mul_plain(self, ct: ipclCipherText, ct_expo, values):
+        """ct * values (a 1-D sequence of len(ct) or 1 plaintext numbers): (result ciphertexts, result exponents)."""
         pk = self.public_key
+        signed = encode_signed_array(values, pk.max_int)
+        if signed is None:      # big Python ints, object arrays: the general path on n_words-wide encodings
+            pt_limbs, pt_expo = encode_array(values, pk.n, pk.max_int, pk.n_words)
+            return self._mul_encoded(ct, pt_limbs, ct_expo, pt_expo)
+        # floats and 64-bit ints: magnitude and sign come straight from the codec -- the rows that meet a negative
+        # plaintext are inverted on the device and raised to |mantissa| (ipcl_python.py:426-441, 470-479)
+        mag, neg, pt_expo = signed
+        rows = np.nonzero(neg)[0]
+        if rows.size:
+            ct = self.__invert_rows(ct, np.arange(len(ct)) if (mag.shape[0] == 1 and len(ct) > 1) else rows)
+        used = 2 if mag[:, 1].any() else 1
+        res = ct * ipclPlainText.from_packed(np.ascontiguousarray(mag[:, :used]))
+        return res, np.asarray(ct_expo, dtype=np.int64) + pt_expo
+
+    def __mul__(self, other) -> "PaillierEncryptedNumber":
         if np.isscalar(other):
-            pt_limbs, pt_expo = encode_array([other], pk.n, pk.max_int, pk.n_words)
-        else:
-            if len(other) != self.__length:
-                raise ValueError("PaillierEncryptedNumber.__mul__: Multiply size mismatch")
-            pt_limbs, pt_expo = encode_array(other, pk.n, pk.max_int, pk.n_words)
-        res, expo = self._mul_encoded(self.__ct, pt_limbs, self.__expo, pt_expo)
+            other = [other]
+        elif len(other) != self.__length:
+            raise ValueError("PaillierEncryptedNumber.__mul__: Multiply size mismatch")
+        res, expo = self._mul_plain(self.__ct, self.__expo, other)
         return self._wrap(res, expo)
 
     def __rmul__(self, other):
@@ -413,9 +427,8 @@ class PaillierEncryptedNumber:
         else:     # self (m x n) @ other (n x k)
             idx_self = (ii * n + ll).reshape(-1)
             pts = other[ll, jj].reshape(-1) if other.ndim == 2 else other[ll].reshape(-1)
-        pt_limbs, pt_expo = encode_array(pts, pk.n, pk.max_int, pk.n_words)
         operands = self.__ct.gather(np.ascontiguousarray(idx_self, dtype=np.int64))       # device gather by the index map
-        prod, expo = self._mul_encoded(operands, pt_limbs, self.__expo[idx_self], pt_expo)
+        prod, expo = self._mul_plain(operands, self.__expo[idx_self], pts)
         expo = expo.reshape(m * k, n)
         top = expo.max(axis=1)
         delta = (top[:, None] - expo).reshape(-1)
