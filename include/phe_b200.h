@@ -154,7 +154,8 @@ int phe_decrypt_mantissas(const phe_privkey* sk, const uint32_t* ct, size_t coun
 int phe_add(const phe_pubkey* pk, const uint32_t* a, size_t na, const uint32_t* b, size_t nb, uint32_t* out);
 
 /* ipcl::CipherText::operator*(PlainText) -> raw_mul -> ipcl::modExp (ipcl_bindings_classes.cpp:324-325):
- *   out[i] = ct[i] ^ e[i] mod n^2; e: ne x e_words (e_words <= n_words), ne is n or 1 (broadcast). */
+ *   out[i] = ct[i] ^ e[i] mod n^2; e: ne x e_words (e_words <= 2 n_words: ipcl::modExp takes exponents beyond n, which
+ *   the reference's exponent alignment produces under small keys), ne is n or 1 (broadcast). */
 int phe_mul(const phe_pubkey* pk, const uint32_t* ct, size_t n, const uint32_t* e, int e_words, size_t ne,
             uint32_t* out);
 

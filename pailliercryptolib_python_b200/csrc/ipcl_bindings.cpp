@@ -508,12 +508,12 @@ std::shared_ptr<CipherText> ct_modinv(const CipherText& a) {
 
 std::shared_ptr<CipherText> ct_mul(const CipherText& a, const PlainText& b) {
   if (b.count != a.count && b.count != 1) throw std::runtime_error("CipherText *: size mismatch");
-  // exponent words: trim to what is used, never more than n_words
+  // exponent words: trim to what is used (the reference's modExp takes any exponent: up to 2 n_words here)
   size_t ew = 1;
   for (size_t i = 0; i < b.count; ++i)
     for (size_t j = b.stride; j-- > ew;)
       if (b.at(i)[j]) { ew = j + 1; break; }
-  if (ew > (size_t)a.pk->n_words) throw std::runtime_error("CipherText *: plaintext larger than n");
+  if (ew > 2 * (size_t)a.pk->n_words) throw std::runtime_error("CipherText *: plaintext larger than n^2");
   const Words e = b.restride(ew, "CipherText *");
   CtOut out(a.pk, a.count);
   int rc;

@@ -1708,7 +1708,9 @@ int phe_mul(const phe_pubkey* pk, const uint32_t* ct, size_t n, const uint32_t* 
   try {
     if (!pk || !ct || !e || !out) return fail("phe_mul: null argument");
     if (ne != n && ne != 1) return fail("phe_mul: size mismatch (exponents must have n or 1 elements)");
-    if (e_words < 1 || e_words > pk->n_words) return fail("phe_mul: e_words out of range");
+    // ipcl::modExp takes exponents of any size (the reference's exponent alignment multiplies by 2^delta, which can
+    // exceed n under small keys: ipcl_python.py:551-560); two key lengths of words are accepted here
+    if (e_words < 1 || e_words > 2 * pk->n_words) return fail("phe_mul: e_words out of range (1 .. 2 n_words)");
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(pk->mu);
     PHE_TRY(pk_ensure_device(pk));

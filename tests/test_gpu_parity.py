@@ -106,7 +106,7 @@ def test_add_and_broadcast(key2048):
         pk.add(capi.ints_to_array(a, 128), capi.ints_to_array(b[:7], 128))
 
 
-@pytest.mark.parametrize("ebits", [1, 7, 53, 160, 700, 2048])
+@pytest.mark.parametrize("ebits", [1, 7, 53, 160, 700, 2048, 2100])
 def test_mul_variable_exponent(key2048, ebits):
     pk_o, sk_o, pk, sk = key2048
     rng = random.Random(SEED + ebits)
