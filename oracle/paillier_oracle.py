@@ -3,13 +3,17 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may import this module.  The product (pailliercryptolib_python_b200) never does.
 
-PARITY STATUS: *parity unpinned* at the ciphertext-bit level.  The reference tree
-(/root/reference) contains no arithmetic: ipcl::PublicKey::encrypt, ipcl::PrivateKey::decrypt,
-ipcl::CipherText::operator+/*, ipcl::modExp and mbx_exp_mb8 live in the un-vendored
-dependencies intel/pailliercryptolib (branch `development`, unpinned; package version 2.0.0,
-/root/reference/lib/ipcl.cmake:6-7, CMakeLists.txt:6) and intel/ipp-crypto, which cannot be
-fetched or built offline, and the reference's own tests hold no golden vectors
-(/root/reference/tests/ipcl_python_test.py:21-66 are tolerance round trips with random keys).
+PARITY STATUS: two halves.
+  * The Python layer (ipcl_python.py: exponent alignment, negative-plaintext rule, matmul index maps, add-tree padding)
+    IS pinned to the reference: oracle/ref_l4.py runs the reference's own ipcl_python.py + fixedpoint.py, unmodified, over
+    a mock of its bindings built on the functions below, and tests/golden/l4_flows.json holds what it produced
+    (tests/golden/make_l4_flows.py).
+  * The arithmetic is *parity unpinned* at the ciphertext-bit level against IPCL itself.  The reference tree
+    (/root/reference) contains no arithmetic: ipcl::PublicKey::encrypt, ipcl::PrivateKey::decrypt,
+    ipcl::CipherText::operator+/*, ipcl::modExp and mbx_exp_mb8 live in the un-vendored dependencies
+    intel/pailliercryptolib (branch `development`, unpinned; package version 2.0.0, /root/reference/lib/ipcl.cmake:6-7,
+    CMakeLists.txt:6) and intel/ipp-crypto, which cannot be fetched or built offline, and the reference's own tests
+    hold no golden vectors (/root/reference/tests/ipcl_python_test.py:21-66 are tolerance round trips with random keys).
 What *is* pinned:
   * every function below has a unique canonical answer in [0, modulus) given its inputs,
     so exact Python-int arithmetic is bit-exact with any correct implementation;
