@@ -229,7 +229,11 @@ PHE_HD void mac_span(uint64_t (&acc)[L], const X& x, double y, uint64_t& hprev, 
 // the emulator and on the GPU -- was built and measured in r02 and is NOT in here: its rows need per-block code next to
 // the general row loop (27 KB loop body, uniform branches between 4-product blocks) and k_dec_pair<20> went from 120.6
 // to 174.9 ms (ncu: no_instruction 1.2 and wait 1.15 stalled warps per issue, 3 % MORE executed instructions).
-// profiles/r02_tri_square_experiment.patch, r02_ncu_k_dec_pair_tri_square_summary.txt.
+// profiles/r02_tri_square_experiment.patch, r02_ncu_k_dec_pair_tri_square_summary.txt.  A lighter form -- X0 = lo + hi B^(L/2),
+// X0^2 = lo (lo + 2 hi B^(L/2)) + hi^2 B^L: full rows for the low half, half rows for the high half, 3/4 of the products,
+// only 4 KB more code -- lost too (139.6 ms; 563 against 459 ms at L = 30): one uniform branch per row is enough to make
+// ptxas reconcile the two paths with register moves (IMAD.MOV 0.33 -> 0.89 per product in the loop) and to cut the
+// scheduling window.  profiles/r02_half_square_experiment.patch.  The row body stays branch-free.
 #ifndef PHE52_U
 #define PHE52_U 4
 #endif
