@@ -233,7 +233,10 @@ PHE_HD void mac_span(uint64_t (&acc)[L], const X& x, double y, uint64_t& hprev, 
 // X0^2 = lo (lo + 2 hi B^(L/2)) + hi^2 B^L: full rows for the low half, half rows for the high half, 3/4 of the products,
 // only 4 KB more code -- lost too (139.6 ms; 563 against 459 ms at L = 30): one uniform branch per row is enough to make
 // ptxas reconcile the two paths with register moves (IMAD.MOV 0.33 -> 0.89 per product in the loop) and to cut the
-// scheduling window.  profiles/r02_half_square_experiment.patch.  The row body stays branch-free.
+// scheduling window.  profiles/r02_half_square_experiment.patch.  With the branch hoisted out -- two row loops, each with a
+// straight-line body (14.3 + 12.1 KB, clean instruction mix) -- it is still 134.5 ms (505 at L = 30): the two loop bodies
+// together no longer stay in the instruction cache while 8 warps are in different passes.
+// profiles/r02_half_square_two_loops_experiment.patch.  ONE branch-free row loop under ~20 KB is what this kernel can afford.
 #ifndef PHE52_U
 #define PHE52_U 4
 #endif
