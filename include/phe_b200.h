@@ -248,6 +248,14 @@ int phe_pubkey_npair_block(const phe_pubkey* pk, int* L_out, int* TPI_out, doubl
  * Returns the program length, 0 if the key does not use the engine, < 0 on error.  Buffers may be NULL. */
 int phe_privkey_pair_block(const phe_privkey* sk, int y, int* L_out, uint64_t* n0inv_out, double* mod_out,
                            double* cst_out, uint32_t* prog_out, int prog_cap);
+/* The same program cut into time slices, as k_dec_pair runs it when a launch has more work units than resident warps
+ * (a unit -- 32 ciphertexts, one modulus -- is then continued segment by segment by whichever warp is free, so the end
+ * of a launch is ragged by one segment instead of one whole exponentiation): segments back to back in prog_out, every
+ * one but the last ending with [PO_TX park, PO_END] and every one but the first starting with [PO_XT park], park = the
+ * table slot after the window table; off_out[k] = start of segment k.  Returns the number of segments (0 if the key
+ * does not use the engine, < 0 on error); *prog_len_out = total length.  Buffers may be NULL to query. */
+int phe_privkey_pair_segments(const phe_privkey* sk, int y, uint32_t* prog_out, int prog_cap, int* off_out, int off_cap,
+                              int* prog_len_out);
 /* Sliding-window program of a shared exponent as executed by k_powm_prog (decrypt: p-1, q-1; classic scheme: n):
  * out[0] = table index of the leading window (0xffff: exponent is zero), out[k>=1] = (squarings << 8) | index into
  * the table of odd powers x^(2 index + 1), index 0xff = no multiplication.  Returns the number of entries (or <0);

@@ -21,7 +21,7 @@ SYMBOLS = [
     "phe_privkey_create", "phe_privkey_destroy", "phe_privkey_get_p", "phe_privkey_get_q", "phe_keygen",
     "phe_encrypt", "phe_obfuscate", "phe_decrypt", "phe_add", "phe_mul", "phe_modexp",
     "phe_encrypt_dev", "phe_decrypt_dev", "phe_add_dev", "phe_mul_dev",
-    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_pubkey_comb_info", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_pubkey_npair_block", "phe_dev_alloc", "phe_dev_free", "phe_copy", "phe_encrypt_dev_multi", "phe_enable_peer_access", "phe_ipc_export", "phe_ipc_open", "phe_ipc_close", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
+    "phe_pubkey_set_comb_bits", "phe_pubkey_comb_bits", "phe_pubkey_comb_info", "phe_host_mont_block", "phe_host_modexp", "phe_host_shape_for_bits", "phe_host_powm_program", "phe_privkey_pair_block", "phe_privkey_pair_segments", "phe_pubkey_npair_block", "phe_dev_alloc", "phe_dev_free", "phe_copy", "phe_encrypt_dev_multi", "phe_enable_peer_access", "phe_ipc_export", "phe_ipc_open", "phe_ipc_close", "phe_chacha20_keystream", "phe_invert", "phe_encrypt_compact",
     "phe_decrypt_mantissas", "phe_gather_rows_dev", "phe_scatter_rows_dev", "phe_scale_rows_dev", "phe_invert_rows_dev", "phe_segsum_dev",
     "phe_timing_enable", "phe_timing_read", "phe_timing_kind_name", "phe_int_pipe_peak", "phe_fp64_pipe_peak",
     "phe_product_mix_peak",
@@ -418,6 +418,21 @@ def pair_block(sk, y):
     dp = ctypes.POINTER(ctypes.c_double)
     lib().phe_privkey_pair_block(sk.h, int(y), None, None, mod.ctypes.data_as(dp), cst.ctypes.data_as(dp), _p(prog), n)
     return {"L": L.value, "n0inv": n0.value, "mod": mod, "cst": cst, "prog": [int(v) for v in prog]}
+
+
+def pair_segments(sk, y):
+    """The pair-engine program of x = p / q cut into the time slices k_dec_pair runs: (prog, offsets), or None
+    (include/phe_b200.h: phe_privkey_pair_segments)."""
+    n = ctypes.c_int()
+    nseg = lib().phe_privkey_pair_segments(sk.h, int(y), None, 0, None, 0, ctypes.byref(n))
+    if nseg < 0:
+        raise RuntimeError(lib().phe_last_error().decode())
+    if nseg == 0:
+        return None
+    prog = np.zeros(n.value, dtype=np.uint32)
+    off = np.zeros(nseg, dtype=np.int32)
+    lib().phe_privkey_pair_segments(sk.h, int(y), _p(prog), n.value, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), nseg, None)
+    return prog, [int(v) for v in off]
 
 
 def host_powm_program(exponent, e_words):

@@ -325,8 +325,62 @@ struct PairBlock {
   uint64_t n0inv = 0;
   std::vector<double> mod;       // [L] x, [L + 1] D
   std::vector<double> cst;       // [PC_COUNT][2][L]
-  std::vector<uint32_t> prog;
+  std::vector<uint32_t> prog;    // the whole program in one piece
+  std::vector<uint32_t> segprog; // the same program cut into time slices (k_dec_pair), segments back to back
+  std::vector<int> segoff;       // start of every segment inside segprog
 };
+
+// Segments a unit of k_dec_pair is time-sliced into when a launch has more units than resident warps (phe_kernels.cuh).
+// 8: the ragged end of a launch is at most 1/8 of an exponentiation; a boundary costs one store + load of the running pair.
+constexpr int PAIR_SEGMENTS = 8;
+static_assert(PAIR_SEGMENTS <= PAIR_MAX_SEG, "DecPairArgs::seg_off is too short");
+
+// Cuts the pair-engine program P into at most `nseg` segments of (nearly) equal cost -- a multiplication is 3 passes, a
+// run of n squarings 2 n (runs are split) -- at points from instruction `zone` on where the only live state is the
+// running pair (X0, X1): before a run of squarings or before the load of a multiplier.  A segment ends with
+// [PO_TX park, PO_END] (the pair goes to table slot `park`), the next one starts with [PO_XT park].
+void split_pair_program(const std::vector<uint32_t>& P, size_t zone, int nseg, uint32_t park, std::vector<uint32_t>* out,
+                        std::vector<int>* off) {
+  auto ins = [](uint32_t op, uint32_t arg) { return op | (arg << 8); };
+  auto cost_of = [](uint32_t w) -> uint64_t {
+    const uint32_t op = w & 0xffu, arg = w >> 8;
+    return op == PO_MUL ? 3u : (op == PO_SQR ? 2ull * arg : 0u);
+  };
+  uint64_t total = 0;
+  for (uint32_t w : P) total += cost_of(w);
+  out->clear(); off->clear();
+  off->push_back(0);
+  uint64_t acc = 0;
+  int k = 1;                                   // next boundary: acc >= k * total / nseg
+  size_t seg_start_cost_marker = 0;            // cost at the start of the current segment (no empty segments)
+  auto target = [&](int kk) { return (total * (uint64_t)kk + nseg - 1) / nseg; };
+  auto cut = [&]() {
+    out->push_back(ins(PO_TX, park)); out->push_back(ins(PO_END, 0));
+    off->push_back((int)out->size());
+    out->push_back(ins(PO_XT, park));
+    seg_start_cost_marker = acc;
+    while (k < nseg && target(k) <= acc) ++k;
+  };
+  for (size_t i = 0; i < P.size(); ++i) {
+    const uint32_t op = P[i] & 0xffu, arg = P[i] >> 8;
+    const bool cuttable = i >= zone && (op == PO_SQR || op == PO_YT || op == PO_YCONST);
+    if (cuttable && k < nseg && acc >= target(k) && acc > seg_start_cost_marker) cut();
+    if (op == PO_SQR && i >= zone) {
+      uint32_t left = arg;
+      while (k < nseg && left > 0 && acc + 2ull * left > target(k)) {   // the boundary falls inside this run
+        const uint64_t need = target(k) > acc ? target(k) - acc : 0;
+        uint32_t a = (uint32_t)((need + 1) / 2);
+        if (a >= left) break;
+        if (a > 0) { out->push_back(ins(PO_SQR, a)); acc += 2ull * a; left -= a; }
+        if (acc > seg_start_cost_marker) cut(); else break;
+      }
+      if (left > 0) { out->push_back(ins(PO_SQR, left)); acc += 2ull * left; }
+    } else {
+      out->push_back(P[i]);
+      acc += cost_of(P[i]);
+    }
+  }
+}
 
 // x: p or q (bits == chunk_bits), hx = h_x, chunk_bits = key bits / 2.  Returns false if no pair shape fits.
 bool build_pair_block(const BN& x, const BN& hx, int chunk_bits, PairBlock* out) {
@@ -368,6 +422,7 @@ bool build_pair_block(const BN& x, const BN& hx, int chunk_bits, PairBlock* out)
   P.push_back(ins(PO_TX, 0)); P.push_back(ins(PO_YX, 0)); P.push_back(ins(PO_SQR, 1)); P.push_back(ins(PO_YX, 0)); P.push_back(ins(PO_XT, 0));
   for (int t = 1; t < TS; ++t) { P.push_back(ins(PO_MUL, 0)); P.push_back(ins(PO_TX, t)); }
   P.push_back(ins(PO_XT, sw[0]));
+  const size_t zone = P.size();   // from here on only the running pair is live between products
   for (size_t i = 1; i < sw.size(); ++i) {
     const uint32_t sq = sw[i] >> 8, idx = sw[i] & 0xffu;
     if (sq) P.push_back(ins(PO_SQR, sq));
@@ -375,6 +430,7 @@ bool build_pair_block(const BN& x, const BN& hx, int chunk_bits, PairBlock* out)
   }
   P.push_back(ins(PO_YCONST, PC_ONE)); P.push_back(ins(PO_MUL, 0)); P.push_back(ins(PO_FINISH, 0));
   P.push_back(ins(PO_YCONST, PC_HR)); P.push_back(ins(PO_MUL, 0)); P.push_back(ins(PO_OUT, 0)); P.push_back(ins(PO_END, 0));
+  split_pair_program(P, zone, PAIR_SEGMENTS, (uint32_t)TS, &out->segprog, &out->segoff);
   return true;
 }
 
@@ -440,7 +496,7 @@ struct phe_privkey {
   // p-adic pair engine (balanced keys): per x = p, q
   bool use_pair = false;
   PairBlock pairb[2];
-  mutable DevBuf d_pair_mod[2], d_pair_cst[2], d_pair_prog[2];
+  mutable DevBuf d_pair_mod[2], d_pair_cst[2], d_pair_prog[2], d_pair_segprog[2];
   mutable MontCtxArgs ctx[2]{};
   int ebits[2] = {0, 0};
   int hw = 0;  // words of x^2 (= n_words)
@@ -584,6 +640,7 @@ int sk_ensure_device(const phe_privkey* sk) {
       std::memcpy(tmp.data(), b.cst.data(), b.cst.size() * 8);
       PHE_TRY(upload(sk->d_pair_cst[y], tmp));
       PHE_TRY(upload(sk->d_pair_prog[y], b.prog));
+      PHE_TRY(upload(sk->d_pair_segprog[y], b.segprog));
     }
   }
   sk->dev_ready = true;
@@ -1023,23 +1080,34 @@ int mul_dev_impl(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uin
   return 0;
 }
 
-// decrypt = two CRT halves m_p, m_q on the pair engine (one lane each) + recombination
+// decrypt = two CRT halves m_p, m_q on the pair engine (one lane each) + recombination.
+// Launches of more units than resident warps run time-sliced (PAIR_SEGMENTS segments per unit, phe_kernels.cuh); the
+// window tables are then per unit (10 KB per ciphertext and modulus at 2048-bit keys), so a launch covers at most
+// PAIR_CHUNK ciphertexts (2.8 GB of tables).  PHE_DEC_SEGMENTS=<n> pins the number of segments (1: whole units).
+constexpr size_t PAIR_CHUNK = 1u << 17;
 int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m, cudaStream_t s) {
   const ShapeOps* o = sk->ops;
   const PairOps* po = pair_ops(sk->pairb[0].L);
   const int hw = sk->hw, cw = 2 * hw, half = hw / 2;
-  const size_t chunk = std::min(count, CHUNK);
+  const size_t chunk = std::min(count, PAIR_CHUNK);
   constexpr int slots = 1 << (PROG_WS - 1);
   for (int y = 0; y < 2; ++y) PHE_TRY(sk->ws_u[y].ensure(chunk * half));
   PHE_TRY(sk->ws_tbl.ensure(po->tbl_words((int)chunk, slots)));
-  PHE_TRY(sk->ws_sched.ensure(1024));
-  for (size_t off = 0; off < count; off += CHUNK) {
-    const int c = (int)std::min(CHUNK, count - off);
+  PHE_TRY(sk->ws_sched.ensure(po->sched_ints((int)chunk)));
+  int want_seg = 0;
+  if (const char* e = getenv("PHE_DEC_SEGMENTS")) want_seg = atoi(e);
+  for (size_t off = 0; off < count; off += PAIR_CHUNK) {
+    const int c = (int)std::min(PAIR_CHUNK, count - off);
     const int L = sk->pairb[0].L;
+    const int units = 2 * ((c + 31) / 32);
+    const int avail = (int)std::min(sk->pairb[0].segoff.size(), sk->pairb[1].segoff.size());
+    const bool sliced = want_seg > 0 ? (want_seg > 1 && avail > 1) : (units > po->warps(c) && avail > 1);
     DecPairArgs a{};
     a.c_w = d_ct + off * cw; a.c_words = cw; a.chunk_words = half; a.out_words = half; a.count = c; a.slots = slots;
+    a.nseg = sliced ? avail : 1;
     for (int y = 0; y < 2; ++y) {
-      a.prog[y] = sk->d_pair_prog[y].p; a.out_w[y] = sk->ws_u[y].p;
+      a.prog[y] = sliced ? sk->d_pair_segprog[y].p : sk->d_pair_prog[y].p; a.out_w[y] = sk->ws_u[y].p;
+      for (int k = 0; k < a.nseg; ++k) a.seg_off[y][k] = sliced ? sk->pairb[y].segoff[k] : 0;
       a.dcon[y] = reinterpret_cast<const double*>(sk->d_pair_mod[y].p) + L;
       a.cst[y] = reinterpret_cast<const double*>(sk->d_pair_cst[y].p);
       a.n0inv[y] = sk->pairb[y].n0inv;
@@ -1252,7 +1320,7 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
 
 void phe_privkey_destroy(phe_privkey* sk) {
   if (!sk) return;
-  for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->d_pair_mod[0], &sk->d_pair_mod[1], &sk->d_pair_cst[0], &sk->d_pair_cst[1], &sk->d_pair_prog[0], &sk->d_pair_prog[1], &sk->ws_in, &sk->ws_out,
+  for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->d_pair_mod[0], &sk->d_pair_mod[1], &sk->d_pair_cst[0], &sk->d_pair_cst[1], &sk->d_pair_prog[0], &sk->d_pair_prog[1], &sk->d_pair_segprog[0], &sk->d_pair_segprog[1], &sk->ws_in, &sk->ws_out,
                     &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl, &sk->ws_sched, &sk->ws_cls, &sk->d_n}) b->release();
   sk->chain.release();
   delete sk;
@@ -1841,6 +1909,23 @@ int phe_privkey_pair_block(const phe_privkey* sk, int y, int* L_out, uint64_t* n
     std::memcpy(prog_out, b.prog.data(), b.prog.size() * 4);
   }
   return (int)b.prog.size();
+}
+
+int phe_privkey_pair_segments(const phe_privkey* sk, int y, uint32_t* prog_out, int prog_cap, int* off_out, int off_cap,
+                              int* prog_len_out) {
+  if (!sk || y < 0 || y > 1) { fail("phe_privkey_pair_segments: bad arguments"); return -1; }
+  if (!sk->use_pair) return 0;
+  const PairBlock& b = sk->pairb[y];
+  if (prog_len_out) *prog_len_out = (int)b.segprog.size();
+  if (prog_out) {
+    if ((int)b.segprog.size() > prog_cap) { fail("phe_privkey_pair_segments: program buffer too small"); return -1; }
+    std::memcpy(prog_out, b.segprog.data(), b.segprog.size() * 4);
+  }
+  if (off_out) {
+    if ((int)b.segoff.size() > off_cap) { fail("phe_privkey_pair_segments: offset buffer too small"); return -1; }
+    std::memcpy(off_out, b.segoff.data(), b.segoff.size() * sizeof(int));
+  }
+  return (int)b.segoff.size();
 }
 
 int phe_chacha20_keystream(const uint32_t key[8], const uint32_t nonce[3], uint32_t counter0, uint32_t* out, size_t words) {

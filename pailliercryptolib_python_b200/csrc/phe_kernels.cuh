@@ -293,26 +293,37 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
 
 // ---- decrypt on the p-adic pair engine: one (ciphertext, modulus) per lane ---------------------------------------
 // Work unit = one warp's worth (32 ciphertexts) of ONE modulus: unit u -> modulus u & 1 (0: p, 1: q), ciphertexts
-// [32 (u >> 1), +32).  Warps pull units from a global counter (there are no shuffles in this kernel, so warps of a CTA
-// may run different numbers of units).  100 000 ciphertexts are 6250 units for 1184 resident warps = 5.28 per warp:
-// CTA-granular loops, or one launch per modulus, pay 6 rounds (tools/tail_probe.py: 2.64 waves cost exactly 3).  Here
-// the first 5 x 1184 units go to whoever asks, and the remaining 330 only to the warps of the FIRST CTA that landed on
-// each SM, i.e. at most one extra unit per SM sub-partition: 11 unit-times per sub-partition instead of 12.
-// The limbs of both moduli travel inside the kernel parameters and are selected into registers once per unit.
+// [32 (u >> 1), +32).  There are no shuffles in this kernel, so warps run independently and pull work from a global
+// counter.  A unit is one sequential 1024-bit exponentiation (~21 ms at 2048-bit keys) and 100 000 ciphertexts are
+// 6250 units for 1184 resident warps = 5.28 per warp: dealt whole, the last round keeps a fraction of the warps busy
+// for a full unit time (r01: 2.64 waves cost 3; r01/r02 with the remainder reserved for one CTA per SM: 5.74 unit
+// times for 5.28 of work, tools/tail_probe.py).  So a unit is TIME-SLICED: the host cuts the program of the exponent
+// into nseg segments of equal cost (phe_api.cu: split_pair_program), every segment ends by parking the running pair
+// (X0, X1) in an extra slot of the unit's window table and the next one starts by reloading it, and the queue holds
+// nseg * units pieces in segment-major order (piece t = segment t / units of unit t % units).  Any warp continues any
+// unit: the window table and the parked pair live in global memory indexed by UNIT (not by resident warp), `done[u]`
+// counts the finished segments of unit u (release / acquire at GPU scope; a piece whose predecessor is still running --
+// only when there are fewer units than a few rounds -- spins on it, and the predecessor is by construction held by a
+// running warp, so the wait is finite).  The end of the launch is then ragged by one SEGMENT instead of one unit.
+// The limbs of both moduli travel inside the kernel parameters and are selected into registers once per piece.
+constexpr int PAIR_MAX_SEG = 16;
 struct DecPairArgs {
   const uint32_t* c_w;       // [count][c_words]
   int c_words, chunk_words;
-  const uint32_t* prog[2];   // pair-engine programs for x = p, q (paillier_items.cuh: PairOp)
+  const uint32_t* prog[2];   // pair-engine programs for x = p, q (paillier_items.cuh: PairOp), all segments back to back
+  int seg_off[2][PAIR_MAX_SEG];   // start of segment s inside prog[y]
+  int nseg;                  // segments per unit (1: the whole program in one piece)
   uint32_t* out_w[2];        // m_p, m_q: [count][out_words]
   int out_words;
   int count;
   const double* dcon[2];     // [L + 1] limbs of D = ceil(R / x) x  (global; staged to shared memory: indexed by row)
   uint64_t n0inv[2];
   const double* cst[2];      // [PC_COUNT][2][L] constant pairs
-  double* tbl;               // [gridDim.x * NT / 32][slots][2][L][32]
+  double* tbl;               // [units][slots + 1][2][L][32]: window table + the parked pair of every unit
   int slots;
-  int* sched;                // zeroed before the launch: [0] phase-1 counter, [1] phase-2 counter, [2 + smid] CTA ranks
+  int* sched;                // zeroed before the launch: [0] piece counter, [PAIR_SCHED_DONE + u] finished segments of unit u
 };
+constexpr int PAIR_SCHED_DONE = 32;
 template <int L> struct ModLimbs { double v[2][L]; };
 
 template <int L> struct PairShape {
@@ -329,19 +340,22 @@ template <int L> struct PairShape {
   static constexpr size_t smem_bytes() { return (size_t)(2 * LE + MOD_DOUBLES + PER_LANE * NTP) * sizeof(double); }
 };
 
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<L>::CTAS) k_dec_pair(const DecPairArgs p, const ModLimbs<L> mod) {
   using PE = DevPairEnv;
   using PS = PairShape<L>;
   extern __shared__ __align__(16) double smem[];
-  __shared__ int s_rank;
   for (int i = threadIdx.x; i < 2 * (L + 1); i += PS::NTP) smem[(i / (L + 1)) * PS::LE + i % (L + 1)] = p.dcon[i / (L + 1)][i % (L + 1)];
   if (PS::MOD_IN_SMEM)
     for (int i = threadIdx.x; i < 2 * L; i += PS::NTP) smem[2 * PS::LE + (i / L) * PS::LE + i % L] = mod.v[i / L][i % L];
-  if (threadIdx.x == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    s_rank = atomicAdd(&p.sched[2 + smid], 1);
-  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, col = threadIdx.x & 31;
   double* wbase = smem + 2 * PS::LE + PS::MOD_DOUBLES + (size_t)warp * PS::PER_LANE * 32 + col;
@@ -351,39 +365,42 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
   sm.y0 = wbase + 2 * L * 32;
   sm.y1 = wbase + 3 * L * 32;
   sm.e = reinterpret_cast<int64_t*>(wbase + 4 * L * 32);
-  double* tbl = p.tbl + ((size_t)blockIdx.x * (PS::NTP / 32) + warp) * ((size_t)p.slots * 2 * L * 32) + col;
 
   const int blocks = (p.count + 31) / 32;
   const int units = 2 * blocks;
-  const int warps = gridDim.x * (PS::NTP / 32);
-  const int rem = units % warps;
-  const int units1 = units - rem;                           // phase 1: a whole number of rounds
-  // phase 2 (the remainder) is reserved for the first CTA of each SM when it fits one unit per such warp
-  const bool phase2 = (s_rank == 0) || (2 * rem > warps);
+  const int total = units * p.nseg;
+  int* const done = p.sched + PAIR_SCHED_DONE;
 #pragma unroll 1
-  for (int phase = 0; phase < 2; ++phase) {
-    if (phase == 1 && !phase2) break;
-#pragma unroll 1
-    for (;;) {
-      int u = 0;
-      if (col == 0) u = atomicAdd(&p.sched[phase], 1);
-      u = __shfl_sync(0xffffffffu, u, 0) + (phase ? units1 : 0);
-      if (u >= (phase ? units : units1)) break;
-      const int y = u & 1;
-      const int want = (u >> 1) * 32 + col;
-      const int item = want < p.count ? want : p.count - 1;
-      if (PS::MOD_IN_SMEM) {
-        item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog[y],
-                             want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words,
-                             smem + 2 * PS::LE + y * PS::LE, smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
-      } else {
-        double n[L];
+  for (;;) {
+    int t = 0;
+    if (col == 0) t = atomicAdd(&p.sched[0], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= total) break;
+    const int seg = t / units, u = t - seg * units;
+    if (seg > 0) {   // the segment before this one has parked the running pair (and, in segment 0, built the table)
+      if (col == 0) while (ld_acquire_gpu(done + u) < seg) __nanosleep(256);
+      __syncwarp();
+    }
+    const int y = u & 1;
+    const int want = (u >> 1) * 32 + col;
+    const int item = want < p.count ? want : p.count - 1;
+    double* tbl = p.tbl + (size_t)u * ((size_t)(p.slots + 1) * 2 * L * 32) + col;
+    const uint32_t* prog = p.prog[y] + p.seg_off[y][seg];
+    if (PS::MOD_IN_SMEM) {
+      item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, prog,
+                           want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words,
+                           smem + 2 * PS::LE + y * PS::LE, smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+    } else {
+      double n[L];
 #pragma unroll
-        for (int j = 0; j < L; ++j) n[j] = y ? mod.v[1][j] : mod.v[0][j];
-        item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, p.prog[y],
-                             want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
-                             smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
-      }
+      for (int j = 0; j < L; ++j) n[j] = y ? mod.v[1][j] : mod.v[0][j];
+      item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, prog,
+                           want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
+                           smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+    }
+    if (seg + 1 < p.nseg) {   // publish: every lane's stores, then the counter
+      __syncwarp();
+      if (col == 0) { __threadfence(); st_release_gpu(done + u, seg + 1); }
     }
   }
 }

@@ -271,27 +271,30 @@ template <int L, int TPI> struct Launch {
 // Launcher of the one-bignum-per-lane pair engine (L = limbs of p, q).
 template <int L> struct PairLaunch {
   static constexpr int NTP = PairShape<L>::NTP;
-  static int grid(int count) {   // both moduli: 2 * ceil(count / 32) warp units, NT / 32 warps per CTA
-    const int units = 2 * ((count + 31) / 32);
-    return grid_for(k_dec_pair<L>, PairShape<L>::smem_bytes(), units, NTP / 32, 1, NTP);
+  static int units_of(int count) { return 2 * ((count + 31) / 32); }   // both moduli: warp units
+  static int grid(int count) {   // NT / 32 warps per CTA
+    return grid_for(k_dec_pair<L>, PairShape<L>::smem_bytes(), units_of(count), NTP / 32, 1, NTP);
   }
-  // mod_p, mod_q: L limbs each (doubles); p.sched: >= 2 + number of SMs ints, zeroed here on the stream
+  // resident warps of a launch over `count` ciphertexts (the host picks the number of segments from it)
+  static int warps(int count) { return grid(count) * (NTP / 32); }
+  // mod_p, mod_q: L limbs each (doubles); p.sched: sched_ints(count) ints, zeroed here on the stream
   static cudaError_t dec_pair(const DecPairArgs& p, const double* mod_p, const double* mod_q, cudaStream_t s) {
     const size_t smem = PairShape<L>::smem_bytes();
     const int g = grid(p.count);
     ModLimbs<L> m;
     for (int i = 0; i < L; ++i) { m.v[0][i] = mod_p[i]; m.v[1][i] = mod_q[i]; }
-    cudaError_t e = cudaMemsetAsync(p.sched, 0, (size_t)(2 + sm_count()) * sizeof(int), s);
+    cudaError_t e = cudaMemsetAsync(p.sched, 0, sched_ints(p.count) * sizeof(int), s);
     if (e != cudaSuccess) return e;
     { TimedLaunch tl_(KK_DEC_PAIR, s);
     k_dec_pair<L><<<g, NTP, smem, s>>>(p, m);
     }
     return cudaGetLastError();
   }
-  static size_t tbl_words(int count, int slots) {   // u32 words
-    return (size_t)grid(count) * (NTP / 32) * slots * 2 * L * 32 * 2;
+  static size_t sched_ints(int count) { return (size_t)PAIR_SCHED_DONE + units_of(count); }
+  static size_t tbl_words(int count, int slots) {   // u32 words: per unit `slots` table entries + the parked pair
+    return (size_t)units_of(count) * (slots + 1) * 2 * L * 32 * 2;
   }
-  static constexpr PairOps ops() { return PairOps{L, &dec_pair, &tbl_words}; }
+  static constexpr PairOps ops() { return PairOps{L, &dec_pair, &tbl_words, &warps, &sched_ints}; }
 };
 
 }  // namespace phe

@@ -67,6 +67,8 @@ struct PairOps {
   int L;
   cudaError_t (*dec_pair)(const DecPairArgs& p, const double* mod_p, const double* mod_q, cudaStream_t s);
   size_t (*tbl_words)(int count, int slots);   // table scratch (u32 words) for a launch
+  int (*warps)(int count);                     // resident warps of that launch
+  size_t (*sched_ints)(int count);             // ints of the scheduler block (piece counter + per-unit progress)
 };
 const PairOps* pair_ops(int L);   // nullptr if not built
 // per plaintext row: signed 63-bit mantissa and class (0 positive, 1 negative = -(n - m), 2 neither); see pair_shapes.cu

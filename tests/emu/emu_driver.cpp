@@ -283,16 +283,22 @@ struct EmuPairEnv {
   static void cp_async_wait() {}
 };
 
+// nseg > 1: the program is the time-sliced one (k_dec_pair); every segment starts on FRESH per-lane state (as when
+// another warp continues the unit), only the unit's table (slots + 1 entries, the last holds the parked pair) persists
 template <int L>
 int do_dec_pair(const uint32_t* c, int c_words, int chunk_words, const uint32_t* prog, uint32_t* out, int out_words,
-                int count, const double* mod, uint64_t n0inv, const double* cst, int slots) {
+                int count, const double* mod, uint64_t n0inv, const double* cst, int slots, int nseg = 1,
+                const int* seg_off = nullptr) {
   std::fesetround(FE_TOWARDZERO);
   for (int i = 0; i < count; ++i) {
-    std::vector<double> xs0(L), x1(L), y0(L), y1(L), tbl((size_t)slots * 2 * L);
-    std::vector<int64_t> e(L + 1);
-    phe::PairSmem<EmuPairEnv> sm{xs0.data(), x1.data(), y0.data(), y1.data(), e.data()};
-    phe::item_dec_pair<L, EmuPairEnv>(c + (size_t)i * c_words, chunk_words, prog, out + (size_t)i * out_words, out_words,
-                                      mod, mod + L, n0inv, cst, tbl.data(), sm);
+    std::vector<double> tbl((size_t)(slots + 1) * 2 * L);
+    for (int s = 0; s < nseg; ++s) {
+      std::vector<double> xs0(L, 7.0), x1(L, 7.0), y0(L, 7.0), y1(L, 7.0);
+      std::vector<int64_t> e(L + 1, 7);
+      phe::PairSmem<EmuPairEnv> sm{xs0.data(), x1.data(), y0.data(), y1.data(), e.data()};
+      phe::item_dec_pair<L, EmuPairEnv>(c + (size_t)i * c_words, chunk_words, prog + (seg_off ? seg_off[s] : 0),
+                                        out + (size_t)i * out_words, out_words, mod, mod + L, n0inv, cst, tbl.data(), sm);
+    }
   }
   std::fesetround(FE_TONEAREST);
   return 0;
@@ -521,6 +527,15 @@ int emu_dec_pair(int L, const uint32_t* c, int c_words, int chunk_words, const u
   if (L == 10) return do_dec_pair<10>(c, c_words, chunk_words, prog, out, out_words, count, mod, n0inv, cst, slots);
   if (L == 20) return do_dec_pair<20>(c, c_words, chunk_words, prog, out, out_words, count, mod, n0inv, cst, slots);
   if (L == 30) return do_dec_pair<30>(c, c_words, chunk_words, prog, out, out_words, count, mod, n0inv, cst, slots);
+  return -1;
+}
+
+int emu_dec_pair_segments(int L, const uint32_t* c, int c_words, int chunk_words, const uint32_t* prog, int nseg,
+                          const int* seg_off, uint32_t* out, int out_words, int count, const double* mod, uint64_t n0inv,
+                          const double* cst, int slots) {
+  if (L == 10) return do_dec_pair<10>(c, c_words, chunk_words, prog, out, out_words, count, mod, n0inv, cst, slots, nseg, seg_off);
+  if (L == 20) return do_dec_pair<20>(c, c_words, chunk_words, prog, out, out_words, count, mod, n0inv, cst, slots, nseg, seg_off);
+  if (L == 30) return do_dec_pair<30>(c, c_words, chunk_words, prog, out, out_words, count, mod, n0inv, cst, slots, nseg, seg_off);
   return -1;
 }
 

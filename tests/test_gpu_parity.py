@@ -93,6 +93,38 @@ def test_decrypt_crt(key2048):
     assert got == O.decrypt_batch(sk_o, cs)
 
 
+@pytest.mark.parametrize("nseg", ["1", "8"])
+def test_decrypt_time_sliced_units(key2048, nseg, monkeypatch):
+    """k_dec_pair continues a unit segment by segment on whichever warp is free (phe_kernels.cuh); PHE_DEC_SEGMENTS pins
+    the number of segments so that a small batch takes the sliced path too.  Ragged batch (last warp unit partly filled),
+    units and non-units, both settings bit-equal to the oracle."""
+    pk_o, sk_o, pk, sk = key2048
+    monkeypatch.setenv("PHE_DEC_SEGMENTS", nseg)
+    rng = random.Random(SEED + 77)
+    ms = [0, 1, pk_o.n - 1] + [rng.randrange(pk_o.n) for _ in range(60)]
+    cs = O.encrypt_batch(pk_o, ms, [rng.getrandbits(1024) for _ in ms])
+    cs += _rand_cts(pk_o, rng, 70) + [0, sk_o.p, pk_o.n, pk_o.nsquare - 1]
+    got = capi.array_to_ints(sk.decrypt(capi.ints_to_array(cs, 128)))
+    assert got[:len(ms)] == ms
+    assert got == O.decrypt_batch(sk_o, cs)
+
+
+def test_decrypt_more_units_than_warps(key2048):
+    """40 000 ciphertexts = 2500 warp units on 1184 resident warps: the automatic choice is the time-sliced launch, pieces
+    of one unit run on different SMs.  Checked by round trip over the whole batch and against the oracle on a sample."""
+    pk_o, sk_o, pk, sk = key2048
+    N = 40000
+    rng = np.random.default_rng(SEED + 78)
+    m = np.zeros((N, 64), dtype=np.uint32)
+    m[:, :2] = rng.integers(0, 1 << 32, size=(N, 2), dtype=np.uint64).astype(np.uint32)
+    r = rng.integers(0, 1 << 32, size=(N, 32), dtype=np.uint64).astype(np.uint32)
+    ct = pk.encrypt(m, r)
+    back = sk.decrypt(ct)
+    assert np.array_equal(back, m)
+    idx = [0, 1, 31, 32, 33, N // 2, N - 33, N - 1]
+    assert capi.array_to_ints(back[idx]) == O.decrypt_batch(sk_o, capi.array_to_ints(ct[idx]))
+
+
 def test_add_and_broadcast(key2048):
     pk_o, sk_o, pk, sk = key2048
     rng = random.Random(SEED + 2)
