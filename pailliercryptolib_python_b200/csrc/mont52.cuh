@@ -236,7 +236,11 @@ PHE_HD void mac_span(uint64_t (&acc)[L], const X& x, double y, uint64_t& hprev, 
 // scheduling window.  profiles/r02_half_square_experiment.patch.  With the branch hoisted out -- two row loops, each with a
 // straight-line body (14.3 + 12.1 KB, clean instruction mix) -- it is still 134.5 ms (505 at L = 30): the two loop bodies
 // together no longer stay in the instruction cache while 8 warps are in different passes.
-// profiles/r02_half_square_two_loops_experiment.patch.  ONE branch-free row loop under ~20 KB is what this kernel can afford.
+// profiles/r02_half_square_two_loops_experiment.patch.  The same two loops at U = 2 and U = 1, where both bodies DO fit
+// (7.5 + 6.4 KB, 3.9 + 3.3 KB): 118.4 / 129.2 ms against 119.6 / 131.7 for the plain square at the same U and 115.5 at
+// U = 4 (profiles/r02_unroll_halfsquare_ab.json) -- every loop back-edge drains the product chains (~50 cycles: U = 2
+// costs 3.5 %, U = 1 14 %), and the half rows then give back 1-2 %, not the 5 % of their product count.
+// ONE branch-free row loop of ~15 KB is what this kernel can afford.
 #ifndef PHE52_U
 #define PHE52_U 4
 #endif

@@ -331,8 +331,9 @@ struct PairBlock {
 };
 
 // Segments a unit of k_dec_pair is time-sliced into when a launch has more units than resident warps (phe_kernels.cuh).
-// 8: the ragged end of a launch is at most 1/8 of an exponentiation; a boundary costs one store + load of the running pair.
-constexpr int PAIR_SEGMENTS = 8;
+// 16: the ragged end of a launch is at most 1/16 of an exponentiation; a boundary costs one store + load of the running
+// pair (measured 4 / 8 / 16 over batch sizes: profiles/r02_dec_sweep_ready_queue.json).
+constexpr int PAIR_SEGMENTS = 16;
 static_assert(PAIR_SEGMENTS <= PAIR_MAX_SEG, "DecPairArgs::seg_off is too short");
 
 // Cuts the pair-engine program P into at most `nseg` segments of (nearly) equal cost -- a multiplication is 3 passes, a
@@ -430,7 +431,9 @@ bool build_pair_block(const BN& x, const BN& hx, int chunk_bits, PairBlock* out)
   }
   P.push_back(ins(PO_YCONST, PC_ONE)); P.push_back(ins(PO_MUL, 0)); P.push_back(ins(PO_FINISH, 0));
   P.push_back(ins(PO_YCONST, PC_HR)); P.push_back(ins(PO_MUL, 0)); P.push_back(ins(PO_OUT, 0)); P.push_back(ins(PO_END, 0));
-  split_pair_program(P, zone, PAIR_SEGMENTS, (uint32_t)TS, &out->segprog, &out->segoff);
+  int nseg = PAIR_SEGMENTS;   // PHE_DEC_SEGMENTS=<2..16> at key creation: another slicing (A/B runs); 1 is handled at launch
+  if (const char* e = getenv("PHE_DEC_SEGMENTS")) { const int v = atoi(e); if (v >= 2 && v <= PAIR_MAX_SEG) nseg = v; }
+  split_pair_program(P, zone, nseg, (uint32_t)TS, &out->segprog, &out->segoff);
   return true;
 }
 
@@ -1083,7 +1086,8 @@ int mul_dev_impl(const phe_pubkey* pk, const uint32_t* d_ct, size_t n, const uin
 // decrypt = two CRT halves m_p, m_q on the pair engine (one lane each) + recombination.
 // Launches of more units than resident warps run time-sliced (PAIR_SEGMENTS segments per unit, phe_kernels.cuh); the
 // window tables are then per unit (10 KB per ciphertext and modulus at 2048-bit keys), so a launch covers at most
-// PAIR_CHUNK ciphertexts (2.8 GB of tables).  PHE_DEC_SEGMENTS=<n> pins the number of segments (1: whole units).
+// PAIR_CHUNK ciphertexts (2.8 GB of tables).  PHE_DEC_SEGMENTS=1 runs whole units, any other value forces the slicing
+// for every batch size (tests; the number of segments itself is fixed when the key is created).
 constexpr size_t PAIR_CHUNK = 1u << 17;
 int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count, uint32_t* d_m, cudaStream_t s) {
   const ShapeOps* o = sk->ops;

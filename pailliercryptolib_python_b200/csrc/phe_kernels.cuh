@@ -299,12 +299,16 @@ template <int L, int TPI> __global__ void __launch_bounds__(NT, MinCtas<L>::V) k
 // for a full unit time (r01: 2.64 waves cost 3; r01/r02 with the remainder reserved for one CTA per SM: 5.74 unit
 // times for 5.28 of work, tools/tail_probe.py).  So a unit is TIME-SLICED: the host cuts the program of the exponent
 // into nseg segments of equal cost (phe_api.cu: split_pair_program), every segment ends by parking the running pair
-// (X0, X1) in an extra slot of the unit's window table and the next one starts by reloading it, and the queue holds
-// nseg * units pieces in segment-major order (piece t = segment t / units of unit t % units).  Any warp continues any
-// unit: the window table and the parked pair live in global memory indexed by UNIT (not by resident warp), `done[u]`
-// counts the finished segments of unit u (release / acquire at GPU scope; a piece whose predecessor is still running --
-// only when there are fewer units than a few rounds -- spins on it, and the predecessor is by construction held by a
-// running warp, so the wait is finite).  The end of the launch is then ragged by one SEGMENT instead of one unit.
+// (X0, X1) in an extra slot of the unit's window table and the next one starts by reloading it.  Any warp continues any
+// unit: the window table and the parked pair live in global memory indexed by UNIT (not by resident warp).  Pieces are
+// dealt from a READY QUEUE: pop number t < units is segment 0 of unit t; a warp that finishes segment s of unit u
+// parks the pair and pushes (s + 1, u) (fence, ticket from `tail`, st.release of the slot); pop number t >= units
+// takes ring slot t - units, spinning (ld.acquire) only while that slot is still empty, i.e. while there is no ready
+// work at all.  That is greedy list scheduling: no warp ever waits for a piece that is merely behind in some fixed
+// order (a static segment-major order with a per-unit progress counter -- the first version -- stalled whole rounds
+// below ~2.3 units per warp: profiles/r02_dec_sweep_static_order.json), pushes = units (nseg - 1) = ring slots, and
+// the slot a waiting pop looks at is filled unless every final segment is already done.  The end of a launch is then
+// ragged by one SEGMENT instead of one unit, whatever the batch size.
 // The limbs of both moduli travel inside the kernel parameters and are selected into registers once per piece.
 constexpr int PAIR_MAX_SEG = 16;
 struct DecPairArgs {
@@ -321,9 +325,9 @@ struct DecPairArgs {
   const double* cst[2];      // [PC_COUNT][2][L] constant pairs
   double* tbl;               // [units][slots + 1][2][L][32]: window table + the parked pair of every unit
   int slots;
-  int* sched;                // zeroed before the launch: [0] piece counter, [PAIR_SCHED_DONE + u] finished segments of unit u
-};
-constexpr int PAIR_SCHED_DONE = 32;
+  int* sched;                // zeroed before the launch: [PAIR_SCHED_HEAD] pops, [PAIR_SCHED_TAIL] pushes, [PAIR_SCHED_RING + k]
+};                           // ring slot k: 1 + segment * units + unit of the k-th piece that became ready after segment 0
+constexpr int PAIR_SCHED_HEAD = 0, PAIR_SCHED_TAIL = 32, PAIR_SCHED_RING = 64;
 template <int L> struct ModLimbs { double v[2][L]; };
 
 template <int L> struct PairShape {
@@ -369,18 +373,22 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
   const int blocks = (p.count + 31) / 32;
   const int units = 2 * blocks;
   const int total = units * p.nseg;
-  int* const done = p.sched + PAIR_SCHED_DONE;
+  int* const ring = p.sched + PAIR_SCHED_RING;
 #pragma unroll 1
   for (;;) {
     int t = 0;
-    if (col == 0) t = atomicAdd(&p.sched[0], 1);
+    if (col == 0) {
+      t = atomicAdd(p.sched + PAIR_SCHED_HEAD, 1);
+      if (t >= units && t < total) {   // a piece some warp has made ready (or is about to)
+        int v;
+        while ((v = ld_acquire_gpu(ring + (t - units))) == 0) __nanosleep(128);
+        t = v - 1;                     // segment * units + unit
+      }
+    }
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= total) break;
+    __syncwarp();                      // the acquire of lane 0 orders the other lanes' loads of the parked pair / table
     const int seg = t / units, u = t - seg * units;
-    if (seg > 0) {   // the segment before this one has parked the running pair (and, in segment 0, built the table)
-      if (col == 0) while (ld_acquire_gpu(done + u) < seg) __nanosleep(256);
-      __syncwarp();
-    }
     const int y = u & 1;
     const int want = (u >> 1) * 32 + col;
     const int item = want < p.count ? want : p.count - 1;
@@ -398,9 +406,13 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
                            want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
                            smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
     }
-    if (seg + 1 < p.nseg) {   // publish: every lane's stores, then the counter
+    if (seg + 1 < p.nseg) {   // publish: every lane's stores, then the ring slot
       __syncwarp();
-      if (col == 0) { __threadfence(); st_release_gpu(done + u, seg + 1); }
+      if (col == 0) {
+        __threadfence();
+        const int k = atomicAdd(p.sched + PAIR_SCHED_TAIL, 1);
+        st_release_gpu(ring + k, 1 + (seg + 1) * units + u);
+      }
     }
   }
 }

@@ -290,7 +290,7 @@ template <int L> struct PairLaunch {
     }
     return cudaGetLastError();
   }
-  static size_t sched_ints(int count) { return (size_t)PAIR_SCHED_DONE + units_of(count); }
+  static size_t sched_ints(int count) { return (size_t)PAIR_SCHED_RING + (size_t)units_of(count) * (PAIR_MAX_SEG - 1); }
   static size_t tbl_words(int count, int slots) {   // u32 words: per unit `slots` table entries + the parked pair
     return (size_t)units_of(count) * (slots + 1) * 2 * L * 32 * 2;
   }

@@ -294,20 +294,21 @@ def test_decrypt_pair_engine(emu, bits, L, shape):
         # the time-sliced form of the same program (k_dec_pair with more units than resident warps): every segment on
         # fresh lane state, only the unit's table and the parked pair carry over
         sprog, soff = capi.pair_segments(csk, y)
-        assert len(soff) == 8 and soff[0] == 0
+        assert len(soff) == 16 and soff[0] == 0
         out2 = np.zeros_like(out)
         offs = np.asarray(soff, dtype=np.int32)
         rc = emu.emu_dec_pair_segments(L, P(cw), bits // 16, half, P(sprog), len(soff), offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
                                        P(out2), half, len(cs), PD(mod), U64(n0.value), PD(cst), 32)
         assert rc == 0
         assert from_words(out2) == want
-        # segments are balanced: passes (3 per multiplication, 2 per squaring) within 2 % of each other
+        # segments are balanced: no segment costs more passes (3 per multiplication, 2 per squaring) than its share,
+        # except that the uncuttable preamble (conversion + window table: 4 + 1 + 31 products = 107 passes) is one piece
         cost = []
         for k in range(len(soff)):
             seg = sprog[soff[k]:(soff[k + 1] if k + 1 < len(soff) else len(sprog))]
             cost.append(sum(3 if (w & 0xff) == 7 else (2 * (int(w) >> 8) if (w & 0xff) == 8 else 0) for w in seg))
         assert sum(cost) == sum(3 if (w & 0xff) == 7 else (2 * (w >> 8) if (w & 0xff) == 8 else 0) for w in prog[:n])
-        assert max(cost) - min(cost) <= max(8, 0.02 * max(cost)), cost
+        assert max(cost) <= max(107, sum(cost) / len(cost)) + 8 and min(cost) > 0, cost
     cst, n0 = _dec_consts(sk, *shape)
     mo = np.zeros((len(cs), hw), dtype=np.uint32)
     assert emu.emu_dec_crt(shape_id(*shape), P(halves[0]), P(halves[1]), half, P(mo), hw, len(cs), PD(cst), P64(n0)) == 0

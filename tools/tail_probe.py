@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """How much of k_dec_pair's time at N = 100 000 is the partial last wave?  One wave is 296 CTAs x 128 lanes = 37 888
-ciphertexts per launch (one launch per modulus): 100 000 is 2.64 waves, 113 664 exactly 3.  Prints one JSON line."""
+ciphertexts per modulus: 100 000 is 2.64 waves, 113 664 exactly 3.  Prints one JSON line.
+    python tools/tail_probe.py [N,N,...]        PHE_DEC_SEGMENTS=1: whole work units instead of time-sliced ones"""
 import json, os, sys
 import numpy as np
 import torch
@@ -15,7 +16,8 @@ sk = capi.PrivKey(pk, p, q)
 dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream().cuda_stream
 out = {}
-for N in (37888, 75776, 100000, 113664):
+sizes = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [37888, 75776, 100000, 113664]
+for i, N in enumerate(sizes):
     m_np, r_np = make_workload(N, 5)
     m = torch.from_numpy(m_np.view(np.int32)).to(dev)
     r = torch.from_numpy(r_np.view(np.int32)).to(dev)
@@ -32,5 +34,5 @@ for N in (37888, 75776, 100000, 113664):
     capi.timing_enable(False)
     assert torch.equal(res, m)
     ms = t["k_dec_pair"][0] / 2
-    out[str(N)] = {"waves_per_launch": N / 37888.0, "k_dec_pair_ms": ms, "decrypt_per_s": N / (ms * 1e-3)}
+    out["%d:%d" % (i, N)] = {"waves_per_launch": N / 37888.0, "k_dec_pair_ms": ms, "decrypt_per_s": N / (ms * 1e-3)}
 print(json.dumps(out))
