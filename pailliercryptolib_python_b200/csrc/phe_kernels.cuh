@@ -406,6 +406,10 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
                            want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
                            smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
     }
+    // (k_dec_pair<30> spills 448 B here.  Keeping only the piece number across the exponentiation and deriving (segment,
+    // unit) again afterwards brings that to 376 B with a cleaner-looking row loop -- and 481 instead of 458 ms per 100 000
+    // at 3072-bit keys; the same spelling at L = 20 makes ptxas re-derive shared-memory addresses inside the row loop.
+    // Measured r02, not kept.)
     if (seg + 1 < p.nseg) {   // publish: every lane's stores, then the ring slot
       __syncwarp();
       if (col == 0) {
