@@ -512,6 +512,10 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
   for (int j = 0; j < L; ++j) acc[j] += bias_of(2 * (j + 1), 2 * j);
   if (e_out) e_out[L * ST] = (int64_t)int_of(dcon[L]);
   if (e_in) acc[0] += (uint64_t)e_in[L * ST];            // top limb of D
+  // (This 3 L-deep chain is hidden by the other warp of the scheduler: a one-step parallel carry -- r[j] = low52(acc[j])
+  // + (acc[j-1] >> 52), sequential fallback only when some r[j] leaves [0, 2^52), probability ~2^-39 per limb -- is
+  // bit-exact and SLOWER, 116.7-117.2 against 115.6 ms for k_dec_pair<20> at 100 000: the kernel is dispatch-bound and
+  // the detection costs 10 more instructions per pass.  r02, gpurun_out/r02_carry*.json; not kept.)
   int64_t c = 0;                                            // signed ripple: single columns may be negative, the
 #pragma unroll
   for (int j = 0; j < L; ++j) {                             // value is in [0, 2x): no carry out of the top
