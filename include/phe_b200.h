@@ -137,7 +137,10 @@ int phe_encrypt_compact(const phe_pubkey* pk, const uint32_t* m, int m_words, si
 int phe_obfuscate(const phe_pubkey* pk, uint32_t* ct_inout, size_t count, const uint32_t* r, int r_words);
 
 /* ipcl::PrivateKey::decrypt(CipherText) -> decryptCRT (ipcl_bindings_classes.cpp:127-133).
- *   ct: count x 2*n_words.  m_out: count x n_words. */
+ *   ct: count x 2*n_words.  m_out: count x n_words.
+ * Device scratch held by the private key after the first call: the window tables of the exponentiations, 10.25 KB per
+ * ciphertext and CRT half at 2048-bit keys (15.5 KB at 3072, 5.1 KB at 1024), for at most 2^17 ciphertexts per launch
+ * (2.8 GB; larger batches run as several launches, and launches shrink further if the device cannot spare that). */
 int phe_decrypt(const phe_privkey* sk, const uint32_t* ct, size_t count, uint32_t* m_out);
 
 /* phe_decrypt followed, on the device, by the classification half of the reference's FixedPointNumber.decode

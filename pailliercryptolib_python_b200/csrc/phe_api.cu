@@ -1093,15 +1093,20 @@ int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count,
   const ShapeOps* o = sk->ops;
   const PairOps* po = pair_ops(sk->pairb[0].L);
   const int hw = sk->hw, cw = 2 * hw, half = hw / 2;
-  const size_t chunk = std::min(count, PAIR_CHUNK);
+  size_t chunk = std::min(count, PAIR_CHUNK);
   constexpr int slots = 1 << (PROG_WS - 1);
+  // the per-unit tables are the one large scratch of the path: on a device that cannot spare them (other keys' comb
+  // tables, the caller's own buffers) run shorter launches rather than fail
+  while (sk->ws_tbl.ensure(po->tbl_words((int)chunk, slots)) != 0) {
+    if (chunk <= 4096) return 1;    // (the error text of the last cudaMalloc stands)
+    chunk = (chunk / 2 + 31) & ~(size_t)31;
+  }
   for (int y = 0; y < 2; ++y) PHE_TRY(sk->ws_u[y].ensure(chunk * half));
-  PHE_TRY(sk->ws_tbl.ensure(po->tbl_words((int)chunk, slots)));
   PHE_TRY(sk->ws_sched.ensure(po->sched_ints((int)chunk)));
   int want_seg = 0;
   if (const char* e = getenv("PHE_DEC_SEGMENTS")) want_seg = atoi(e);
-  for (size_t off = 0; off < count; off += PAIR_CHUNK) {
-    const int c = (int)std::min(PAIR_CHUNK, count - off);
+  for (size_t off = 0; off < count; off += chunk) {
+    const int c = (int)std::min(chunk, count - off);
     const int L = sk->pairb[0].L;
     const int units = 2 * ((c + 31) / 32);
     const int avail = (int)std::min(sk->pairb[0].segoff.size(), sk->pairb[1].segoff.size());
