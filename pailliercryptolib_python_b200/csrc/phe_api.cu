@@ -1109,14 +1109,13 @@ int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count,
     const int c = (int)std::min(chunk, count - off);
     const int L = sk->pairb[0].L;
     const int units = 2 * ((c + 31) / 32);
-    const int avail = (int)std::min(sk->pairb[0].segoff.size(), sk->pairb[1].segoff.size());
-    const bool sliced = want_seg > 0 ? (want_seg > 1 && avail > 1) : (units > po->warps(c) && avail > 1);
+    const bool sliced = want_seg > 0 ? want_seg > 1 : units > po->warps(c);
     DecPairArgs a{};
     a.c_w = d_ct + off * cw; a.c_words = cw; a.chunk_words = half; a.out_words = half; a.count = c; a.slots = slots;
-    a.nseg = sliced ? avail : 1;
     for (int y = 0; y < 2; ++y) {
+      a.nseg[y] = sliced ? (int)sk->pairb[y].segoff.size() : 1;   // (the two programs may cut into different counts)
       a.prog[y] = sliced ? sk->d_pair_segprog[y].p : sk->d_pair_prog[y].p; a.out_w[y] = sk->ws_u[y].p;
-      for (int k = 0; k < a.nseg; ++k) a.seg_off[y][k] = sliced ? sk->pairb[y].segoff[k] : 0;
+      for (int k = 0; k < a.nseg[y]; ++k) a.seg_off[y][k] = sliced ? sk->pairb[y].segoff[k] : 0;
       a.dcon[y] = reinterpret_cast<const double*>(sk->d_pair_mod[y].p) + L;
       a.cst[y] = reinterpret_cast<const double*>(sk->d_pair_cst[y].p);
       a.n0inv[y] = sk->pairb[y].n0inv;

@@ -316,7 +316,7 @@ struct DecPairArgs {
   int c_words, chunk_words;
   const uint32_t* prog[2];   // pair-engine programs for x = p, q (paillier_items.cuh: PairOp), all segments back to back
   int seg_off[2][PAIR_MAX_SEG];   // start of segment s inside prog[y]
-  int nseg;                  // segments per unit (1: the whole program in one piece)
+  int nseg[2];               // segments per unit of modulus y (1: the whole program in one piece)
   uint32_t* out_w[2];        // m_p, m_q: [count][out_words]
   int out_words;
   int count;
@@ -372,7 +372,7 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
 
   const int blocks = (p.count + 31) / 32;
   const int units = 2 * blocks;
-  const int total = units * p.nseg;
+  const int total = blocks * (p.nseg[0] + p.nseg[1]);
   int* const ring = p.sched + PAIR_SCHED_RING;
 #pragma unroll 1
   for (;;) {
@@ -410,7 +410,7 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
     // unit) again afterwards brings that to 376 B with a cleaner-looking row loop -- and 481 instead of 458 ms per 100 000
     // at 3072-bit keys; the same spelling at L = 20 makes ptxas re-derive shared-memory addresses inside the row loop.
     // Measured r02, not kept.)
-    if (seg + 1 < p.nseg) {   // publish: every lane's stores, then the ring slot
+    if (seg + 1 < p.nseg[y]) {   // publish: every lane's stores, then the ring slot
       __syncwarp();
       if (col == 0) {
         __threadfence();

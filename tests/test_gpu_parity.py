@@ -109,6 +109,26 @@ def test_decrypt_time_sliced_units(key2048, nseg, monkeypatch):
     assert got == O.decrypt_batch(sk_o, cs)
 
 
+@pytest.mark.parametrize("bits", [512, 1024, 3072])
+def test_decrypt_time_sliced_other_key_sizes(bits, monkeypatch):
+    """Forced slicing on keys where the uncuttable preamble (conversion + window table) spans several segment targets,
+    so the programs of p and q may cut into different numbers of segments (k_dec_pair takes a count per modulus)."""
+    monkeypatch.setenv("PHE_DEC_SEGMENTS", "16")
+    pk_o, sk_o = O.seeded_keypair(bits, 321)
+    pk = capi.PubKey(pk_o.n, bits, djn=True, hs=pk_o.hs)
+    sk = capi.PrivKey(pk, sk_o.p, sk_o.q)
+    assert capi.pair_block(sk, 0) is not None
+    segs = [len(capi.pair_segments(sk, y)[1]) for y in (0, 1)]
+    assert all(2 <= v <= 16 for v in segs)
+    rng = random.Random(SEED + bits + 5)
+    nw = -(-bits // 32)
+    ms = [0, 1, pk_o.n - 1] + [rng.randrange(pk_o.n) for _ in range(70)]
+    cs = O.encrypt_batch(pk_o, ms, [rng.getrandbits(bits // 2) for _ in ms]) + [0, sk_o.p, pk_o.n]
+    got = capi.array_to_ints(sk.decrypt(capi.ints_to_array(cs, 2 * nw)))
+    assert got[:len(ms)] == ms
+    assert got == O.decrypt_batch(sk_o, cs)
+
+
 def test_decrypt_more_units_than_warps(key2048):
     """40 000 ciphertexts = 2500 warp units on 1184 resident warps: the automatic choice is the time-sliced launch, pieces
     of one unit run on different SMs.  Checked by round trip over the whole batch and against the oracle on a sample."""
