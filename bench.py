@@ -92,7 +92,7 @@ def make_workload(count, seed=SEED):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=float(os.environ.get("PHE_BENCH_CLOCK_PERIOD", "0.1"))):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -305,6 +305,7 @@ def run_gpu(args):
     # ---- device-resident timing --------------------------------------------------------------------------
     t_w0 = time.perf_counter()
     for _ in range(args.warmup):
+        flush.zero_()            # the warm-up runs exactly what a timed step runs (the fill kernel is loaded lazily too)
         step_dev()
     torch.cuda.synchronize()
     warmup_s = time.perf_counter() - t_w0

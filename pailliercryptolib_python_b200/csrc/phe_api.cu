@@ -1112,10 +1112,10 @@ int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count,
     const bool sliced = want_seg > 0 ? want_seg > 1 : units > po->warps(c);
     DecPairArgs a{};
     a.c_w = d_ct + off * cw; a.c_words = cw; a.chunk_words = half; a.out_words = half; a.count = c; a.slots = slots;
+    a.nseg = sliced ? (int)sk->pairb[0].segoff.size() : 1;   // (equal for p and q: phe_privkey_create pads)
     for (int y = 0; y < 2; ++y) {
-      a.nseg[y] = sliced ? (int)sk->pairb[y].segoff.size() : 1;   // (the two programs may cut into different counts)
       a.prog[y] = sliced ? sk->d_pair_segprog[y].p : sk->d_pair_prog[y].p; a.out_w[y] = sk->ws_u[y].p;
-      for (int k = 0; k < a.nseg[y]; ++k) a.seg_off[y][k] = sliced ? sk->pairb[y].segoff[k] : 0;
+      for (int k = 0; k < a.nseg; ++k) a.seg_off[y][k] = sliced ? sk->pairb[y].segoff[k] : 0;
       a.dcon[y] = reinterpret_cast<const double*>(sk->d_pair_mod[y].p) + L;
       a.cst[y] = reinterpret_cast<const double*>(sk->d_pair_cst[y].p);
       a.n0inv[y] = sk->pairb[y].n0inv;
@@ -1320,6 +1320,12 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
       const char* off = getenv("PHE_NO_PAIR_ENGINE");
       sk->use_pair = !(off && off[0] == '1') && build_pair_block(P, hx[0], chunk_bits, &sk->pairb[0]) &&
                      build_pair_block(Q, hx[1], chunk_bits, &sk->pairb[1]) && sk->pairb[0].L == sk->pairb[1].L;
+      if (sk->use_pair) {   // the programs of p and q may cut into different numbers of time slices: k_dec_pair takes ONE count,
+        for (int y = 0; y < 2; ++y) {   // so the shorter one gets empty segments ([PO_END]) at its end
+          PairBlock& b = sk->pairb[y];
+          while (b.segoff.size() < sk->pairb[1 - y].segoff.size()) { b.segoff.push_back((int)b.segprog.size()); b.segprog.push_back(PO_END); }
+        }
+      }
     }
     *out = sk.release();
     return 0;

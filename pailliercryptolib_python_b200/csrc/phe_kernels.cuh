@@ -316,7 +316,8 @@ struct DecPairArgs {
   int c_words, chunk_words;
   const uint32_t* prog[2];   // pair-engine programs for x = p, q (paillier_items.cuh: PairOp), all segments back to back
   int seg_off[2][PAIR_MAX_SEG];   // start of segment s inside prog[y]
-  int nseg[2];               // segments per unit of modulus y (1: the whole program in one piece)
+  int nseg;                  // segments per unit (1: the whole program in one piece); the same for both moduli: the host
+                             // pads the shorter program with empty segments ([PO_END])
   uint32_t* out_w[2];        // m_p, m_q: [count][out_words]
   int out_words;
   int count;
@@ -372,7 +373,7 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
 
   const int blocks = (p.count + 31) / 32;
   const int units = 2 * blocks;
-  const int total = blocks * (p.nseg[0] + p.nseg[1]);
+  const int total = units * p.nseg;
   int* const ring = p.sched + PAIR_SCHED_RING;
 #pragma unroll 1
   for (;;) {
@@ -406,11 +407,16 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
                            want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
                            smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
     }
+    // NOTE on code generation: this kernel sits at 252-255 registers and ptxas' row loop (mont52.cuh: pair_pass) flips
+    // between two forms with any change to what is live across item_dec_pair -- e.g. a per-modulus segment count cost
+    // 3 % (119.3 vs 115.6 ms): the loop re-derived the shared-memory address of D inside every row (S2UR / ULEA + three
+    // extra branches per iteration).  After touching this function check `cuobjdump -sass build/pair_shapes.o`: the hot loop
+    // of k_dec_pair<20> is 918 instructions with 3 BRA.
     // (k_dec_pair<30> spills 448 B here.  Keeping only the piece number across the exponentiation and deriving (segment,
     // unit) again afterwards brings that to 376 B with a cleaner-looking row loop -- and 481 instead of 458 ms per 100 000
     // at 3072-bit keys; the same spelling at L = 20 makes ptxas re-derive shared-memory addresses inside the row loop.
     // Measured r02, not kept.)
-    if (seg + 1 < p.nseg[y]) {   // publish: every lane's stores, then the ring slot
+    if (seg + 1 < p.nseg) {   // publish: every lane's stores, then the ring slot
       __syncwarp();
       if (col == 0) {
         __threadfence();

@@ -66,3 +66,39 @@ def test_packing_helpers_roundtrip():
     arr = capi.ints_to_array(vals, 64)
     assert arr.dtype == np.uint32 and arr.shape == (4, 64)
     assert capi.array_to_ints(arr) == vals
+
+
+def test_row_loop_of_the_decrypt_kernel_is_branch_free():
+    """k_dec_pair<20> sits at 252-255 registers and ptxas flips its row loop (mont52.cuh: pair_pass) between two forms
+    with any change to what is live around it; the bad one re-derives a shared-memory address inside every row (S2UR /
+    ULEA + three extra branches per iteration) and costs 3 % of the headline (119.3 vs 115.6 ms, r02).  The SASS of the
+    built object must show the good one: a 4-row body of ~915 instructions, 320 DFMA, 3 BRA, no S2UR."""
+    import shutil
+    import subprocess
+    obj = os.path.join(ROOT, "pailliercryptolib_python_b200", "build", "pair_shapes.o")
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(obj) or not os.path.exists(tool):
+        pytest.skip("no built object / cuobjdump")
+    sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True).stdout
+    start = sass.index("k_dec_pairILi20")
+    end = sass.index("Function :", start)
+    ins = []
+    for ln in sass[start:end].splitlines():
+        m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", ln)
+        if m:
+            ins.append((int(m.group(1), 16), m.group(2)))
+    loops = []
+    for a, t in ins:
+        if "BRA" in t:
+            m = re.search(r"(0x[0-9a-f]+)", t)
+            if m and int(m.group(1), 16) < a:
+                loops.append((int(m.group(1), 16), a))
+    body = None
+    for lo, hi in loops:     # the innermost loop with a whole chunk of rows of products in it
+        inner = [t for a, t in ins if lo <= a <= hi]
+        if sum("DFMA" in t for t in inner) == 320 and (body is None or len(inner) < len(body)):
+            body = inner
+    assert body is not None, "row loop of k_dec_pair<20> not found (U != 4?)"
+    assert len(body) <= 925, len(body)
+    assert sum(" BRA" in (" " + t) for t in body) <= 3
+    assert not any(re.search(r"\bS2U?R\b", t) for t in body)
