@@ -246,7 +246,7 @@ int phe_pubkey_npair_block(const phe_pubkey* pk, int* L_out, int* TPI_out, doubl
                            uint64_t* d_top_out);
 /* Decrypt runs its two CRT halves on the p-adic pair engine when p and q both have exactly bits/2 bits (every key
  * made by a keygen).  This dumps what the engine is given for x = p (y = 0) or q (y = 1): L (limbs per number),
- * n0inv = -x^-1 mod 2^52, mod_out = [L] limbs of x then [L + 1] limbs of D = ceil(R / x) x (doubles), cst_out =
+ * n0inv = -x^-1 mod 2^52, mod_out = [L] limbs of x (doubles), cst_out =
  * [6][2][L] constant pairs (W_0..W_3, (1, 0), (h_x R mod x, 0)) and the program (csrc/paillier_items.cuh: PairOp).
  * Returns the program length, 0 if the key does not use the engine, < 0 on error.  Buffers may be NULL. */
 int phe_privkey_pair_block(const phe_privkey* sk, int y, int* L_out, uint64_t* n0inv_out, double* mod_out,

@@ -412,7 +412,7 @@ def pair_block(sk, y):
         return None
     L, n0 = ctypes.c_int(), ctypes.c_uint64()
     lib().phe_privkey_pair_block(sk.h, int(y), ctypes.byref(L), ctypes.byref(n0), None, None, None, 0)
-    mod = np.zeros(2 * L.value + 1, dtype=np.float64)
+    mod = np.zeros(L.value, dtype=np.float64)
     cst = np.zeros(6 * 2 * L.value, dtype=np.float64)
     prog = np.zeros(n, dtype=np.uint32)
     dp = ctypes.POINTER(ctypes.c_double)

@@ -245,7 +245,10 @@ PHE_HD void mac_span(uint64_t (&acc)[L], const X& x, double y, uint64_t& hprev, 
 #define PHE52_U 4
 #endif
 // L = 30 (one-lane pair engine of 3072-bit keys): 5 rows are 300 products = 27 KB of code, 3 rows 16 KB
-template <int L> struct Unroll { static constexpr int U = (L > 24 && L % 3 == 0) ? 3 : (L % PHE52_U == 0) ? PHE52_U : (L % 5 == 0) ? 5 : (L % 4 == 0) ? 4 : (L % 3 == 0) ? 3 : (L % 2 == 0) ? 2 : 1; };
+#ifndef PHE52_U_WIDE
+#define PHE52_U_WIDE 3
+#endif
+template <int L> struct Unroll { static constexpr int U = (L > 24 && L % PHE52_U_WIDE == 0) ? PHE52_U_WIDE : (L % PHE52_U == 0) ? PHE52_U : (L % 5 == 0) ? 5 : (L % 4 == 0) ? 4 : (L % 3 == 0) ? 3 : (L % 2 == 0) ? 2 : 1; };
 
 // index of limb `row` in the padded [TPI][LP] layout
 template <int L> PHE_HD int padded_index(int row) {
@@ -433,23 +436,31 @@ PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, con
 // against 8 L^2 for one Montgomery product of 2L limbs -- and everything fits ONE lane (L = 20 at 2048-bit keys):
 // no shuffles, 32 ciphertexts per warp.  The L function comes for free: c^(x-1) = 1 + L x.
 //
-// pair_pass is one reduction:  r = (a b + E + m x) / R  with E = sum_i e_in[i] 2^(52 i) a (signed) column addend.
-// Pass 1 of a product (a = X0, b = Y0) records e_out[i] = D_i - q_i, D = k x >= R; pass 2 (a = X0, b = Y1) takes it as
-// e_in: that is the "- m" term made non-negative; a third pass (a = X1, b = Y0) gives the other cross term and the two
+// pair_pass is one reduction:  r = (a b - M + m x) / R  with M = sum_i e_in[i] 2^(52 i) subtracted column by column.
+// Pass 1 of a product (a = X0, b = Y0) records its quotient digits, e_out[i] = q_i; pass 2 (a = X0, b = Y1) takes them as
+// e_in: that is the "- m" term.  No multiple of x has to be added to keep things non-negative: a b - M + m' x is a multiple
+// of R and, with a b >= 0 and M < R, greater than -R, hence >= 0 -- only single columns go negative on the way, and the
+// column arithmetic is signed (arithmetic carry shifts, signed final ripple).  (r01 / early r02 fed D_i - q_i with
+// D = ceil(R / x) x instead: one load, a masked subtraction and two moves more per row, 2.6 % of the row loop.)
+// A third pass (a = X1, b = Y0) gives the other cross term and the two
 // are added (a square needs only pass 2 with a = 2 X0, b = X1).  One code body serves every pass: a fused
 // two-multiplicand pass saves one reduction per multiplication but needs a second, 26 KB loop body that evicts the hot
 // one from the 32 KB instruction cache (measured: no_instruction 0.64 stalled warps per issue).  b is read from, and
 // the result written to, (shared) memory with a stride of PE::STRIDE doubles between limbs (one column per lane); n
-// and dcon (L + 1 limbs of D) are shared by all lanes.  Result: exact limbs, value < 2x.  r_out may alias b.
+// is shared by all lanes.  Result: exact limbs, value < a b / R + x.  r_out may alias b.
 // ------------------------------------------------------------------------------------------------
 template <int L, class PE>
 PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, const int64_t* e_in, int64_t* e_out,
-                      const double* n, const double* dcon, uint64_t n0inv) {
+                      const double* n, uint64_t n0inv) {
   constexpr int U = Unroll<L>::U;
   constexpr int ST = PE::STRIDE;
-  // product chains in flight per batch: 20 at L <= 20; at L = 30 a batch of 20 (120 registers of temporaries next to
-  // 60 + 60 for a and the accumulators) spills, 15 = half a row does not
-  constexpr int G = (L > 20) ? (L + 1) / 2 : PHE52_G;
+  // product chains in flight per batch: a whole row (L) at every shape.  At L = 30 that is 90 registers of temporaries next
+  // to 60 + 60 for a and the accumulators and ptxas spills a little more outside the row loop, but r02 measured
+  // k_dec_pair<30> at 100 000 x 3072 bits: G = 30 451 ms, 20 465, 15 469, 10 457 (tools/ab_wide.sh).
+#ifndef PHE52_G_WIDE
+#define PHE52_G_WIDE L
+#endif
+  constexpr int G = (L > 20) ? PHE52_G_WIDE : PHE52_G;
   constexpr uint64_t INIT = 0ull - bias_of(2 * L, 2 * L);
   uint64_t acc[L];
 #pragma unroll
@@ -461,7 +472,7 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
     const double b0 = b[0];
     uint64_t h;
     mac_first(acc[0], a[0], b0, h);
-    if (e_in) acc[0] += (uint64_t)e_in[0];
+    if (e_in) acc[0] -= (uint64_t)e_in[0];
     q = (acc[0] * n0inv) & M52;
     mac_span<L, 1, L, double[L], G>(acc, a, b0, h, 0);
     topA = h;
@@ -473,7 +484,7 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
     for (int u = 0; u < U; ++u) {   // row i = row0 + u; column c of row i lives in acc[(c + u) % L]
       const int row = row0 + u;
       const bool last = (u == U - 1) && (row == L - 1);
-      if (e_out) e_out[row * ST] = (int64_t)int_of(dcon[row]) - (int64_t)q;   // D_i - q_i
+      if (e_out) e_out[row * ST] = (int64_t)q;
       uint64_t hN, hA = 0;
       const double n0 = n[0], n1 = n[1];
       mac_first(acc[u % L], n0, qd, hN);
@@ -489,7 +500,7 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
       if (!last) {
         bn = b[(row + 1) * ST];
         mac_first(acc[(u + 1) % L], a[0], bn, hA);
-        if (e_in) acc[(u + 1) % L] += (uint64_t)e_in[(row + 1) * ST];
+        if (e_in) acc[(u + 1) % L] -= (uint64_t)e_in[(row + 1) * ST];
         q = (acc[(u + 1) % L] * n0inv) & M52;
       }
       mac_span<L, 2, L, const double*, G>(acc, n, qd, hN, u);
@@ -510,8 +521,6 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
   }
 #pragma unroll
   for (int j = 0; j < L; ++j) acc[j] += bias_of(2 * (j + 1), 2 * j);
-  if (e_out) e_out[L * ST] = (int64_t)int_of(dcon[L]);
-  if (e_in) acc[0] += (uint64_t)e_in[L * ST];            // top limb of D
   // (This 3 L-deep chain is hidden by the other warp of the scheduler: a one-step parallel carry -- r[j] = low52(acc[j])
   // + (acc[j-1] >> 52), sequential fallback only when some r[j] leaves [0, 2^52), probability ~2^-39 per limb -- is
   // bit-exact and SLOWER, 116.7-117.2 against 115.6 ms for k_dec_pair<20> at 100 000: the kernel is dispatch-bound and

@@ -704,7 +704,7 @@ template <int L> PHE_HD void pair_double(double (&x)[L]) {
 
 template <int L, class PE>
 PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* prog, uint32_t* out_w, int out_words,
-                          const double* n, const double* dcon, uint64_t n0inv, const double* cst, double* tbl,
+                          const double* n, uint64_t n0inv, const double* cst, double* tbl,
                           PairSmem<PE> sm) {
   constexpr int ST = PE::STRIDE;
   double x[L];
@@ -866,7 +866,7 @@ PHE_HD void item_dec_pair(const uint32_t* c_w, int chunk_words, const uint32_t* 
       rout = sm.x1;
     }
 
-    pair_pass<L, PE>(rout, x, b, ein, eout, n, dcon, n0inv);
+    pair_pass<L, PE>(rout, x, b, ein, eout, n, n0inv);
 
     if (sub == 0) {
       sub = 1;

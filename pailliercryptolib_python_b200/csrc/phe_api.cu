@@ -323,7 +323,7 @@ void to_limbs52(const BN& v, int L, double* out) {
 struct PairBlock {
   int L = 0;
   uint64_t n0inv = 0;
-  std::vector<double> mod;       // [L] x, [L + 1] D
+  std::vector<double> mod;       // [L] limbs of x
   std::vector<double> cst;       // [PC_COUNT][2][L]
   std::vector<uint32_t> prog;    // the whole program in one piece
   std::vector<uint32_t> segprog; // the same program cut into time slices (k_dec_pair), segments back to back
@@ -392,12 +392,8 @@ bool build_pair_block(const BN& x, const BN& hx, int chunk_bits, PairBlock* out)
   out->n0inv = neg_inv52(x);
   const BN R = hbn::shl(BN(1), 52 * (size_t)L);
   const BN x2 = hbn::mul(x, x);
-  // D = ceil(R / x) * x: a multiple of x that is >= R > every Montgomery quotient
-  BN k = hbn::div(hbn::add(R, hbn::sub(x, BN(1))), x);
-  const BN D = hbn::mul(k, x);
-  out->mod.assign(2 * (size_t)L + 1, 0.0);
+  out->mod.assign((size_t)L, 0.0);
   to_limbs52(x, L, out->mod.data());
-  to_limbs52(D, L + 1, out->mod.data() + L);
   out->cst.assign((size_t)PC_COUNT * 2 * L, 0.0);
   auto put_pair = [&](int idx, const BN& v0, const BN& v1) {
     to_limbs52(v0, L, &out->cst[((size_t)idx * 2 + 0) * L]);
@@ -499,7 +495,7 @@ struct phe_privkey {
   // p-adic pair engine (balanced keys): per x = p, q
   bool use_pair = false;
   PairBlock pairb[2];
-  mutable DevBuf d_pair_mod[2], d_pair_cst[2], d_pair_prog[2], d_pair_segprog[2];
+  mutable DevBuf d_pair_cst[2], d_pair_prog[2], d_pair_segprog[2];
   mutable MontCtxArgs ctx[2]{};
   int ebits[2] = {0, 0};
   int hw = 0;  // words of x^2 (= n_words)
@@ -636,10 +632,7 @@ int sk_ensure_device(const phe_privkey* sk) {
   if (sk->use_pair) {
     for (int y = 0; y < 2; ++y) {
       const PairBlock& b = sk->pairb[y];
-      std::vector<uint32_t> tmp(b.mod.size() * 2);
-      std::memcpy(tmp.data(), b.mod.data(), b.mod.size() * 8);
-      PHE_TRY(upload(sk->d_pair_mod[y], tmp));
-      tmp.assign(b.cst.size() * 2, 0);
+      std::vector<uint32_t> tmp(b.cst.size() * 2, 0);
       std::memcpy(tmp.data(), b.cst.data(), b.cst.size() * 8);
       PHE_TRY(upload(sk->d_pair_cst[y], tmp));
       PHE_TRY(upload(sk->d_pair_prog[y], b.prog));
@@ -1107,7 +1100,6 @@ int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count,
   if (const char* e = getenv("PHE_DEC_SEGMENTS")) want_seg = atoi(e);
   for (size_t off = 0; off < count; off += chunk) {
     const int c = (int)std::min(chunk, count - off);
-    const int L = sk->pairb[0].L;
     const int units = 2 * ((c + 31) / 32);
     const bool sliced = want_seg > 0 ? want_seg > 1 : units > po->warps(c);
     DecPairArgs a{};
@@ -1116,7 +1108,6 @@ int decrypt_pair_impl(const phe_privkey* sk, const uint32_t* d_ct, size_t count,
     for (int y = 0; y < 2; ++y) {
       a.prog[y] = sliced ? sk->d_pair_segprog[y].p : sk->d_pair_prog[y].p; a.out_w[y] = sk->ws_u[y].p;
       for (int k = 0; k < a.nseg; ++k) a.seg_off[y][k] = sliced ? sk->pairb[y].segoff[k] : 0;
-      a.dcon[y] = reinterpret_cast<const double*>(sk->d_pair_mod[y].p) + L;
       a.cst[y] = reinterpret_cast<const double*>(sk->d_pair_cst[y].p);
       a.n0inv[y] = sk->pairb[y].n0inv;
     }
@@ -1334,7 +1325,7 @@ int phe_privkey_create(const phe_pubkey* pk, const uint32_t* p, int p_words, con
 
 void phe_privkey_destroy(phe_privkey* sk) {
   if (!sk) return;
-  for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->d_pair_mod[0], &sk->d_pair_mod[1], &sk->d_pair_cst[0], &sk->d_pair_cst[1], &sk->d_pair_prog[0], &sk->d_pair_prog[1], &sk->d_pair_segprog[0], &sk->d_pair_segprog[1], &sk->ws_in, &sk->ws_out,
+  for (DevBuf* b : {&sk->d_ctx[0], &sk->d_ctx[1], &sk->d_exp[0], &sk->d_exp[1], &sk->d_prog[0], &sk->d_prog[1], &sk->d_tail, &sk->d_pair_cst[0], &sk->d_pair_cst[1], &sk->d_pair_prog[0], &sk->d_pair_prog[1], &sk->d_pair_segprog[0], &sk->d_pair_segprog[1], &sk->ws_in, &sk->ws_out,
                     &sk->ws_mont[0], &sk->ws_mont[1], &sk->ws_u[0], &sk->ws_u[1], &sk->ws_tbl, &sk->ws_sched, &sk->ws_cls, &sk->d_n}) b->release();
   sk->chain.release();
   delete sk;

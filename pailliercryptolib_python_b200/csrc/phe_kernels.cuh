@@ -321,7 +321,6 @@ struct DecPairArgs {
   uint32_t* out_w[2];        // m_p, m_q: [count][out_words]
   int out_words;
   int count;
-  const double* dcon[2];     // [L + 1] limbs of D = ceil(R / x) x  (global; staged to shared memory: indexed by row)
   uint64_t n0inv[2];
   const double* cst[2];      // [PC_COUNT][2][L] constant pairs
   double* tbl;               // [units][slots + 1][2][L][32]: window table + the parked pair of every unit
@@ -332,17 +331,17 @@ constexpr int PAIR_SCHED_HEAD = 0, PAIR_SCHED_TAIL = 32, PAIR_SCHED_RING = 64;
 template <int L> struct ModLimbs { double v[2][L]; };
 
 template <int L> struct PairShape {
-  static constexpr int LE = (L + 2) & ~1;                       // L + 1 entries of E / D, padded to even
+  static constexpr int LE = (L + 2) & ~1;                       // entries of E per lane (L used), padded
   static constexpr int PER_LANE = 4 * L + LE;                   // doubles of shared memory per lane
   // threads per CTA.  L = 30 needs 1216 B of shared memory per lane: one 128-thread CTA per SM is all that fits; a
   // 160-thread CTA (a fifth warp, 195 KB) was measured and is no faster (518 vs 513 ms per 100 000 at 3072-bit keys)
   static constexpr int NTP = NT;
   static constexpr int CTAS = (L > 20) ? 1 : 2;
   // L > 20: the 2 L modulus limbs do not fit the register file next to the accumulators (k_dec_pair<30> spilled
-  // 256 bytes with them in registers): they are staged into shared memory instead ([2][LE] doubles after D)
+  // 256 bytes with them in registers): they are staged into shared memory instead ([2][LE] doubles)
   static constexpr bool MOD_IN_SMEM = L > 20;
   static constexpr int MOD_DOUBLES = MOD_IN_SMEM ? 2 * LE : 0;
-  static constexpr size_t smem_bytes() { return (size_t)(2 * LE + MOD_DOUBLES + PER_LANE * NTP) * sizeof(double); }
+  static constexpr size_t smem_bytes() { return (size_t)(MOD_DOUBLES + PER_LANE * NTP) * sizeof(double); }
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -358,12 +357,11 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
   using PE = DevPairEnv;
   using PS = PairShape<L>;
   extern __shared__ __align__(16) double smem[];
-  for (int i = threadIdx.x; i < 2 * (L + 1); i += PS::NTP) smem[(i / (L + 1)) * PS::LE + i % (L + 1)] = p.dcon[i / (L + 1)][i % (L + 1)];
   if (PS::MOD_IN_SMEM)
-    for (int i = threadIdx.x; i < 2 * L; i += PS::NTP) smem[2 * PS::LE + (i / L) * PS::LE + i % L] = mod.v[i / L][i % L];
+    for (int i = threadIdx.x; i < 2 * L; i += PS::NTP) smem[(i / L) * PS::LE + i % L] = mod.v[i / L][i % L];
   __syncthreads();
   const int warp = threadIdx.x >> 5, col = threadIdx.x & 31;
-  double* wbase = smem + 2 * PS::LE + PS::MOD_DOUBLES + (size_t)warp * PS::PER_LANE * 32 + col;
+  double* wbase = smem + PS::MOD_DOUBLES + (size_t)warp * PS::PER_LANE * 32 + col;
   PairSmem<PE> sm;
   sm.xs0 = wbase;
   sm.x1 = wbase + L * 32;
@@ -398,14 +396,14 @@ template <int L> __global__ void __launch_bounds__(PairShape<L>::NTP, PairShape<
     if (PS::MOD_IN_SMEM) {
       item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, prog,
                            want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words,
-                           smem + 2 * PS::LE + y * PS::LE, smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+                           smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
     } else {
       double n[L];
 #pragma unroll
       for (int j = 0; j < L; ++j) n[j] = y ? mod.v[1][j] : mod.v[0][j];
       item_dec_pair<L, PE>(p.c_w + (size_t)item * p.c_words, p.chunk_words, prog,
                            want < p.count ? p.out_w[y] + (size_t)item * p.out_words : nullptr, p.out_words, n,
-                           smem + y * PS::LE, p.n0inv[y], p.cst[y], tbl, sm);
+                           p.n0inv[y], p.cst[y], tbl, sm);
     }
     // NOTE on code generation: this kernel sits at 252-255 registers and ptxas' row loop (mont52.cuh: pair_pass) flips
     // between two forms with any change to what is live across item_dec_pair -- e.g. a per-modulus segment count cost

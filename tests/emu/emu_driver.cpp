@@ -297,7 +297,7 @@ int do_dec_pair(const uint32_t* c, int c_words, int chunk_words, const uint32_t*
       std::vector<int64_t> e(L + 1, 7);
       phe::PairSmem<EmuPairEnv> sm{xs0.data(), x1.data(), y0.data(), y1.data(), e.data()};
       phe::item_dec_pair<L, EmuPairEnv>(c + (size_t)i * c_words, chunk_words, prog + (seg_off ? seg_off[s] : 0),
-                                        out + (size_t)i * out_words, out_words, mod, mod + L, n0inv, cst, tbl.data(), sm);
+                                        out + (size_t)i * out_words, out_words, mod, n0inv, cst, tbl.data(), sm);
     }
   }
   std::fesetround(FE_TONEAREST);
