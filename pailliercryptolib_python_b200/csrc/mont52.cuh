@@ -162,6 +162,25 @@ PHE_HD constexpr uint64_t bias_of(int nlo, int nhi) {
   return (uint64_t)nlo * BIAS_LO + (uint64_t)nhi * BIAS_HI;   // mod 2^64
 }
 
+// The row loops below add the multiplicand part of row i + 1 inside the iteration of row i.  After the LAST row that part
+// used to be skipped by a branch -- a conditional region in the last row of every unrolled chunk, inside which ptxas cannot
+// interleave the quotient-digit chain (LDS -> DFMA -> DADD -> DFMA -> IADD3 -> 4 IMAD) with other products: ncu r02 put
+// 6.4 % of the stall samples of k_dec_pair<20> on those 11 instructions.  With PHE52_GHOST the part always runs, after the
+// last row with b = 0: L "ghost" products per pass that only add their exponent-field biases (one low half to every
+// result column, one high half to every column but the first), which final_bias takes off again at compile time.
+// k_dec_pair<20> 112.7 -> 108.6 ms, k_dec_pair<30> 451 -> 444 ms.  The multi-lane products (montmul, montmul_e: K = L TPI
+// rows per pass, so the ghost products are a smaller share, but so is the gain) lose: k_encrypt_npair<20,2> 15.62 -> 15.82
+// ms, HE mul 5.83 -> 5.72 M/s, HE add +0.3 %; they keep the branch (PHE52_GHOST_MULTI = 0).
+#ifndef PHE52_GHOST
+#define PHE52_GHOST 1
+#endif
+#ifndef PHE52_GHOST_MULTI
+#define PHE52_GHOST_MULTI 0
+#endif
+PHE_HD constexpr uint64_t final_bias(int j, bool ghost) {
+  return ghost ? bias_of(2 * j + 1, j ? 2 * j - 1 : 0) : bias_of(2 * (j + 1), 2 * j);
+}
+
 template <int L> PHE_HD uint32_t ripple(uint64_t (&x)[L], uint32_t cin) {
   uint64_t c = cin;
 #pragma unroll
@@ -274,6 +293,7 @@ PHE_HD void montmul(double (&r)[L], const double (&a)[L], const double* b, const
   static_assert(L >= 2 && L <= 64, "limbs per lane out of range");
   constexpr int K = L * TPI;
   constexpr int U = Unroll<L>::U;
+  constexpr bool GHOST = PHE52_GHOST_MULTI != 0;
   const int lane = Env::lane();
   const double* n = n_entry + lane * Pad<L>::LP;
   const uint64_t topmask = (lane == TPI - 1) ? 0ull : ~0ull;
@@ -312,14 +332,19 @@ PHE_HD void montmul(double (&r)[L], const double (&a)[L], const double* b, const
         acc[u % L] = from_above64<Env>(low & M52) & topmask;   // becomes the new top column (column L of row i)
       }
       double bn = 0.0;
-      if (!last) {
+      if (GHOST) {   // branch-free: after the last row the multiplicand part runs with b = 0 (see pair_pass)
+        bn = b[padded_index<L>(last ? row : row + 1)];
+        if (last) bn = 0.0;
+        mac_first(acc[(u + 1) % L], a[0], bn, hA);
+        q = bcast64<Env>((acc[(u + 1) % L] * n0inv) & M52, 0);
+      } else if (!last) {
         bn = b[padded_index<L>(row + 1)];
         mac_first(acc[(u + 1) % L], a[0], bn, hA);
         q = bcast64<Env>((acc[(u + 1) % L] * n0inv) & M52, 0);
       }
       mac_span<L, 2, L>(acc, n, qd, hN, u);
       acc[u % L] += topA + hN + INIT;
-      if (!last) {
+      if (GHOST || !last) {
         mac_span<L, 1, L>(acc, a, bn, hA, u + 1);
         topA = hA;
         qd = limb_of(q);
@@ -334,7 +359,7 @@ PHE_HD void montmul(double (&r)[L], const double (&a)[L], const double* b, const
     }
   }
 #pragma unroll
-  for (int j = 0; j < L; ++j) acc[j] += bias_of(2 * (j + 1), 2 * j);
+  for (int j = 0; j < L; ++j) acc[j] += final_bias(j, GHOST);
   normalize_exact<L, TPI, Env>(acc);
 #pragma unroll
   for (int j = 0; j < L; ++j) r[j] = limb_of(acc[j]);
@@ -356,6 +381,7 @@ PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, con
   static_assert(L >= 2 && L <= 64, "limbs per lane out of range");
   constexpr int K = L * TPI;
   constexpr int U = Unroll<L>::U;
+  constexpr bool GHOST = PHE52_GHOST_MULTI != 0;
   const int lane = Env::lane();
   const double* n = n_entry + lane * Pad<L>::LP;
   const uint64_t topmask = (lane == TPI - 1) ? 0ull : ~0ull;
@@ -397,7 +423,13 @@ PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, con
         acc[u % L] = from_above64<Env>(low & M52) & topmask;   // becomes the new top column (column L of row i)
       }
       double bn = 0.0;
-      if (!last) {
+      if (GHOST) {   // branch-free: after the last row the multiplicand part runs with b = 0 (see pair_pass)
+        bn = b[padded_index<L>(last ? row : row + 1)];
+        if (last) bn = 0.0;
+        mac_first(acc[(u + 1) % L], a[0], bn, hA);
+        if (ein && lead && !last) acc[(u + 1) % L] += ein[padded_index<L>(row + 1)];
+        q = bcast64<Env>((acc[(u + 1) % L] * n0inv) & qmask, 0);
+      } else if (!last) {
         bn = b[padded_index<L>(row + 1)];
         mac_first(acc[(u + 1) % L], a[0], bn, hA);
         if (ein && lead) acc[(u + 1) % L] += ein[padded_index<L>(row + 1)];
@@ -405,7 +437,7 @@ PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, con
       }
       mac_span<L, 2, L>(acc, n, qd, hN, u);
       acc[u % L] += topA + hN + INIT;
-      if (!last) {
+      if (GHOST || !last) {
         mac_span<L, 1, L>(acc, a, bn, hA, u + 1);
         topA = hA;
         qd = limb_of(q);
@@ -420,7 +452,7 @@ PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, con
     }
   }
 #pragma unroll
-  for (int j = 0; j < L; ++j) acc[j] += bias_of(2 * (j + 1), 2 * j);
+  for (int j = 0; j < L; ++j) acc[j] += final_bias(j, GHOST);
   if (ein && lead) acc[0] += ein[TPI * Pad<L>::LP];        // top limb of E: column K
   normalize_exact<L, TPI, Env>(acc);
 #pragma unroll
@@ -469,6 +501,7 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
   // digit inside the rows: the same 3 instructions per digit, but only in the passes that have an M (r02: k_dec_pair<20>
   // 114.0 -> 113.0 ms; k_dec_pair<30> 450.6 -> 462.5 ms, so that shape keeps the in-row form)
   constexpr bool M_UPFRONT = (L <= 20);
+  constexpr bool GHOST = PHE52_GHOST != 0;
   if (M_UPFRONT && e_in) {
 #pragma unroll
     for (int j = 0; j < L; ++j) acc[j] -= (uint64_t)e_in[j * ST];
@@ -505,7 +538,16 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
         acc[u % L] = 0;                                    // becomes the new top column (column L of row i)
       }
       double bn = 0.0;
-      if (!last) {
+      if (GHOST) {
+        // no branch around the multiplicand part of the next row: after the last row it runs with b = 0 and only adds
+        // exponent-field biases, which the constants below take off again (20 ghost products per pass against a
+        // conditional region in the last row of every chunk, where ptxas cannot interleave the quotient-digit chain)
+        bn = b[(last ? row : row + 1) * ST];
+        if (last) bn = 0.0;
+        mac_first(acc[(u + 1) % L], a[0], bn, hA);
+        if (!M_UPFRONT && e_in && !last) acc[(u + 1) % L] -= (uint64_t)e_in[(row + 1) * ST];
+        q = (acc[(u + 1) % L] * n0inv) & M52;
+      } else if (!last) {
         bn = b[(row + 1) * ST];
         mac_first(acc[(u + 1) % L], a[0], bn, hA);
         if (!M_UPFRONT && e_in) acc[(u + 1) % L] -= (uint64_t)e_in[(row + 1) * ST];
@@ -513,7 +555,7 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
       }
       mac_span<L, 2, L, const double*, G>(acc, n, qd, hN, u);
       acc[u % L] += topA + hN + INIT;
-      if (!last) {
+      if (GHOST || !last) {
         mac_span<L, 1, L, double[L], G>(acc, a, bn, hA, u + 1);
         topA = hA;
         qd = limb_of(q);
@@ -528,7 +570,7 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
     }
   }
 #pragma unroll
-  for (int j = 0; j < L; ++j) acc[j] += bias_of(2 * (j + 1), 2 * j);
+  for (int j = 0; j < L; ++j) acc[j] += final_bias(j, GHOST);
   // (This 3 L-deep chain is hidden by the other warp of the scheduler: a one-step parallel carry -- r[j] = low52(acc[j])
   // + (acc[j-1] >> 52), sequential fallback only when some r[j] leaves [0, 2^52), probability ~2^-39 per limb -- is
   // bit-exact and SLOWER, 116.7-117.2 against 115.6 ms for k_dec_pair<20> at 100 000: the kernel is dispatch-bound and
