@@ -481,10 +481,14 @@ PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, con
 // the result written to, (shared) memory with a stride of PE::STRIDE doubles between limbs (one column per lane); n
 // is shared by all lanes.  Result: exact limbs, value < a b / R + x.  r_out may alias b.
 // ------------------------------------------------------------------------------------------------
+// rows per chunk of the one-lane engine: with the branch-free row body a loop back-edge costs little (U = 2: +0.5 %) and
+// five rows of 40 products (17.7 KB) still sit in the instruction cache: k_dec_pair<20> U = 5 107.7, U = 4 108.5, U = 2 109.1 ms
+template <int L> struct PairUnroll { static constexpr int U = (L <= 20 && L % 5 == 0) ? 5 : Unroll<L>::U; };
+
 template <int L, class PE>
 PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, const int64_t* e_in, int64_t* e_out,
                       const double* n, uint64_t n0inv) {
-  constexpr int U = Unroll<L>::U;
+  constexpr int U = PairUnroll<L>::U;
   constexpr int ST = PE::STRIDE;
   // product chains in flight per batch: a whole row (L) at every shape.  At L = 30 that is 90 registers of temporaries next
   // to 60 + 60 for a and the accumulators and ptxas spills a little more outside the row loop, but r02 measured

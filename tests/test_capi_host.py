@@ -69,10 +69,11 @@ def test_packing_helpers_roundtrip():
 
 
 def test_row_loop_of_the_decrypt_kernel_is_branch_free():
-    """k_dec_pair<20> sits at 252-255 registers and ptxas flips its row loop (mont52.cuh: pair_pass) between two forms
-    with any change to what is live around it; the bad one re-derives a shared-memory address inside every row (S2UR /
-    ULEA + three extra branches per iteration) and costs 3 % of the headline (119.3 vs 115.6 ms, r02).  The SASS of the
-    built object must show the good one: a 4-row body of ~915 instructions, 320 DFMA, 3 BRA, no S2UR."""
+    """k_dec_pair<20> sits at 252-255 registers and ptxas flips its row loop (mont52.cuh: pair_pass) between forms with
+    any change to what is live around it; a bad one re-derives a shared-memory address inside every row (S2UR / ULEA +
+    three extra branches per iteration) and cost 3 % of the headline (119.3 vs 115.6 ms, r02), and a conditional region in
+    the last row of a chunk cost another 3.6 %.  The SASS of the built object must show the good one: a 5-row body of 400
+    DFMA and at most 5.55 instructions per limb product, no branch but the back-edge, no S2R / S2UR."""
     import shutil
     import subprocess
     obj = os.path.join(ROOT, "pailliercryptolib_python_b200", "build", "pair_shapes.o")
@@ -94,11 +95,14 @@ def test_row_loop_of_the_decrypt_kernel_is_branch_free():
             if m and int(m.group(1), 16) < a:
                 loops.append((int(m.group(1), 16), a))
     body = None
-    for lo, hi in loops:     # the innermost loop with a whole chunk of rows of products in it
+    for lo, hi in loops:     # the innermost loop with whole rows of products in it
         inner = [t for a, t in ins if lo <= a <= hi]
-        if sum("DFMA" in t for t in inner) == 320 and (body is None or len(inner) < len(body)):
+        dfma = sum("DFMA" in t for t in inner)
+        if dfma >= 160 and dfma % 80 == 0 and (body is None or len(inner) < len(body)):
             body = inner
-    assert body is not None, "row loop of k_dec_pair<20> not found (U != 4?)"
-    assert len(body) <= 925, len(body)
-    assert sum(" BRA" in (" " + t) for t in body) <= 3
+    assert body is not None, "row loop of k_dec_pair<20> not found"
+    products = sum("DFMA" in t for t in body) // 2
+    assert products == 200, products                       # U = 5 rows of 2 * 20 limb products
+    assert len(body) <= 5.55 * products, (len(body), products)
+    assert sum(bool(re.search(r"\bBRA\b", t)) for t in body) == 1
     assert not any(re.search(r"\bS2U?R\b", t) for t in body)
