@@ -503,15 +503,11 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
   uint64_t acc[L];
 #pragma unroll
   for (int j = 0; j < L; ++j) acc[j] = 0ull - bias_of(2 * (j + 1), 2 * j);
-  // L <= 20: M is subtracted whole before the first row (digit j sits in window column j of row 0) instead of digit by
+  // L <= 20: M is subtracted whole around the first row (digit j sits in window column j of row 0) instead of digit by
   // digit inside the rows: the same 3 instructions per digit, but only in the passes that have an M (r02: k_dec_pair<20>
   // 114.0 -> 113.0 ms; k_dec_pair<30> 450.6 -> 462.5 ms, so that shape keeps the in-row form)
   constexpr bool M_UPFRONT = (L <= 20);
   constexpr bool GHOST = PHE52_GHOST != 0;
-  if (M_UPFRONT && e_in) {
-#pragma unroll
-    for (int j = 0; j < L; ++j) acc[j] -= (uint64_t)e_in[j * ST];
-  }
 
   uint64_t topA, q;
   double qd;
@@ -519,11 +515,17 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
     const double b0 = b[0];
     uint64_t h;
     mac_first(acc[0], a[0], b0, h);
-    if (!M_UPFRONT && e_in) acc[0] -= (uint64_t)e_in[0];
+    if (e_in) acc[0] -= (uint64_t)e_in[0];
     q = (acc[0] * n0inv) & M52;
     mac_span<L, 1, L, double[L], G>(acc, a, b0, h, 0);
     topA = h;
     qd = limb_of(q);
+  }
+  // (after the first row, not before it: the pre-charge constants of the columns then fold into the first additions as
+  // immediates instead of being moved into 2 L registers first)
+  if (M_UPFRONT && e_in) {
+#pragma unroll
+    for (int j = 1; j < L; ++j) acc[j] -= (uint64_t)e_in[j * ST];
   }
 #pragma unroll 1
   for (int row0 = 0; row0 < L; row0 += U) {
