@@ -483,6 +483,9 @@ PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, con
 // ------------------------------------------------------------------------------------------------
 // rows per chunk of the one-lane engine: with the branch-free row body a loop back-edge costs little (U = 2: +0.5 %) and
 // five rows of 40 products (17.7 KB) still sit in the instruction cache: k_dec_pair<20> U = 5 107.7, U = 4 108.5, U = 2 109.1 ms
+// (Offset carries -- every column pre-charged with 2^63 - 2^11 more, so that the carry it hands on is the non-negative
+// (value >> 52) and needs no sign word: one SHF less per row, 25 instructions less per pass, bit-exact -- measure the
+// same: 107.2 vs 107.0 ms.  r02, not kept.)
 // (Fetching the multiplier limb of a chunk's first row one chunk ahead -- ncu puts 3.5 % of the stall samples on the first
 // DFMA behind that LDS -- costs two registers across the back-edge and LOSES: 110.4 vs 108.1 ms.  r02, not kept.)
 template <int L> struct PairUnroll { static constexpr int U = (L <= 20 && L % 5 == 0) ? 5 : Unroll<L>::U; };
