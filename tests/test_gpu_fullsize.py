@@ -127,3 +127,25 @@ def test_config5_3072_bit_100k_round_trip():
     idx = list(range(8)) + random.Random(5).sample(range(N), 56)
     want = O.encrypt_batch(pk_o, capi.array_to_ints(m[idx]), capi.array_to_ints(r[idx]))
     assert capi.array_to_ints(_host(ct)[idx]) == want
+
+
+def test_decrypt_across_launch_boundary(key):
+    """A decrypt of more than 2^17 ciphertexts runs as several launches of k_dec_pair (the per-unit window tables bound a
+    launch): 140 000 = one time-sliced launch of 131 072 + one of 8 928 with whole units.  Round trip over every row, the
+    rows either side of the boundary and the ragged end against the oracle."""
+    import torch
+    pk_o, sk_o, pk, sk = key
+    N = 140000
+    rng = np.random.Generator(np.random.PCG64(SEED + 9))
+    m = np.zeros((N, 64), dtype=np.uint32)
+    m[:, :2] = rng.integers(0, 1 << 32, size=(N, 2), dtype=np.uint64).astype(np.uint32)
+    r = rng.integers(0, 1 << 32, size=(N, 32), dtype=np.uint64).astype(np.uint32)
+    dm = _dev(m)
+    ct = torch.empty((N, 128), dtype=torch.int32, device="cuda:0")
+    out = torch.empty((N, 64), dtype=torch.int32, device="cuda:0")
+    pk.encrypt_dev(dm.data_ptr(), N, _dev(r).data_ptr(), 32, ct.data_ptr())
+    sk.decrypt_dev(ct.data_ptr(), N, out.data_ptr())
+    assert torch.equal(out, dm)
+    idx = [0, 131071, 131072, 131073, N - 33, N - 1]
+    cts = capi.array_to_ints(_host(ct[idx]))
+    assert capi.array_to_ints(_host(out[idx])) == O.decrypt_batch(sk_o, cts)
