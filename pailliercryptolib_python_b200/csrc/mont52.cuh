@@ -263,9 +263,11 @@ PHE_HD void mac_span(uint64_t (&acc)[L], const X& x, double y, uint64_t& hprev, 
 #ifndef PHE52_U
 #define PHE52_U 4
 #endif
-// L = 30 (one-lane pair engine of 3072-bit keys): 5 rows are 300 products = 27 KB of code, 3 rows 16 KB
+// L = 30 (one-lane pair engine of 3072-bit keys): 5 rows are 300 products = 27 KB of code, 3 rows 16 KB, 2 rows 11 KB.
+// With the branch-free row body (PHE52_GHOST) a back-edge is cheap and the smallest body wins at this size:
+// k_dec_pair<30> U = 1 415.9, U = 2 437.7, U = 3 444.2, U = 5 459.1 ms
 #ifndef PHE52_U_WIDE
-#define PHE52_U_WIDE 3
+#define PHE52_U_WIDE 1
 #endif
 template <int L> struct Unroll { static constexpr int U = (L > 24 && L % PHE52_U_WIDE == 0) ? PHE52_U_WIDE : (L % PHE52_U == 0) ? PHE52_U : (L % 5 == 0) ? 5 : (L % 4 == 0) ? 4 : (L % 3 == 0) ? 3 : (L % 2 == 0) ? 2 : 1; };
 
@@ -488,7 +490,10 @@ PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, con
 // same: 107.2 vs 107.0 ms.  r02, not kept.)
 // (Fetching the multiplier limb of a chunk's first row one chunk ahead -- ncu puts 3.5 % of the stall samples on the first
 // DFMA behind that LDS -- costs two registers across the back-edge and LOSES: 110.4 vs 108.1 ms.  r02, not kept.)
-template <int L> struct PairUnroll { static constexpr int U = (L <= 20 && L % 5 == 0) ? 5 : Unroll<L>::U; };
+#ifndef PHE52_U_PAIR
+#define PHE52_U_PAIR 5
+#endif
+template <int L> struct PairUnroll { static constexpr int U = (L <= 20 && L % PHE52_U_PAIR == 0) ? PHE52_U_PAIR : Unroll<L>::U; };
 
 template <int L, class PE>
 PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, const int64_t* e_in, int64_t* e_out,
