@@ -511,10 +511,13 @@ PHE_HD void pair_pass(double* r_out, const double (&a)[L], const double* b, cons
   uint64_t acc[L];
 #pragma unroll
   for (int j = 0; j < L; ++j) acc[j] = 0ull - bias_of(2 * (j + 1), 2 * j);
-  // L <= 20: M is subtracted whole around the first row (digit j sits in window column j of row 0) instead of digit by
-  // digit inside the rows: the same 3 instructions per digit, but only in the passes that have an M (r02: k_dec_pair<20>
-  // 114.0 -> 113.0 ms; k_dec_pair<30> 450.6 -> 462.5 ms, so that shape keeps the in-row form)
-  constexpr bool M_UPFRONT = (L <= 20);
+  // M is subtracted whole around the first row (digit j sits in window column j of row 0) instead of digit by digit inside
+  // the rows: the same 3 instructions per digit, but only in the passes that have an M (r02: k_dec_pair<20> 114.0 -> 113.0
+  // ms; k_dec_pair<30> lost with it at 3 rows per chunk, 450.6 -> 462.5 ms, and wins at 1 row per chunk, 416.6 -> 404.4 ms)
+#ifndef PHE_PAIR_MUP_MAXL
+#define PHE_PAIR_MUP_MAXL 64
+#endif
+  constexpr bool M_UPFRONT = (L <= PHE_PAIR_MUP_MAXL);
   constexpr bool GHOST = PHE52_GHOST != 0;
 
   uint64_t topA, q;
