@@ -376,6 +376,9 @@ PHE_HD void montmul(double (&r)[L], const double (&a)[L], const double* b, const
 //                    plain == true : the low half of the product (limb i = retired column i)
 //   plain          : q is forced to 0: r = floor((a b + E) / R), i.e. an ordinary 2K-limb product with cap as low half.
 // cap may alias ein (digit i + 1 of ein is read in the iteration that writes digit i of cap).
+// (Adding E whole before the first row, every lane its own L digits -- what pays in the one-lane engine -- loses here:
+// k_encrypt_npair<20,2> 15.62 -> 15.96 ms.  So do the branch-free last row, 15.82, and other unrolls, U = 5 15.94, U = 2
+// 16.69.  r02 A/B builds; the multi-lane product stays as it was at the start of the round.)
 // ------------------------------------------------------------------------------------------------
 template <int L, int TPI, class Env>
 PHE_HD void montmul_e(double (&r)[L], const double (&a)[L], const double* b, const double* n_entry, uint64_t n0inv,
