@@ -210,7 +210,8 @@ def _dec_pair_products(capi, sk):
     for b in pair:
         t, m_, s_ = _products_of_pair_program(b["prog"], L)
         tot, muls, sqrs = tot + t, muls + m_, sqrs + s_
-    return tot, "%d squares (2 passes) + %d multiplications (3 passes) of 2*%d^2 limb products per pass" % (sqrs, muls, L)
+    return tot, ("%d squares (2 passes) + %d multiplications (3 passes) of 2*%d^2 limb products per pass; the kernel also runs "
+                 "%d products by zero per pass (branch-free last row) that are NOT counted here" % (sqrs, muls, L, L))
 
 
 def _enc_npair_products(capi, pk):
